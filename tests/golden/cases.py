@@ -1,0 +1,115 @@
+"""Deterministic inputs shared by make_golden.py (reference side) and the tests
+(oracle / CUDA side).  numpy PCG64 streams only, so they regenerate bit-identically
+on any box.  Shapes follow the dataset tuple of
+/root/reference/LiDARGen/datasets/kitti360_im_8Batch.py:304 (real [B,2,H,W], mask,
+sky [B,1,H,W], toWorld/fromWorld [B,1,4,4] float64)."""
+import numpy as np
+import torch
+
+FULL_STRIDE = 487     # sample stride for the 64x1024 fixture
+
+
+def _rng(*seed):
+    return np.random.Generator(np.random.PCG64(list(seed)))
+
+
+def big_rows(H):
+    return int(50 * H // 28)
+
+
+def line_poses(B, A, step=5.0, yaw=0.01, lateral=0.3):
+    """B views in groups of A, each group a line of sensor poses along +x with a small yaw."""
+    to_world = np.zeros((B, 1, 4, 4), dtype=np.float64)
+    for b in range(B):
+        i = b % A
+        g = b // A
+        a = yaw * i + 0.05 * g
+        T = np.eye(4)
+        T[:3, :3] = [[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]]
+        T[:3, 3] = [step * (i + 1), lateral * i - 0.2 * g, 0.05 * i]
+        to_world[b, 0] = T
+    from_world = np.linalg.inv(to_world)
+    return torch.from_numpy(to_world), torch.from_numpy(from_world)
+
+
+def smooth_range_image(B, H, W, seed):
+    """log-range in [0,1]: d ~ 2..60 m, smoothed along rows; intensity U(0,0.5)."""
+    r = _rng(seed, 1)
+    d = r.uniform(2.0, 60.0, size=(B, H, W))
+    k = np.ones(5) / 5
+    d = np.apply_along_axis(lambda v: np.convolve(np.concatenate([v[-2:], v, v[:2]]), k, mode="valid"), 2, d)
+    depth = np.clip(np.log2(d + 1) / 6, 0, 1)
+    inten = r.uniform(0, 0.5, size=(B, H, W))
+    return torch.from_numpy(np.stack([depth, inten], 1).astype(np.float32))
+
+
+def small_multiview(kind="pose", B=4, A=2, H=16, W=64, seed=2024, outlier=False):
+    r = _rng(seed, 2)
+    refer = smooth_range_image(B, H, W, seed)
+    # sample: reference + noise, with a share of negative ranges to exercise the mirror path
+    x = refer + torch.from_numpy(r.normal(0, 0.15, size=refer.shape).astype(np.float32))
+    neg = torch.from_numpy(r.uniform(size=(B, H, W)) < 0.08)
+    x[:, 0] = torch.where(neg, -x[:, 0].abs() * 0.5, x[:, 0])
+    if outlier:
+        x[1, 0, 3, 5] = 200.0
+    mask = torch.from_numpy((r.uniform(size=(B, 1, H, W)) < 0.6).astype(np.int32)).repeat(1, 2, 1, 1).contiguous()
+    sky = torch.ones(B, 1, H, W, dtype=torch.bool)
+    if kind == "trans":        # the API allows False sky pixels even if the KITTI datasets never produce them
+        sky = torch.from_numpy(r.uniform(size=(B, 1, H, W)) < 0.9)
+    exist = torch.from_numpy(r.uniform(size=(A, H, W)) < 0.85)
+    case = dict(B=B, A=A, H=H, W=W, R=big_rows(H), x=x, refer=refer, mask=mask, sky=sky, exist=exist,
+                allowance=10, coef=0.25)
+    if kind == "pose":
+        case["toWorld"], case["fromWorld"] = line_poses(B, A, step=1.5, yaw=0.03)
+    else:
+        case["mods"] = torch.tensor([[0, 0, 0], [5, -5, 0], [-5, -5, 0], [0, 5, 0], [-10, 10, 0], [10, 10, 0],
+                                     [-10, 0, 0]], dtype=torch.int64)
+    return case
+
+
+def full_multiview(B=3, A=3, H=64, W=1024, seed=4242):
+    r = _rng(seed, 3)
+    refer = smooth_range_image(B, H, W, seed)
+    x = refer + torch.from_numpy(r.normal(0, 0.05, size=refer.shape).astype(np.float32))
+    neg = torch.from_numpy(r.uniform(size=(B, H, W)) < 0.03)
+    x[:, 0] = torch.where(neg, -x[:, 0].abs() * 0.5, x[:, 0])
+    mask = torch.from_numpy((r.uniform(size=(B, 1, H, W)) < 0.6).astype(np.int32)).repeat(1, 2, 1, 1).contiguous()
+    sky = torch.ones(B, 1, H, W, dtype=torch.bool)
+    exist = torch.from_numpy(r.uniform(size=(1, H, W)) < 0.7).repeat(A, 1, 1).contiguous()
+    to_world, from_world = line_poses(B, A, step=5.0, yaw=0.01)
+    return dict(B=B, A=A, H=H, W=W, R=big_rows(H), x=x, refer=refer, mask=mask, sky=sky, exist=exist,
+                allowance=10, coef=0.01, toWorld=to_world, fromWorld=from_world)
+
+
+def short_sigmas():
+    """4-level schedule spanning sigma>1 (sigmaMod=sigma) and sigma<=1 (sigmaMod=1); numpy float32
+    like the runner's get_sigmas(config).cpu().numpy() (ncsn_runner_kitti_simultaneous.py:491-492)."""
+    return np.array([4.0, 1.3, 0.2, 0.01], dtype=np.float32)
+
+
+def fake_score(sigmas):
+    """cheap deterministic stand-in for the score net: pulls towards a smooth field."""
+    sig = torch.from_numpy(np.asarray(sigmas, dtype=np.float32))
+
+    def score(x, y):
+        H, W = x.shape[-2:]
+        target = 0.5 + 0.25 * torch.sin(torch.arange(W, dtype=torch.float32, device=x.device) * (6.283185 / W)).view(1, 1, 1, W)
+        return -(x - target) / (sig.to(x.device)[y].view(-1, 1, 1, 1) ** 2) * 0.05
+    return score
+
+
+def noise_list(shape, n, seed):
+    r = _rng(seed, 4)
+    return [torch.from_numpy(r.standard_normal(size=tuple(shape)).astype(np.float32)) for _ in range(n)]
+
+
+def scorenet_input(H, W, B=2, seed=99):
+    r = _rng(seed, 5)
+    x = torch.from_numpy(r.uniform(0, 1, size=(B, 2, H, W)).astype(np.float32))
+    y = torch.tensor([3, 200][:B], dtype=torch.int64)
+    return x, y
+
+
+def subsample_tap(t):
+    """[B,C,H,W] -> strided sample (every 16th channel, 4th row, 8th column)."""
+    return t[:, ::16, ::4, ::8].contiguous()
