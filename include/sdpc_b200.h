@@ -1,0 +1,189 @@
+/*
+ * sdpc_b200.h - C ABI of the B200-native simultaneous multi-view Langevin sampling step.
+ *
+ * The reference (Ryan-Faulkner/Simultaneous-Diffusion-for-Pointclouds) has no FFI: its
+ * hot path sits behind two Python call sites.  This header is the boundary a
+ * maintainer binds instead (ctypes stub in INTEGRATION.md).  Each entry point cites the
+ * reference code it replaces.
+ *
+ * Conventions
+ *   - every function returns an int status (0 = SDPC_OK, <0 = error); nothing throws, nothing
+ *     synchronises the device implicitly; sdpc_last_error() returns a thread-local message.
+ *   - unless a parameter says "host", pointers are CUDA device pointers owned by the caller.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - tensors are dense, row-major, in the reference's own layouts (NCHW float32 images).
+ *   - a handle is not re-entrant: one forward at a time per handle.
+ */
+#ifndef SDPC_B200_H
+#define SDPC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDPC_ABI_VERSION 1
+
+enum sdpc_status {
+  SDPC_OK = 0,
+  SDPC_ERR_ARG = -1,        /* bad argument (null pointer, unsupported shape, ...) */
+  SDPC_ERR_CUDA = -2,       /* a CUDA runtime / driver call failed */
+  SDPC_ERR_STATE = -3,      /* call order violated (e.g. forward before finalize) */
+  SDPC_ERR_WORKSPACE = -4,  /* workspace pointer null or too small */
+  SDPC_ERR_NAME = -5,       /* unknown parameter name / wrong shape for that name */
+  SDPC_ERR_UNSUPPORTED = -6 /* device is not sm_100 or configuration not supported */
+};
+
+/* Arithmetic of the score network's 3x3 convolutions (the 75 conv2d of ncsnv2.py:420-518). */
+enum sdpc_precision {
+  SDPC_PREC_FP32 = 0, /* CUDA-core fp32 FMA, strict-parity arm (matches CPU fp32 to ~1e-5) */
+  SDPC_PREC_TF32 = 1, /* tcgen05 kind::tf32, fp32 activations rounded to tf32, fp32 accumulate */
+  SDPC_PREC_BF16 = 2  /* tcgen05 kind::f16 (bf16 operands), fp32 accumulate in TMEM */
+};
+
+int sdpc_abi_version(void);
+const char* sdpc_last_error(void);
+/* Name of the kernels this build contains, e.g. "sm_100a". */
+const char* sdpc_build_arch(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Score network: NCSN_LiDAR_small.forward(x, y)        LiDARGen/models/ncsnv2.py:484-518
+ * (constructor / parameter inventory                    LiDARGen/models/ncsnv2.py:420-477)
+ * ---------------------------------------------------------------------------------------- */
+typedef struct sdpc_score sdpc_score_t;
+
+typedef struct sdpc_score_config {
+  int32_t channels;    /* config.data.channels (2: log-range, intensity) */
+  int32_t height;      /* config.data.image_size  (64) */
+  int32_t width;       /* config.data.image_width (1024) */
+  int32_t ngf;         /* config.model.ngf (128) */
+  int32_t num_classes; /* config.model.num_classes = length of the `sigmas` buffer */
+  int32_t precision;   /* enum sdpc_precision */
+  int32_t max_views;   /* largest batch a forward will see (sizes the activation arena) */
+  int32_t reserved;
+} sdpc_score_config;
+
+int sdpc_score_create(const sdpc_score_config* cfg, sdpc_score_t** out);
+int sdpc_score_destroy(sdpc_score_t* h);
+
+/* Number of state_dict entries the handle expects (153 parameters + the `sigmas` buffer). */
+int sdpc_score_param_count(const sdpc_score_t* h);
+/* i-th expected entry: its reference state_dict key and shape (ndim <= 4). */
+int sdpc_score_param_info(const sdpc_score_t* h, int i, const char** name, int64_t shape[4], int* ndim);
+
+/* Load one float32 tensor by its reference state_dict key (checkpoint layout of
+ * runners/ncsn_runner_kitti_simultaneous.py:472-489 after stripping "module.").
+ * `data` may be a host or a device pointer (on_device = 0/1). */
+int sdpc_score_load_param(sdpc_score_t* h, const char* name, const float* data,
+                          const int64_t* shape, int ndim, int on_device, void* stream);
+/* Repack the loaded weights into the kernels' layouts; fails if an entry is missing. */
+int sdpc_score_finalize(sdpc_score_t* h, void* stream);
+
+size_t sdpc_score_workspace_bytes(const sdpc_score_t* h, int n_views);
+
+/* out[b] = s(x[b], sigma[labels[b]]);  x,out: float32 [n_views, channels, H, W] (NCHW);
+ * labels: int64 [n_views].  Replaces `scorenet(x_mod, labels)` at KITTISampling.py:137,505 and
+ * models/__init__.py:240,594,1401,1431. */
+int sdpc_score_forward(sdpc_score_t* h, const float* x, const int64_t* labels, float* out,
+                       int n_views, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Test hook: after a forward, copy a named intermediate (e.g. "res1.0", "refine4") as float32
+ * NCHW into `out` (device, capacity in elements). Writes its [C,H,W] to chw. */
+int sdpc_score_read_tap(sdpc_score_t* h, const char* tap, float* out, size_t capacity,
+                        int n_views, int chw[3], void* stream);
+/* Kernels launched by the most recent forward (for bench.py's gpu_launches). */
+int sdpc_score_last_launch_count(const sdpc_score_t* h);
+/* CUDA-event time (ms) of the convolution kernels alone is measured by bench.py itself; this
+ * returns the algorithmic FLOPs (2*M*N*K over all convolutions) of one view-forward. */
+double sdpc_score_flops_per_view(const sdpc_score_t* h);
+
+/* ------------------------------------------------------------------------------------------
+ * Langevin update + cross-view consistency step
+ *   a-4  KITTISampling.py:137-490   (pose matrices)         variant = SDPC_VARIANT_POSE
+ *   a-5  models/__init__.py:240-582 (translations)          variant = SDPC_VARIANT_TRANSLATION
+ *   a-6  models/__init__.py:1401-1416 (update only)         share = 0
+ * ---------------------------------------------------------------------------------------- */
+enum sdpc_variant { SDPC_VARIANT_POSE = 0, SDPC_VARIANT_TRANSLATION = 1 };
+
+typedef struct sdpc_step_params {
+  int32_t n_views;       /* B: views in x (all groups) */
+  int32_t group_size;    /* A = actualBatchSize; B % A == 0 */
+  int32_t height;        /* H */
+  int32_t width;         /* W */
+  int32_t big_rows;      /* R = bigRowCount (KITTISampling.py:68) */
+  int32_t variant;       /* enum sdpc_variant */
+  int32_t share;         /* c >= minStepToShare (KITTISampling.py:160) */
+  int32_t nan_to_num;    /* zero NaN / clamp inf of the score (KITTISampling.py:138); a-6: 0 */
+  int32_t sky_filter;    /* a-5: drop candidates whose SOURCE pixel has sky == 0 (__init__.py:352) */
+  int32_t tgt_first;     /* first target view this call resolves (multi-GPU sharding), else 0 */
+  int32_t tgt_count;     /* number of target views, else n_views */
+  int32_t reserved;
+  float step_size;       /* eps: float32 value of step_lr*(sigma/sigmas[-1])**2 (KITTISampling.py:135) */
+  float noise_scale;     /* float32 value of np.sqrt(step_size*2) (KITTISampling.py:156) */
+  float grad_ref;        /* step_refer */
+  float corr_coef;       /* correlation_coefficient */
+  float sigma_mod;       /* sigmaMod (KITTISampling.py:117-119) */
+  float min_depth_thr;   /* float32 log-range threshold (KITTISampling.py:273-275); < 0 disables */
+  double allowance;      /* controlled-average allowance in metres (KITTISampling.py:381); < 0: plain average */
+  double h_min, dh;      /* horizontalMin, horizontalAngles (KITTISampling.py:64,66) */
+  double big_row_min, dv;/* bigRowMin, verticalAngles     (KITTISampling.py:65,71) */
+} sdpc_step_params;
+
+typedef struct sdpc_step_buffers {
+  float* x;                 /* in/out [B,2,H,W]: x_mod */
+  const float* grad;        /* [B,2,H,W] score (may be NULL when step_size == 0) */
+  const float* noise;       /* [B,2,H,W] z ~ N(0,1), drawn by the caller (torch.randn_like) */
+  const float* refer;       /* [B,2,H,W] refer_image */
+  const int32_t* mask;      /* [B,2,H,W] refer_mask (int32 0/1) */
+  const uint8_t* sky;       /* [B,H,W]   sky (bool) */
+  const uint8_t* exist;     /* [A,H,W]   existMask[:A] (bool) */
+  const double* to_world;   /* [B,16] row-major 4x4 (pose variant) */
+  const double* from_world; /* [B,16] */
+  const float* origins;     /* [A,3] originList[:A,:,0,0] (translation variant) */
+  const double* cos_az;     /* [W] cos(azimuth)   (KITTISampling.py:101,176) */
+  const double* sin_az;     /* [W] */
+  const double* cos_el;     /* [H] cos(elevation) (KITTISampling.py:102,176) */
+  const double* sin_el;     /* [H] */
+  float* grad_likelihood;   /* optional out [B,2,H,W]: -mask*(x_before-refer) (KITTISampling.py:144) */
+  float* new_images;        /* optional out [B,2,H,W]: newImages (KITTISampling.py:415) */
+  int32_t* too_high;        /* optional out [1]: the tooHigh gate (KITTISampling.py:162) */
+  /* optional debug outputs for parity tests */
+  int32_t* dbg_row;         /* [B, A*H*W] row in the R-row grid, per (target, source point) */
+  int32_t* dbg_col;         /* [B, A*H*W] */
+  uint8_t* dbg_valid;       /* [B, A*H*W] */
+  int32_t* dbg_cnt;         /* [B,R,W] candidates per pixel */
+  int32_t* dbg_winner;      /* [B,R,W] source point id (a*H*W + r*W + c) of the nearest candidate, -1 if empty */
+  double* dbg_min_d;        /* [B,R,W] its log-range */
+} sdpc_step_buffers;
+
+size_t sdpc_step_workspace_bytes(int n_views, int height, int width, int big_rows);
+
+/* x <- x + eps*nan_to_num(grad) + rho*(-mask*(x-refer)) + noise_scale*noise  (KITTISampling.py:137-156);
+ * also leaves max|x[:,0]| of the updated sample in the workspace for the tooHigh gate. */
+int sdpc_langevin_update(const sdpc_step_params* p, const sdpc_step_buffers* b,
+                         void* workspace, size_t workspace_bytes, void* stream);
+/* Optional hook between update and share for sharded runs: fold other ranks' max|x0| in. */
+int sdpc_step_merge_max(void* workspace, const float* other_max, int n, void* stream);
+int sdpc_step_read_max(void* workspace, float* out_max, void* stream);
+/* Cross-view block on the updated sample (KITTISampling.py:160-490): un-project, pose transform,
+ * re-project, z-buffer (count, sums, nearest), fusion, crop/mirror, correction. */
+int sdpc_crossview_share(const sdpc_step_params* p, const sdpc_step_buffers* b,
+                         void* workspace, size_t workspace_bytes, void* stream);
+/* update followed by share (when p->share != 0) on one stream. */
+int sdpc_langevin_reproject_step(const sdpc_step_params* p, const sdpc_step_buffers* b,
+                                 void* workspace, size_t workspace_bytes, void* stream);
+
+/* Same step with HOST buffers (pinned or pageable): copies x, grad/noise in, runs the step,
+ * copies x (and new_images when non-NULL) back.  Static inputs (refer, mask, sky, exist, poses,
+ * LUTs) stay device pointers in `b`.  Used by bench.py's e2e leg. */
+int sdpc_langevin_reproject_step_host(const sdpc_step_params* p, const sdpc_step_buffers* b,
+                                      float* x_host, const float* grad_host, const float* noise_host,
+                                      float* new_images_host, void* workspace, size_t workspace_bytes,
+                                      void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDPC_B200_H */

@@ -1,0 +1,20 @@
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.h"
+
+namespace sdpc {
+static thread_local char g_err[512] = "";
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+}  // namespace sdpc
+
+extern "C" int sdpc_abi_version(void) { return SDPC_ABI_VERSION; }
+extern "C" const char* sdpc_last_error(void) { return sdpc::g_err; }
+extern "C" const char* sdpc_build_arch(void) { return "sm_100a"; }

@@ -1,0 +1,135 @@
+// TEST INFRASTRUCTURE: serial host emulation of crossview.cu's kernels, built with g++ from the
+// same per-element header (csrc/crossview_core.h).  Lets the CPU test-suite check the kernels'
+// arithmetic and indexing against the oracle before any GPU time is spent.  Never shipped.
+#include <algorithm>
+#include <cstring>
+#include <limits>
+#include <vector>
+
+#include "../../include/sdpc_b200.h"
+#include "../../simultaneous-diffusion-for-pointclouds_b200/csrc/crossview_core.h"
+
+using namespace sdpc;
+
+extern "C" int emul_langevin_reproject_step(const sdpc_step_params* p, const sdpc_step_buffers* b) {
+  const int B = p->n_views, A = p->group_size, H = p->height, W = p->width, R = p->big_rows;
+  const int HW = H * W;
+  const int t0 = p->tgt_first, tn = p->tgt_count ? p->tgt_count : B;
+  // update
+  float mx = 0.0f;
+  bool has_nan = false;
+  for (int v = t0; v < t0 + tn; ++v)
+    for (int ch = 0; ch < 2; ++ch)
+      for (int q = 0; q < HW; ++q) {
+        size_t e = ((size_t)v * 2 + ch) * HW + q;
+        float g = b->grad ? b->grad[e] : 0.0f;
+        if (p->nan_to_num) g = nan_to_num(g);
+        float z = b->noise ? b->noise[e] : 0.0f;
+        float gl;
+        float o = langevin_value(b->x[e], g, b->refer[e], b->mask[e], z, p->step_size, p->grad_ref, p->noise_scale, &gl);
+        b->x[e] = o;
+        if (b->grad_likelihood) b->grad_likelihood[e] = gl;
+        if (ch == 0) { if (o != o) has_nan = true; mx = std::max(mx, fabsf(o)); }
+      }
+  if (has_nan) mx = std::numeric_limits<float>::quiet_NaN();
+  if (!p->share) return 0;
+  GeoConsts geo{p->h_min, p->dh, p->big_row_min, p->dv, H, W, R};
+  const size_t cells = (size_t)B * R * W;
+  std::vector<unsigned long long> zmin(cells, ~0ull);
+  std::vector<unsigned> winner(cells, ~0u), cnt(cells, 0u);
+  std::vector<long long> sum_d(cells, 0), sum_i(cells, 0);
+  for (int pass = 0; pass < 2; ++pass)
+    for (int g = 0; g < B / A; ++g)
+      for (int sa = 0; sa < A; ++sa) {
+        const int bsrc = g * A + sa;
+        const int t_lo = std::max(g * A, t0), t_hi = std::min((g + 1) * A, t0 + tn);
+        for (int q = 0; q < HW; ++q) {
+          bool src_ok = b->exist[(size_t)sa * HW + q] != 0;
+          if (p->sky_filter) src_ok = src_ok && b->sky[(size_t)bsrc * HW + q] != 0;
+          const int r = q / W, c = q % W;
+          const float x0 = b->x[((size_t)bsrc * 2) * HW + q], x1 = b->x[((size_t)bsrc * 2 + 1) * HW + q];
+          const float dist = decode_range(x0, p->sigma_mod);
+          double P[3];
+          unproject(dist, b->cos_az[c], b->sin_az[c], b->cos_el[r], b->sin_el[r], P);
+          double wx, wy, wz, ww = 1.0;
+          if (p->variant == SDPC_VARIANT_POSE) {
+            const double* m = b->to_world + (size_t)bsrc * 16;
+            wx = dot4(m, P[0], P[1], P[2], 1.0); wy = dot4(m + 4, P[0], P[1], P[2], 1.0);
+            wz = dot4(m + 8, P[0], P[1], P[2], 1.0); ww = dot4(m + 12, P[0], P[1], P[2], 1.0);
+          } else {
+            wx = P[0] + (double)b->origins[sa * 3]; wy = P[1] + (double)b->origins[sa * 3 + 1];
+            wz = P[2] + (double)b->origins[sa * 3 + 2];
+          }
+          const unsigned src_id = (unsigned)(sa * HW + q);
+          for (int t = t_lo; t < t_hi; ++t) {
+            double qx, qy, qz;
+            if (p->variant == SDPC_VARIANT_POSE) {
+              const double* m = b->from_world + (size_t)t * 16;
+              qx = dot4(m, wx, wy, wz, ww); qy = dot4(m + 4, wx, wy, wz, ww); qz = dot4(m + 8, wx, wy, wz, ww);
+            } else {
+              const int ta = t - g * A;
+              qx = wx - (double)b->origins[ta * 3]; qy = wy - (double)b->origins[ta * 3 + 1];
+              qz = wz - (double)b->origins[ta * 3 + 2];
+            }
+            Candidate cd = reproject(qx, qy, qz, p->sigma_mod, geo);
+            bool ok = src_ok && in_grid(cd, geo);
+            if (p->min_depth_thr >= 0.0f) ok = ok && cd.nd > (double)p->min_depth_thr;
+            if (pass == 0 && b->dbg_row) {
+              size_t k = (size_t)t * A * HW + src_id;
+              b->dbg_row[k] = cd.row; b->dbg_col[k] = cd.col; b->dbg_valid[k] = ok;
+            }
+            if (!ok) continue;
+            size_t cell = ((size_t)t * R + cd.row) * W + cd.col;
+            unsigned long long key;
+            memcpy(&key, &cd.nd, 8);
+            if (pass == 0) {
+              zmin[cell] = std::min(zmin[cell], key);
+              cnt[cell]++;
+              sum_d[cell] += depth_to_fixed(cd.nd);
+              sum_i[cell] += inten_to_fixed(x1);
+            } else if (zmin[cell] == key) {
+              winner[cell] = std::min(winner[cell], src_id);
+            }
+          }
+        }
+      }
+  for (size_t k = 0; k < cells; ++k) {
+    if (b->dbg_cnt) b->dbg_cnt[k] = (int)cnt[k];
+    if (b->dbg_winner) b->dbg_winner[k] = cnt[k] ? (int)winner[k] : -1;
+    if (b->dbg_min_d) { double d = 0; if (cnt[k]) memcpy(&d, &zmin[k], 8); b->dbg_min_d[k] = d; }
+  }
+  // resolve
+  std::vector<float> img((size_t)B * 2 * HW, 0.0f);
+  std::vector<uint8_t> sm((size_t)B * HW, 0);
+  for (int t = t0; t < t0 + tn; ++t)
+    for (int q = 0; q < HW; ++q) {
+      const int r = q / W, c = q % W;
+      const size_t i0 = ((size_t)t * 2) * HW + q, i1 = i0 + HW;
+      const bool neg = b->x[i0] < 0.0f;
+      int gr = neg ? (H - 1 - r) : (r + R - H);
+      int gc = neg ? ((c - W / 2 + W) % W) : c;
+      size_t cell = ((size_t)t * R + gr) * W + gc;
+      double min_d = 0; float min_i = 0;
+      if (cnt[cell]) {
+        memcpy(&min_d, &zmin[cell], 8);
+        unsigned w = winner[cell];
+        int wa = w / HW, wp = w % HW;
+        min_i = b->x[((size_t)((t / A) * A + wa) * 2 + 1) * HW + wp];
+      }
+      Fused f = fuse_cell(cnt[cell], sum_d[cell], sum_i[cell], min_d, min_i, p->sigma_mod, p->allowance);
+      img[i0] = (float)(neg ? f.depth * -1.0 : f.depth);
+      img[i1] = f.inten;
+      sm[(size_t)t * HW + q] = f.filled && b->exist[q] && b->sky[(size_t)t * HW + q];
+    }
+  const bool too_high = (mx * 6.0f) / p->sigma_mod > 50.0f;
+  if (b->too_high) *b->too_high = too_high;
+  for (int t = t0; t < t0 + tn; ++t)
+    for (int ch = 0; ch < 2; ++ch)
+      for (int q = 0; q < HW; ++q) {
+        size_t e = ((size_t)t * 2 + ch) * HW + q;
+        float corr = too_high ? 0.0f : (float)(-(int)sm[(size_t)t * HW + q] * (b->mask[e] == 0 ? 1 : 0)) * (b->x[e] - img[e]);
+        if (b->new_images) b->new_images[e] = img[e];
+        b->x[e] = b->x[e] + p->corr_coef * corr;
+      }
+  return 0;
+}
