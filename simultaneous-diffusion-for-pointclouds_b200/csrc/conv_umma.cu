@@ -1,0 +1,246 @@
+// Implicit-GEMM 3x3 / 1x1 convolution on the 5th-generation tensor cores (tcgen05 + TMEM),
+// operands staged by TMA.  This is the kernel that carries ~99% of the score network's FLOPs
+// (NCSN_LiDAR_small: LiDARGen/models/ncsnv2.py:484-518, conv definitions layers.py:37-60).
+//
+// GEMM view:  D[m, co] = sum_{tap, ci} X[pixel(m) + offset(tap), ci] * Wt[tap, co, ci]
+//   M tile : 128 output pixels = a BH x BW box of one image (BW = min(W,128))
+//   N tile : all Cout (128 or 256) -> the activation tile is fetched once per pixel tile
+//   K loop : taps x (Cin / BK), BK = 128 bytes of channels (64 bf16 / 32 tf32)
+// A operand: the input activation is an NHWC tensor with a materialised halo (circular wrap or
+//   zeros), so every shifted tap is an in-bounds 4-D TMA box {BK, BW, BH, 1}; the box lands in
+//   shared memory as 128 rows x 128 B, 128B-swizzled = the canonical K-major UMMA layout.
+// B operand: weights repacked to [tap][Cout][Cin] (K-major), 3-D TMA box {BK, Cout, 1}.
+// Accumulator: fp32 in TMEM, double buffered (2 x Cout columns) so the epilogue of tile i
+//   overlaps the MMAs of tile i+1.  Persistent CTAs, one per SM, static round-robin tiles.
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane) + TMEM allocator,
+//   warps 2-5 = epilogue (tcgen05.ld -> bias / residual / ELU / stores, see score_types.cuh).
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "common.h"
+#include "conv_umma.h"
+#include "score_types.cuh"
+#include "sm100_prims.cuh"
+
+namespace sdpc {
+using namespace sm100;
+
+constexpr int kTileM = 128;
+constexpr int kRowBytes = 128;                  // bytes of K per smem row (one swizzle span)
+constexpr int kABytes = kTileM * kRowBytes;     // 16 KiB
+constexpr int kThreads = 192;
+constexpr int kSmemBudget = 200 * 1024;
+
+template <int N_TILE>
+struct UmmaCfg {
+  static constexpr int kBBytes = N_TILE * kRowBytes;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = kSmemBudget / kStageBytes;          // 4 (N=256) / 6 (N=128)
+  static constexpr int kTmemCols = 2 * N_TILE;                       // 512 / 256
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <typename T, int N_TILE>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const ConvGeom g, const EpiParams e) {
+  using Cfg = UmmaCfg<N_TILE>;
+  constexpr bool kTf32 = sizeof(T) == 4;
+  constexpr int kBK = kRowBytes / (int)sizeof(T);     // channels per k-block: 64 bf16 / 32 tf32
+  constexpr int kUmmaK = 32 / (int)sizeof(T);         // 16 / 8 -> 32 bytes per MMA along K
+  constexpr int kMmasPerStage = kBK / kUmmaK;         // 4
+  constexpr uint32_t kIdesc = umma_idesc(kTf32 ? 2u : 1u, kTileM, N_TILE);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* full_bar = bars;                         // [kStages]  TMA -> MMA
+  uint64_t* empty_bar = bars + Cfg::kStages;         // [kStages]  MMA -> TMA
+  uint64_t* acc_full = bars + 2 * Cfg::kStages;      // [2]        MMA -> epilogue
+  uint64_t* acc_empty = acc_full + 2;                // [2]        epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_b);
+    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int k_chunks = g.Cin / kBK;
+  const int k_iters = g.taps * k_chunks;
+  const int tiles_per_img = g.tiles_w * g.tiles_h;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+        const int n = tile / tiles_per_img;
+        const int rem = tile - n * tiles_per_img;
+        const int h0 = (rem / g.tiles_w) * g.BH;
+        const int w0 = (rem % g.tiles_w) * g.BW;
+        for (int tap = 0; tap < g.taps; ++tap) {
+          const int dy = (g.taps == 9) ? (tap / 3 - 1) * g.dil : 0;
+          const int dx = (g.taps == 9) ? (tap % 3 - 1) * g.dil : 0;
+          for (int kc = 0; kc < k_chunks; ++kc) {
+            mbar_wait(empty_bar + stage, phase ^ 1);
+            uint8_t* sa = smem + stage * Cfg::kStageBytes;
+            uint8_t* sb = sa + kABytes;
+            mbar_arrive_expect_tx(full_bar + stage, Cfg::kStageBytes);
+            tma_load_4d(sa, &tmap_a, full_bar + stage, kc * kBK, w0 + g.in_pad + dx, h0 + g.in_pad + dy, n);
+            tma_load_3d(sb, &tmap_b, full_bar + stage, kc * kBK, 0, tap);
+            if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int local = 0;
+      for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++local) {
+        const int ab = local & 1;
+        const uint32_t acc_phase = (local >> 1) & 1;
+        mbar_wait(acc_empty + ab, acc_phase ^ 1);            // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + ab * N_TILE;
+        for (int k = 0; k < k_iters; ++k) {
+          mbar_wait(full_bar + stage, phase);                // TMA bytes have landed
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint64_t da = umma_desc_sw128_kmajor(sa);
+          const uint64_t db = umma_desc_sw128_kmajor(sa + kABytes);
+#pragma unroll
+          for (int j = 0; j < kMmasPerStage; ++j) {
+            // advance 32 bytes along K inside the swizzle span: +2 in the (addr >> 4) field
+            umma_ss<kTf32>(d_tmem, da + (uint64_t)(2 * j), db + (uint64_t)(2 * j), kIdesc, (k | j) != 0);
+          }
+          umma_commit(empty_bar + stage);                    // frees the smem slot when the MMAs retire
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(acc_full + ab);                          // accumulator complete
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (warps 2..5)
+    const int quad = warp & 3;                               // TMEM lane quadrant this warp may read
+    const int m = quad * 32 + lane;                          // row of the tile = pixel
+    int local = 0;
+    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++local) {
+      const int ab = local & 1;
+      const uint32_t acc_phase = (local >> 1) & 1;
+      const int n = tile / tiles_per_img;
+      const int rem = tile - n * tiles_per_img;
+      const int h = (rem / g.tiles_w) * g.BH + m / g.BW;
+      const int w = (rem % g.tiles_w) * g.BW + m % g.BW;
+      mbar_wait(acc_full + ab, acc_phase);
+      __syncwarp();
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + ab * N_TILE;
+#pragma unroll 1
+      for (int c0 = 0; c0 < N_TILE; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(t_addr + c0, r);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+        epi_store<T, 32>(e, g, n, h, w, c0, v);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty + ab);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+int make_tmap(CUtensorMap* out, void* base, int elem_bytes, int rank, const uint64_t* dims, const uint32_t* box) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return set_error(SDPC_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t gdim[5], gstride[5];
+  cuuint32_t bdim[5], estr[5];
+  uint64_t stride = (uint64_t)elem_bytes;
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bdim[i] = box[i];
+    estr[i] = 1;
+    stride *= dims[i];
+    if (i < rank - 1) gstride[i] = stride;       // byte stride of dimension i+1
+  }
+  CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  CUresult r = enc(out, dt, (cuuint32_t)rank, base, gdim, gstride, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(SDPC_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return SDPC_OK;
+}
+
+template <typename T, int N_TILE>
+static int launch_t(const UmmaConvLaunch& L, cudaStream_t stream) {
+  using Cfg = UmmaCfg<N_TILE>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SDPC_CUDA(cudaFuncSetAttribute(conv_umma_kernel<T, N_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  int grid = L.geom.num_tiles < L.num_sms ? L.geom.num_tiles : L.num_sms;
+  conv_umma_kernel<T, N_TILE><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(L.tmap_a, L.tmap_b, L.geom, L.epi);
+  SDPC_CUDA(cudaGetLastError());
+  return SDPC_OK;
+}
+
+int conv_umma_launch(const UmmaConvLaunch& L, cudaStream_t stream) {
+  const ConvGeom& g = L.geom;
+  const int bk = 128 / L.elem_bytes;
+  if (g.BW * g.BH != kTileM || g.Cin % bk != 0 || (g.Cout != 128 && g.Cout != 256))
+    return set_error(SDPC_ERR_UNSUPPORTED, "conv_umma: unsupported shape Cin=%d Cout=%d tile=%dx%d", g.Cin, g.Cout,
+                     g.BH, g.BW);
+  if (L.elem_bytes == 2) {
+    return g.Cout == 256 ? launch_t<__nv_bfloat16, 256>(L, stream) : launch_t<__nv_bfloat16, 128>(L, stream);
+  }
+  return g.Cout == 256 ? launch_t<float, 256>(L, stream) : launch_t<float, 128>(L, stream);
+}
+
+}  // namespace sdpc

@@ -1,0 +1,24 @@
+// Host-side launch interface of the tcgen05 implicit-GEMM convolution (conv_umma.cu).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "score_types.cuh"
+
+namespace sdpc {
+
+struct UmmaConvLaunch {
+  CUtensorMap tmap_a;   // input operand  {C, W+2p, H+2p, N}, box {BK, BW, BH, 1}, 128B swizzle
+  CUtensorMap tmap_b;   // weights        {Cin, Cout, taps}, box {BK, Cout, 1}
+  ConvGeom geom;
+  EpiParams epi;
+  int elem_bytes;       // 2 = bf16 (kind::f16), 4 = tf32 (kind::tf32)
+  int num_sms;
+};
+
+// rank-`rank` tiled tensor map with 128-byte swizzle; dims/box innermost first.
+int make_tmap(CUtensorMap* out, void* base, int elem_bytes, int rank, const uint64_t* dims, const uint32_t* box);
+int conv_umma_launch(const UmmaConvLaunch& L, cudaStream_t stream);
+
+}  // namespace sdpc

@@ -268,7 +268,6 @@ __global__ void __launch_bounds__(256) resolve_kernel(ResolveArgs a) {
   const size_t i0 = ((size_t)t * 2) * HW + p;
   const size_t i1 = i0 + HW;
   const float x0 = a.x[i0];
-  const float x1 = a.x[i1];
   const bool neg = x0 < 0.0f;
   // crop rows [R-H, R); negative ranges read the point-mirrored cell (KITTISampling.py:401-403)
   int gr = neg ? (H - 1 - r) : (r + R - H);

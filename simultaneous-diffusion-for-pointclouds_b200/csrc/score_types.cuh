@@ -1,0 +1,113 @@
+// Shared types of the score-network kernels: convolution geometry, fused epilogue.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sdpc {
+
+// All activations are NHWC.  "raw" tensors are fp32 without halo; "operand" tensors carry a
+// halo of `pad` pixels on every side of H and W (circular wrap or zeros, decided by their
+// producer) so that a shifted 3x3 tap is always an in-bounds box for TMA.
+struct ConvGeom {
+  int N, H, W;        // output (= input) spatial size, batch
+  int Cin, Cout;
+  int taps;           // 9 (3x3) or 1 (1x1)
+  int dil;            // dilation of the 3x3
+  int in_pad;         // halo of the input operand (>= dil for 3x3)
+  int BW, BH;         // pixel tile: BH rows x BW columns, BW*BH == tile M
+  int tiles_w, tiles_h, num_tiles;
+};
+
+// Fused epilogue of every convolution (SIMT and tcgen05 kernels share it).
+struct EpiParams {
+  const float* bias;      // [Cout] or null
+  const float* residual;  // fp32 raw [N,H,W,Cout] added after bias, or null
+  float* out_raw;         // fp32 raw, value after bias + residual, or null
+  float* out_acc;         // fp32 raw, value after bias only (CRP path), or null
+  void* out_op;           // operand (T) with halo `op_pad`, value = act(after bias+residual), or null
+  int op_pad;
+  int op_elu;             // 1: ELU before the operand store
+  int op_tf32;            // 1: round the fp32 operand to tf32 (rna)
+};
+
+__device__ __forceinline__ float elu1(float v) { return v > 0.0f ? v : expm1f(v); }
+
+__device__ __forceinline__ float round_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+
+template <typename T>
+__device__ __forceinline__ void store_op4(T* dst, const float* v, bool tf32);
+template <>
+__device__ __forceinline__ void store_op4<float>(float* dst, const float* v, bool tf32) {
+  float4 o = tf32 ? make_float4(round_tf32(v[0]), round_tf32(v[1]), round_tf32(v[2]), round_tf32(v[3]))
+                  : make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(dst) = o;
+}
+template <>
+__device__ __forceinline__ void store_op4<__nv_bfloat16>(__nv_bfloat16* dst, const float* v, bool) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]);
+  __nv_bfloat162 b = __floats2bfloat162_rn(v[2], v[3]);
+  uint2 o;
+  o.x = *reinterpret_cast<uint32_t*>(&a);
+  o.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(dst) = o;
+}
+
+// Store NV (multiple of 4) consecutive output channels [c0, c0+NV) of pixel (n,h,w).
+template <typename T, int NV>
+__device__ __forceinline__ void epi_store(const EpiParams& e, const ConvGeom& g, int n, int h, int w, int c0,
+                                          float* v) {
+  const size_t pix = ((size_t)n * g.H + h) * g.W + w;
+  if (e.bias) {
+#pragma unroll
+    for (int i = 0; i < NV; i += 4) {
+      float4 b = *reinterpret_cast<const float4*>(e.bias + c0 + i);
+      v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+    }
+  }
+  if (e.out_acc) {
+    float* d = e.out_acc + pix * g.Cout + c0;
+#pragma unroll
+    for (int i = 0; i < NV; i += 4) *reinterpret_cast<float4*>(d + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+  }
+  if (e.residual) {
+    const float* r = e.residual + pix * g.Cout + c0;
+#pragma unroll
+    for (int i = 0; i < NV; i += 4) {
+      float4 b = *reinterpret_cast<const float4*>(r + i);
+      v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+    }
+  }
+  if (e.out_raw) {
+    float* d = e.out_raw + pix * g.Cout + c0;
+#pragma unroll
+    for (int i = 0; i < NV; i += 4) *reinterpret_cast<float4*>(d + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+  }
+  if (e.out_op) {
+    if (e.op_elu) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) v[i] = elu1(v[i]);
+    }
+    const int P = e.op_pad, Hp = g.H + 2 * P, Wp = g.W + 2 * P;
+    // interior position plus the circular-halo duplicates this pixel owns
+    int hs[3], ws[3], nh = 0, nw = 0;
+    hs[nh++] = h + P;
+    if (h < P) hs[nh++] = h + P + g.H;
+    if (h >= g.H - P) hs[nh++] = h + P - g.H;
+    ws[nw++] = w + P;
+    if (w < P) ws[nw++] = w + P + g.W;
+    if (w >= g.W - P) ws[nw++] = w + P - g.W;
+    for (int a = 0; a < nh; ++a)
+      for (int b = 0; b < nw; ++b) {
+        T* d = reinterpret_cast<T*>(e.out_op) + (((size_t)n * Hp + hs[a]) * Wp + ws[b]) * g.Cout + c0;
+#pragma unroll
+        for (int i = 0; i < NV; i += 4) store_op4<T>(d + i, v + i, e.op_tf32 != 0);
+      }
+  }
+}
+
+}  // namespace sdpc

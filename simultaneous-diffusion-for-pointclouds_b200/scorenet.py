@@ -1,0 +1,206 @@
+"""NCSN_LiDAR_small: host mirror of the reference score network's module interface
+(LiDARGen/models/ncsnv2.py:420-518) on top of the C ABI (include/sdpc_b200.h).
+
+Same constructor argument (the nested-Namespace config), same `forward(x, y)`, same
+state_dict keys and registration order (so `DataParallel(model).load_state_dict(states[0],
+strict=True)` and `EMAHelper` work unchanged), but forward runs the hand-written sm_100a
+kernels.  There is no CPU / eager fallback: a CPU tensor or a missing library raises.
+"""
+import ctypes as C
+import math
+import os
+
+import torch
+import torch.nn as nn
+
+from . import cabi
+from .sigmas import get_sigmas
+
+
+def parameter_inventory(ngf=128, channels=2):
+    """[(name, shape)] in the reference's registration order (ncsnv2.py:433-477; blocks
+    layers.py:62-83,112-134,165-184,214-249,291-313,401-456; norm normalization.py:150-162)."""
+    g, g2 = ngf, 2 * ngf
+    out = []
+
+    def conv(pre, co, ci, k, bias):
+        out.append((pre + ".weight", (co, ci, k, k)))
+        if bias:
+            out.append((pre + ".bias", (co,)))
+
+    def norm(pre, c):
+        for p in ("alpha", "gamma", "beta"):
+            out.append((f"{pre}.{p}", (c,)))
+
+    def res(pre, ci, co, kind):
+        if kind == "plain":
+            conv(pre + ".conv1", co, ci, 3, True); norm(pre + ".normalize2", co); conv(pre + ".conv2", co, co, 3, True)
+        elif kind == "down_pool":
+            conv(pre + ".conv1", ci, ci, 3, True); norm(pre + ".normalize2", ci)
+            conv(pre + ".conv2.conv", co, ci, 3, True); conv(pre + ".shortcut.conv", co, ci, 1, True)
+        else:
+            conv(pre + ".conv1", ci, ci, 3, True); norm(pre + ".normalize2", ci)
+            conv(pre + ".conv2", co, ci, 3, True); conv(pre + ".shortcut", co, ci, 3, True)
+        norm(pre + ".normalize1", ci)
+
+    def refine(pre, in_planes, f, start=False, end=False):
+        for i, cp in enumerate(in_planes):
+            for b in (1, 2):
+                for s in (1, 2):
+                    conv(f"{pre}.adapt_convs.{i}.{b}_{s}_conv", cp, cp, 3, False)
+        for b in range(1, (3 if end else 1) + 1):
+            for s in (1, 2):
+                conv(f"{pre}.output_convs.{b}_{s}_conv", f, f, 3, False)
+        if not start:
+            for i, cp in enumerate(in_planes):
+                conv(f"{pre}.msf.convs.{i}", f, cp, 3, True)
+        for i in (0, 1):
+            conv(f"{pre}.crp.convs.{i}", f, f, 3, False)
+
+    conv("begin_conv", g, channels + 2, 3, True)
+    norm("normalizer", g)
+    conv("end_conv", channels, g, 3, True)
+    res("res1.0", g, g, "plain"); res("res1.1", g, g, "plain")
+    res("res2.0", g, g2, "down_pool"); res("res2.1", g2, g2, "plain")
+    res("res3.0", g2, g2, "dilated"); res("res3.1", g2, g2, "plain")
+    res("res4.0", g2, g2, "dilated"); res("res4.1", g2, g2, "plain")
+    refine("refine1", [g2], g2, start=True)
+    refine("refine2", [g2, g2], g2)
+    refine("refine3", [g2, g2], g)
+    refine("refine4", [g, g], g, end=True)
+    return out
+
+
+class _Node(nn.Module):
+    """Anonymous container: only there to give parameters the reference's dotted names."""
+
+    def forward(self, *a, **k):
+        raise RuntimeError("sub-blocks are not callable: NCSN_LiDAR_small.forward runs the fused CUDA plan")
+
+
+class NCSN_LiDAR_small(nn.Module):
+    def __init__(self, config, precision=None):
+        super().__init__()
+        self.config = config
+        self.logit_transform = config.data.logit_transform
+        self.rescaled = config.data.rescaled
+        if self.logit_transform or self.rescaled:
+            raise NotImplementedError("only the LiDAR configuration (logit_transform=False, rescaled=False) is supported")
+        if config.model.normalization != "InstanceNorm++" or config.model.nonlinearity.lower() != "elu":
+            raise NotImplementedError("only normalization='InstanceNorm++' with nonlinearity='elu' is supported")
+        self.ngf = config.model.ngf
+        self.num_classes = config.model.num_classes
+        self.channels = config.data.channels
+        self.precision = (precision or getattr(config.model, "precision", None)
+                          or os.environ.get("SDPC_PRECISION", "tf32")).lower()
+        if self.precision not in cabi.PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(cabi.PRECISIONS)}")
+        self.register_buffer('sigmas', get_sigmas(config))
+        for name, shape in parameter_inventory(self.ngf, self.channels):
+            parts = name.split(".")
+            node = self
+            for part in parts[:-1]:
+                if part not in node._modules:
+                    node.add_module(part, _Node())
+                node = node._modules[part]
+            node.register_parameter(parts[-1], nn.Parameter(self._init(parts[-1], shape)))
+        self._handles = {}          # (device index, H, W) -> state
+        self._dirty = True
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module.refresh_weights())
+
+    @staticmethod
+    def _init(kind, shape):
+        t = torch.empty(shape)
+        if kind == "weight":                      # nn.Conv2d default (kaiming_uniform_, a=sqrt(5))
+            fan_in = shape[1] * shape[2] * shape[3]
+            nn.init.uniform_(t, -1 / math.sqrt(fan_in), 1 / math.sqrt(fan_in))
+        elif kind == "bias":
+            nn.init.uniform_(t, -0.05, 0.05)
+        elif kind in ("alpha", "gamma"):          # normalization.py:157-158
+            t.normal_(1, 0.02)
+        else:
+            t.zero_()
+        return t
+
+    # ------------------------------------------------------------------------------ C ABI
+    def refresh_weights(self):
+        """Mark the packed device copies stale (call after mutating parameters in place)."""
+        self._dirty = True
+
+    def _fingerprint(self):
+        return tuple(p._version for p in self.parameters())
+
+    def _state(self, x):
+        lib = cabi.load()
+        key = (x.device.index, x.shape[2], x.shape[3])
+        st = self._handles.get(key)
+        if st is None:
+            cfg = cabi.ScoreConfig(self.channels, x.shape[2], x.shape[3], self.ngf, self.num_classes,
+                                   cabi.PRECISIONS[self.precision], 1024, int(os.environ.get("SDPC_KEEP_TAPS", "0")))
+            h = C.c_void_p()
+            cabi.check(lib, lib.sdpc_score_create(C.byref(cfg), C.byref(h)), "sdpc_score_create")
+            st = dict(handle=h, ws=None, ws_views=0, fp=None)
+            self._handles[key] = st
+        fp = self._fingerprint()
+        if self._dirty or st["fp"] != fp or st.get("loaded_on") != x.device:
+            stream = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+            sd = dict(self.named_parameters())
+            sd["sigmas"] = self.sigmas
+            for name, t in sd.items():
+                t = t.detach().to(device=x.device, dtype=torch.float32).contiguous()
+                shape = (C.c_int64 * t.dim())(*t.shape)
+                cabi.check(lib, lib.sdpc_score_load_param(st["handle"], name.encode(), C.c_void_p(t.data_ptr()), shape,
+                                                          t.dim(), 1, stream), f"sdpc_score_load_param({name})")
+            cabi.check(lib, lib.sdpc_score_finalize(st["handle"], stream), "sdpc_score_finalize")
+            torch.cuda.current_stream(x.device).synchronize()     # temporaries above may be freed now
+            st["fp"], st["loaded_on"] = fp, x.device
+            self._dirty = False
+        return lib, st
+
+    def forward(self, x, y):
+        if not x.is_cuda:
+            raise cabi.SdpcError("NCSN_LiDAR_small.forward needs a CUDA tensor: the B200 path has no CPU fallback")
+        x = x.detach().to(torch.float32).contiguous()
+        y = y.detach().to(device=x.device, dtype=torch.int64).contiguous()
+        B = x.shape[0]
+        with torch.cuda.device(x.device):
+            lib, st = self._state(x)
+            if st["ws"] is None or st["ws_views"] != B:
+                nbytes = lib.sdpc_score_workspace_bytes(st["handle"], B)
+                st["ws"] = torch.empty(int(nbytes), dtype=torch.uint8, device=x.device)
+                st["ws_views"] = B
+            out = torch.empty_like(x)
+            stream = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+            cabi.check(lib, lib.sdpc_score_forward(st["handle"], C.c_void_p(x.data_ptr()), C.c_void_p(y.data_ptr()),
+                                                   C.c_void_p(out.data_ptr()), B, C.c_void_p(st["ws"].data_ptr()),
+                                                   st["ws"].numel(), stream), "sdpc_score_forward")
+        return out
+
+    # ------------------------------------------------------------------------------ introspection
+    def read_tap(self, name, x):
+        """Test hook (needs SDPC_KEEP_TAPS=1 at handle creation): named intermediate as NCHW fp32."""
+        lib, st = self._state(x)
+        B = x.shape[0]
+        buf = torch.empty(B * 256 * x.shape[2] * x.shape[3], dtype=torch.float32, device=x.device)
+        chw = (C.c_int * 3)()
+        stream = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+        cabi.check(lib, lib.sdpc_score_read_tap(st["handle"], name.encode(), C.c_void_p(buf.data_ptr()), buf.numel(), B,
+                                                chw, stream), f"sdpc_score_read_tap({name})")
+        c, h, w = chw[0], chw[1], chw[2]
+        return buf[:B * c * h * w].view(B, c, h, w).clone()
+
+    def launch_count(self, x):
+        lib, st = self._state(x)
+        return lib.sdpc_score_last_launch_count(st["handle"])
+
+    def flops_per_view(self, x):
+        lib, st = self._state(x)
+        return lib.sdpc_score_flops_per_view(st["handle"])
+
+    def __del__(self):
+        try:
+            lib = cabi.load()
+            for st in self._handles.values():
+                lib.sdpc_score_destroy(st["handle"])
+        except Exception:
+            pass
