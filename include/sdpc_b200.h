@@ -98,6 +98,11 @@ int sdpc_score_last_launch_count(const sdpc_score_t* h);
 /* CUDA-event time (ms) of the convolution kernels alone is measured by bench.py itself; this
  * returns the algorithmic FLOPs (2*M*N*K over all convolutions) of one view-forward. */
 double sdpc_score_flops_per_view(const sdpc_score_t* h);
+/* Roofline support for bench.py: when on, every tensor-core convolution launch of a forward is
+ * bracketed by CUDA events on the launching stream; collect() waits for them and returns the summed
+ * device time, the summed algorithmic FLOPs (2*M*N*K) and the number of launches, then resets. */
+int sdpc_score_set_profiling(sdpc_score_t* h, int on);
+int sdpc_score_profile_collect(sdpc_score_t* h, double* total_ms, double* total_flops, int* n_launches);
 
 /* ------------------------------------------------------------------------------------------
  * Langevin update + cross-view consistency step
@@ -119,7 +124,8 @@ typedef struct sdpc_step_params {
   int32_t sky_filter;    /* a-5: drop candidates whose SOURCE pixel has sky == 0 (__init__.py:352) */
   int32_t tgt_first;     /* first target view this call resolves (multi-GPU sharding), else 0 */
   int32_t tgt_count;     /* number of target views, else n_views */
-  int32_t reserved;
+  int32_t scalar_div_recip; /* 1: tensor/python-scalar divisions as x*(1/s) like torch's CUDA kernels (matches the
+                               reference on a GPU bit-for-bit); 0: IEEE division like torch's CPU kernels */
   float step_size;       /* eps: float32 value of step_lr*(sigma/sigmas[-1])**2 (KITTISampling.py:135) */
   float noise_scale;     /* float32 value of np.sqrt(step_size*2) (KITTISampling.py:156) */
   float grad_ref;        /* step_refer */

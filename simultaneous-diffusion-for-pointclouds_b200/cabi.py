@@ -18,7 +18,7 @@ class StepParams(C.Structure):
     _fields_ = [
         ("n_views", C.c_int32), ("group_size", C.c_int32), ("height", C.c_int32), ("width", C.c_int32),
         ("big_rows", C.c_int32), ("variant", C.c_int32), ("share", C.c_int32), ("nan_to_num", C.c_int32),
-        ("sky_filter", C.c_int32), ("tgt_first", C.c_int32), ("tgt_count", C.c_int32), ("reserved", C.c_int32),
+        ("sky_filter", C.c_int32), ("tgt_first", C.c_int32), ("tgt_count", C.c_int32), ("scalar_div_recip", C.c_int32),
         ("step_size", C.c_float), ("noise_scale", C.c_float), ("grad_ref", C.c_float), ("corr_coef", C.c_float),
         ("sigma_mod", C.c_float), ("min_depth_thr", C.c_float),
         ("allowance", C.c_double), ("h_min", C.c_double), ("dh", C.c_double),
@@ -58,6 +58,8 @@ SYMBOLS = [
     ("sdpc_score_read_tap", _I, [_P, C.c_char_p, _P, _SZ, _I, C.POINTER(_I), _P]),
     ("sdpc_score_last_launch_count", _I, [_P]),
     ("sdpc_score_flops_per_view", C.c_double, [_P]),
+    ("sdpc_score_set_profiling", _I, [_P, _I]),
+    ("sdpc_score_profile_collect", _I, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_I)]),
     ("sdpc_step_workspace_bytes", _SZ, [_I, _I, _I, _I]),
     ("sdpc_langevin_update", _I, [C.POINTER(StepParams), C.POINTER(StepBuffers), _P, _SZ, _P]),
     ("sdpc_step_merge_max", _I, [_P, _P, _I, _P]),

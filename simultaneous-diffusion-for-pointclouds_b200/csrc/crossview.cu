@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(256) scatter_kernel(ScatterArgs a) {
   const int r = p / a.geo.W, c = p - r * a.geo.W;
   const float x0 = a.x[((size_t)b * 2) * HW + p];
   const float x1 = a.x[((size_t)b * 2 + 1) * HW + p];
-  const float dist = decode_range(x0, a.sigma_mod);
+  const float dist = decode_range(x0, a.sigma_mod, a.geo.recip);
   double P[3];
   unproject(dist, a.cos_az[c], a.sin_az[c], a.cos_el[r], a.sin_el[r], P);
   double wx, wy, wz, ww = 1.0;
@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(256) resolve_kernel(ResolveArgs a) {
     const int wa = w / HW, wp = w - wa * HW;
     min_i = a.x[((size_t)(g * a.A + wa) * 2 + 1) * HW + wp];
   }
-  Fused f = fuse_cell(cnt, a.ws.sum_d[cell], a.ws.sum_i[cell], min_d, min_i, a.sigma_mod, a.allowance);
+  Fused f = fuse_cell(cnt, a.ws.sum_d[cell], a.ws.sum_i[cell], min_d, min_i, a.sigma_mod, a.allowance, a.geo.recip);
   float nd = (float)(neg ? f.depth * -1.0 : f.depth);
   float ni = f.inten;
   a.img[i0] = nd;
@@ -297,9 +297,9 @@ __global__ void __launch_bounds__(256)
 correct_kernel(float* __restrict__ x, const float* __restrict__ img, const uint8_t* __restrict__ smask,
                const int32_t* __restrict__ mask, const unsigned int* __restrict__ max_bits,
                int32_t* __restrict__ too_high_out, int HW, int v_first, long long n_vec, float sigma_mod,
-               float corr_coef) {
+               float corr_coef, int recip) {
   const float mx = __uint_as_float(*max_bits);
-  const bool too_high = (mx * 6.0f) / sigma_mod > 50.0f;
+  const bool too_high = too_high_gate(mx, sigma_mod, recip);
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i == 0 && too_high_out) *too_high_out = too_high ? 1 : 0;
   if (i >= n_vec) return;
@@ -423,6 +423,7 @@ extern "C" int sdpc_crossview_share(const sdpc_step_params* p, const sdpc_step_b
   sa.ws = ws;
   sa.geo.h_min = p->h_min; sa.geo.dh = p->dh; sa.geo.big_row_min = p->big_row_min; sa.geo.dv = p->dv;
   sa.geo.H = p->height; sa.geo.W = p->width; sa.geo.R = p->big_rows;
+  sa.geo.recip = p->scalar_div_recip ? 1 : 0;
   sa.A = p->group_size; sa.variant = p->variant; sa.sky_filter = p->sky_filter;
   sa.tgt_first = p->tgt_first; sa.tgt_count = tcount;
   sa.sigma_mod = p->sigma_mod; sa.min_depth_thr = p->min_depth_thr;
@@ -448,7 +449,7 @@ extern "C" int sdpc_crossview_share(const sdpc_step_params* p, const sdpc_step_b
   long long n_vec = (long long)tcount * 2 * HW / 4;
   correct_kernel<<<(unsigned)((n_vec + 255) / 256), 256, 0, stream>>>(b->x, ra.img, ws.shared_mask, b->mask, ws.max_bits,
                                                                      b->too_high, HW, p->tgt_first, n_vec,
-                                                                     p->sigma_mod, p->corr_coef);
+                                                                     p->sigma_mod, p->corr_coef, sa.geo.recip);
   SDPC_CUDA(cudaGetLastError());
   return SDPC_OK;
 }

@@ -21,12 +21,19 @@ namespace sdpc {
 struct GeoConsts {
   double h_min, dh, big_row_min, dv;
   int H, W, R;
+  // torch divides a tensor by a Python/NumPy scalar differently per device: the CPU kernels divide,
+  // the CUDA kernel multiplies by the reciprocal (BinaryDivTrueKernel.cu, "may lose one bit").
+  // recip = 1 reproduces the CUDA reference bit-for-bit, recip = 0 the CPU reference.
+  int recip;
 };
 
+SDPC_HD float sdiv(float a, float b, int recip) { return recip ? a * (1.0f / b) : a / b; }
+SDPC_HD double sdiv(double a, double b, int recip) { return recip ? a * (1.0 / b) : a / b; }
+
 // KITTISampling.py:161-166: realDistance = (2^(|x0|*6/sigmaMod) - 1) * sign, all float32.
-SDPC_HD float decode_range(float x0, float sigma_mod) {
+SDPC_HD float decode_range(float x0, float sigma_mod, int recip) {
   float e = fabsf(x0) * 6.0f;
-  e = e / sigma_mod;
+  e = sdiv(e, sigma_mod, recip);
   float d = powf(2.0f, e) - 1.0f;
   return (x0 < 0.0f) ? d * -1.0f : d * 1.0f;
 }
@@ -61,12 +68,12 @@ SDPC_HD Candidate reproject(double qx, double qy, double qz, float sigma_mod, co
   double xy = qx * qx + qy * qy;
   double r = sqrt(xy + qz * qz);
   double nd = log2(r + 1.0);
-  nd = nd / 6.0;
+  nd = sdiv(nd, 6.0, g.recip);
   c.nd = nd * (double)sigma_mod;
   double horiz = atan2(qy, qx);
   double vert = atan2(qz, sqrt(xy));
-  double cf = rint((horiz - g.h_min) / g.dh);
-  double rf = rint((vert - g.big_row_min) / g.dv);
+  double cf = rint(sdiv(horiz - g.h_min, g.dh, g.recip));
+  double rf = rint(sdiv(vert - g.big_row_min, g.dv, g.recip));
   // .int() of an already rounded double; NaN/inf map to INT_MIN like x86 cvttsd2si
   int ci = (cf >= -2147483648.0 && cf <= 2147483647.0) ? (int)cf : INT32_MIN;
   int ri = (rf >= -2147483648.0 && rf <= 2147483647.0) ? (int)rf : INT32_MIN;
@@ -93,7 +100,7 @@ struct Fused {
 
 // KITTISampling.py:348-394 for one grid cell: average, optional controlled average, re-log.
 SDPC_HD Fused fuse_cell(unsigned cnt, long long sum_d_fx, long long sum_i_fx, double min_d, float min_i,
-                        float sigma_mod, double allowance) {
+                        float sigma_mod, double allowance, int recip) {
   Fused f;
   f.filled = cnt > 0;
   float scaling = (float)cnt + 0.000000001f;                  // float32, as in the reference
@@ -102,11 +109,11 @@ SDPC_HD Fused fuse_cell(unsigned cnt, long long sum_d_fx, long long sum_i_fx, do
   if (!f.filled) { min_d = 0.0; min_i = 0.0f; }
   if (allowance >= 0.0) {
     double sm = (double)sigma_mod;
-    double m_avg = pow(2.0, fabs(avg_d) * 6.0 / sm) - 1.0;
-    double m_min = pow(2.0, fabs(min_d) * 6.0 / sm) - 1.0;
+    double m_avg = pow(2.0, sdiv(fabs(avg_d) * 6.0, sm, recip)) - 1.0;
+    double m_min = pow(2.0, sdiv(fabs(min_d) * 6.0, sm, recip)) - 1.0;
     bool far = m_avg > m_min + allowance;
     if (far) { avg_i = min_i; m_avg = m_min + allowance / 5.0; }
-    avg_d = log2(m_avg + 1.0) / 6.0 * sm;
+    avg_d = sdiv(log2(m_avg + 1.0), 6.0, recip) * sm;
   }
   f.depth = avg_d;
   f.inten = avg_i;
@@ -130,6 +137,11 @@ SDPC_HD float langevin_value(float x, float g, float ref, int mask, float z, flo
   a = a + rho * gl;
   a = a + z * noise_scale;
   return a;
+}
+
+// tooHigh gate (KITTISampling.py:162): max|x0| * 6 / sigmaMod > 50 in float32
+SDPC_HD bool too_high_gate(float max_abs, float sigma_mod, int recip) {
+  return sdiv(max_abs * 6.0f, sigma_mod, recip) > 50.0f;
 }
 
 }  // namespace sdpc

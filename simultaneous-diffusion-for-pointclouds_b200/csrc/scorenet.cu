@@ -69,6 +69,15 @@ struct sdpc_score {
   Plan plan;
   int last_launches = 0;
   double flops_per_view = 0.0;
+  // optional CUDA-event bracketing of the tensor-core convolution launches (bench.py roofline)
+  bool profiling = false;
+  std::vector<cudaEvent_t> ev_pool;
+  struct ProfRec { cudaEvent_t a, b; double flops; };
+  std::vector<ProfRec> prof;
+  cudaEvent_t get_event() {
+    if (!ev_pool.empty()) { cudaEvent_t e = ev_pool.back(); ev_pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+  }
   int elem_bytes() const { return cfg.precision == SDPC_PREC_BF16 ? 2 : 4; }
   const float* P(const std::string& n) const { return params[index.at(n)].dev; }
 };
@@ -322,8 +331,18 @@ struct Builder {
     uint32_t bbox[3] = {(uint32_t)bk, (uint32_t)cw.Cout, 1u};
     if (int st = make_tmap(&L.tmap_a, in.ptr, L.elem_bytes, 4, adims, abox)) { status = st; return; }
     if (int st = make_tmap(&L.tmap_b, cw.w_tc, L.elem_bytes, 3, bdims, bbox)) { status = st; return; }
-    plan->umma_flops += 2.0 * (double)N * in.H * in.W * cw.Cout * cw.Cin * cw.taps;
-    push([=](cudaStream_t s, const float*, const int64_t*, float*) -> int { return conv_umma_launch(L, s); });
+    const double fl = 2.0 * (double)N * in.H * in.W * cw.Cout * cw.Cin * cw.taps;
+    plan->umma_flops += fl;
+    sdpc_score* hh = h;
+    push([=](cudaStream_t s, const float*, const int64_t*, float*) -> int {
+      if (!hh->profiling) return conv_umma_launch(L, s);
+      sdpc_score::ProfRec r{hh->get_event(), hh->get_event(), fl};
+      cudaEventRecord(r.a, s);
+      int st = conv_umma_launch(L, s);
+      cudaEventRecord(r.b, s);
+      hh->prof.push_back(r);
+      return st;
+    });
   }
 
   // ---- blocks ---------------------------------------------------------------------------
@@ -717,3 +736,28 @@ extern "C" int sdpc_score_read_tap(sdpc_score_t* h, const char* tap, float* out,
 
 extern "C" int sdpc_score_last_launch_count(const sdpc_score_t* h) { return h ? h->last_launches : 0; }
 extern "C" double sdpc_score_flops_per_view(const sdpc_score_t* h) { return h ? h->flops_per_view : 0.0; }
+
+extern "C" int sdpc_score_set_profiling(sdpc_score_t* h, int on) {
+  if (!h) return set_error(SDPC_ERR_ARG, "set_profiling: null handle");
+  h->profiling = on != 0;
+  return SDPC_OK;
+}
+
+extern "C" int sdpc_score_profile_collect(sdpc_score_t* h, double* total_ms, double* total_flops, int* n_launches) {
+  if (!h) return set_error(SDPC_ERR_ARG, "profile_collect: null handle");
+  double ms = 0.0, fl = 0.0;
+  for (auto& r : h->prof) {
+    SDPC_CUDA(cudaEventSynchronize(r.b));
+    float t = 0.0f;
+    SDPC_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
+    ms += t;
+    fl += r.flops;
+    h->ev_pool.push_back(r.a);
+    h->ev_pool.push_back(r.b);
+  }
+  if (total_ms) *total_ms = ms;
+  if (total_flops) *total_flops = fl;
+  if (n_launches) *n_launches = (int)h->prof.size();
+  h->prof.clear();
+  return SDPC_OK;
+}

@@ -36,8 +36,10 @@ def _report(prefix_verbose, c, step_size, sigma, grad, grad_likelihood, noise, x
 
 def _simultaneous(variant, x_mod, refer_image, refer_mask, sky, minStepToShare, setting, allowance, scorenet, sigmas,
                   actualBatchSize, n_steps_each, step_lr, existMask, denoise, verbose, grad_ref,
-                  correlation_coefficient, fromWorld=None, toWorld=None, modificationList=None, shard=None):
-    _require_cuda(x_mod)
+                  correlation_coefficient, fromWorld=None, toWorld=None, modificationList=None, shard=None,
+                  _lib=None):
+    if _lib is None:            # _lib: test-only host emulation of the C ABI (tests/host_emul), CPU tensors
+        _require_cuda(x_mod)
     dev = x_mod.device
     images, targets, sharedImages = [], [], []
     B = x_mod.shape[0]
@@ -48,9 +50,10 @@ def _simultaneous(variant, x_mod, refer_image, refer_mask, sky, minStepToShare, 
         kw = dict(to_world=toWorld.to(dev).reshape(B, 4, 4), from_world=fromWorld.to(dev).reshape(B, 4, 4))
     else:
         kw = dict(origins=translation_origins(modificationList.to(dev)))
-    run = StepRunner(x.shape, dev, refer, refer_mask, sky, existMask, actualBatchSize, variant, **kw)
+    run = StepRunner(x.shape, dev, refer, refer_mask, sky, existMask, actualBatchSize, variant, lib=_lib, **kw)
     if shard is not None:
         shard.attach(run, x)
+    grad_full = torch.zeros_like(x) if shard is not None else None
     pose = variant == cabi.SDPC_VARIANT_POSE
     L = len(sigmas)
     new_images = torch.empty_like(x)
@@ -85,8 +88,8 @@ def _simultaneous(variant, x_mod, refer_image, refer_mask, sky, minStepToShare, 
         want_images = share and (c in (0, 20, 110) or c == L - 1)
         wants_print = (verbose and c % 20 == 0) or (pose and (c == 1 or c == 2))
         for s in range(n_steps_each):
-            grad = scorenet(x, labels)
-            noise = torch.randn_like(x)
+            grad = scorenet(x, labels) if shard is None else shard.score(scorenet, x, labels, grad_full)
+            noise = torch.randn_like(x)        # sharded: every rank draws the full tensor (same seed) and uses its block
             last = s == n_steps_each - 1
             keep_gl = last and (c == L - 1 or wants_print)
             b = run.buffers(x, grad, noise, grad_likelihood=grad_likelihood if keep_gl else None,
@@ -96,16 +99,26 @@ def _simultaneous(variant, x_mod, refer_image, refer_mask, sky, minStepToShare, 
             else:
                 shard.step(run, p, b, x)
             if want_images:
-                snap = new_images.to('cpu')
+                snap = (new_images if shard is None else shard.gather_result(new_images)).to('cpu')
                 if c in (0, 20, 110):
                     sharedImages.append(snap)
                 if c == L - 1:
                     images.append(snap)
-        if wants_print:
+        if wants_print and shard is None:
             _report(verbose, c, step_size, sigma, torch.nan_to_num(grad), grad_likelihood, noise, x, refer, grad_ref)
 
     if mask_f is None:
         mask_f = refer_mask.to(dev)
+    if shard is not None:                                       # finish on the rank's own views, then gather
+        sl = slice(shard.lo, shard.hi)
+        xl, rl, ml = x[sl], refer[sl], mask_f[sl]
+        if denoise:
+            last_noise = ((L - 1) * torch.ones(xl.shape[0], device=dev)).long()
+            xl = xl + sigmas[-1] ** 2 * scorenet(xl.contiguous(), last_noise) + grad_ref * grad_likelihood[sl]
+        xl = xl + grad_ref * (-ml * (xl - rl))
+        x[sl] = xl
+        images.append(shard.gather_result(x).to('cpu'))
+        return images, targets, sharedImages
     if denoise:                                                 # KITTISampling.py:502-507 (stale grad_likelihood)
         last_noise = ((L - 1) * torch.ones(B, device=dev)).long()
         x = x + sigmas[-1] ** 2 * scorenet(x, last_noise) + grad_ref * grad_likelihood
@@ -125,22 +138,23 @@ def _simultaneous(variant, x_mod, refer_image, refer_mask, sky, minStepToShare, 
 def anneal_Langevin_dynamics_inpainting_simultaneous_basic_kitti(
         x_mod, refer_image, refer_mask, sky, x_indices, minStepToShare, setting, allowance, scorenet, sigmas,
         fromWorld, toWorld, actualBatchSize, n_steps_each=100, step_lr=0.000008, existMask=None, denoise=True,
-        verbose=True, grad_ref=0.1, correlation_coefficient=0.1, sampling_step=16, shard=None):
-    """a-4, pose-matrix simultaneous sampler (Line.yml path)."""
+        verbose=True, grad_ref=0.1, correlation_coefficient=0.1, sampling_step=16, shard=None, _lib=None):
+    """a-4, pose-matrix simultaneous sampler (Line.yml path).  `shard`: optional dist.ViewShard."""
     return _simultaneous(cabi.SDPC_VARIANT_POSE, x_mod, refer_image, refer_mask, sky, minStepToShare, setting,
                          allowance, scorenet, sigmas, actualBatchSize, n_steps_each, step_lr, existMask, denoise,
-                         verbose, grad_ref, correlation_coefficient, fromWorld=fromWorld, toWorld=toWorld, shard=shard)
+                         verbose, grad_ref, correlation_coefficient, fromWorld=fromWorld, toWorld=toWorld, shard=shard,
+                         _lib=_lib)
 
 
 @torch.no_grad()
 def anneal_Langevin_dynamics_inpainting_simultaneous_basic(
         x_mod, refer_image, refer_mask, sky, x_indices, minStepToShare, setting, scorenet, sigmas, modificationList,
         actualBatchSize, n_steps_each=100, step_lr=0.000008, existMask=None, denoise=True, verbose=True,
-        grad_ref=0.1, correlation_coefficient=0.1, sampling_step=16, shard=None):
+        grad_ref=0.1, correlation_coefficient=0.1, sampling_step=16, shard=None, _lib=None):
     """a-5, translation-only simultaneous sampler (Inpainting / Densification path)."""
     return _simultaneous(cabi.SDPC_VARIANT_TRANSLATION, x_mod, refer_image, refer_mask, sky, minStepToShare, setting,
                          None, scorenet, sigmas, actualBatchSize, n_steps_each, step_lr, existMask, denoise, verbose,
-                         grad_ref, correlation_coefficient, modificationList=modificationList, shard=shard)
+                         grad_ref, correlation_coefficient, modificationList=modificationList, shard=shard, _lib=_lib)
 
 
 @torch.no_grad()

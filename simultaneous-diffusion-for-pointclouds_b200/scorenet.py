@@ -104,6 +104,7 @@ class NCSN_LiDAR_small(nn.Module):
                     node.add_module(part, _Node())
                 node = node._modules[part]
             node.register_parameter(parts[-1], nn.Parameter(self._init(parts[-1], shape)))
+        self._keep_taps = int(os.environ.get("SDPC_KEEP_TAPS", "0"))   # test hook: keep every intermediate
         self._handles = {}          # (device index, H, W) -> state
         self._dirty = True
         self.register_load_state_dict_post_hook(lambda module, incompatible: module.refresh_weights())
@@ -136,7 +137,7 @@ class NCSN_LiDAR_small(nn.Module):
         st = self._handles.get(key)
         if st is None:
             cfg = cabi.ScoreConfig(self.channels, x.shape[2], x.shape[3], self.ngf, self.num_classes,
-                                   cabi.PRECISIONS[self.precision], 1024, int(os.environ.get("SDPC_KEEP_TAPS", "0")))
+                                   cabi.PRECISIONS[self.precision], 1024, self._keep_taps)
             h = C.c_void_p()
             cabi.check(lib, lib.sdpc_score_create(C.byref(cfg), C.byref(h)), "sdpc_score_create")
             st = dict(handle=h, ws=None, ws_views=0, fp=None)
@@ -188,6 +189,18 @@ class NCSN_LiDAR_small(nn.Module):
                                                 chw, stream), f"sdpc_score_read_tap({name})")
         c, h, w = chw[0], chw[1], chw[2]
         return buf[:B * c * h * w].view(B, c, h, w).clone()
+
+    def set_profiling(self, x, on):
+        lib, st = self._state(x)
+        cabi.check(lib, lib.sdpc_score_set_profiling(st["handle"], int(on)), "sdpc_score_set_profiling")
+
+    def profile_collect(self, x):
+        """(device ms, algorithmic FLOPs, launches) of the tensor-core convolutions since the last collect."""
+        lib, st = self._state(x)
+        ms, fl, n = C.c_double(), C.c_double(), C.c_int()
+        cabi.check(lib, lib.sdpc_score_profile_collect(st["handle"], C.byref(ms), C.byref(fl), C.byref(n)),
+                   "sdpc_score_profile_collect")
+        return ms.value, fl.value, n.value
 
     def launch_count(self, x):
         lib, st = self._state(x)

@@ -32,7 +32,7 @@ def translation_origins(modification_list):
 class StepRunner:
     def __init__(self, x_shape, device, refer, mask, sky, exist, group_size, variant,
                  to_world=None, from_world=None, origins=None, lib=None, tgt_first=0, tgt_count=0,
-                 debug=False):
+                 debug=False, scalar_div_recip=None):
         B, Cn, H, W = x_shape
         assert Cn == 2
         self.lib = lib if lib is not None else cabi.load()
@@ -49,6 +49,9 @@ class StepRunner:
         self.from_world = from_world.to(device=device, dtype=torch.float64).reshape(B, 16).contiguous() if from_world is not None else None
         self.origins = origins[:group_size, :, 0, 0].to(**f32).contiguous() if origins is not None else None
         self.tgt_first, self.tgt_count = tgt_first, tgt_count
+        # torch's CUDA kernels evaluate tensor / python-scalar as tensor * (1/scalar); its CPU kernels divide.
+        # Follow whichever reference arm runs on this device (override for tests against CPU goldens).
+        self.scalar_div_recip = (torch.device(device).type == "cuda") if scalar_div_recip is None else bool(scalar_div_recip)
         nbytes = 256 if self.lib is None else self._ws_bytes()
         self.workspace = torch.empty(nbytes, dtype=torch.uint8, device=device)
         self.too_high = torch.zeros(1, dtype=torch.int32, device=device)
@@ -72,6 +75,7 @@ class StepRunner:
         p.n_views, p.group_size, p.height, p.width, p.big_rows = self.B, self.A, self.H, self.W, g.R
         p.variant, p.share, p.nan_to_num, p.sky_filter = self.variant, int(share), int(nan_to_num), int(sky_filter)
         p.tgt_first, p.tgt_count = self.tgt_first, self.tgt_count
+        p.scalar_div_recip = int(self.scalar_div_recip)
         p.step_size, p.noise_scale = float(step_size), float(noise_scale)
         p.grad_ref, p.corr_coef, p.sigma_mod = float(grad_ref), float(corr_coef), float(sigma_mod)
         p.min_depth_thr = min_depth_threshold(sigma_mod) if min_depth_filter else -1.0
@@ -94,6 +98,8 @@ class StepRunner:
         return b
 
     def _stream(self):
+        if torch.device(self.device).type != "cuda":       # test-only host emulation
+            return None
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def step(self, p, b):

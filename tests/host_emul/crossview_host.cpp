@@ -33,7 +33,7 @@ extern "C" int emul_langevin_reproject_step(const sdpc_step_params* p, const sdp
       }
   if (has_nan) mx = std::numeric_limits<float>::quiet_NaN();
   if (!p->share) return 0;
-  GeoConsts geo{p->h_min, p->dh, p->big_row_min, p->dv, H, W, R};
+  GeoConsts geo{p->h_min, p->dh, p->big_row_min, p->dv, H, W, R, p->scalar_div_recip ? 1 : 0};
   const size_t cells = (size_t)B * R * W;
   std::vector<unsigned long long> zmin(cells, ~0ull);
   std::vector<unsigned> winner(cells, ~0u), cnt(cells, 0u);
@@ -48,7 +48,7 @@ extern "C" int emul_langevin_reproject_step(const sdpc_step_params* p, const sdp
           if (p->sky_filter) src_ok = src_ok && b->sky[(size_t)bsrc * HW + q] != 0;
           const int r = q / W, c = q % W;
           const float x0 = b->x[((size_t)bsrc * 2) * HW + q], x1 = b->x[((size_t)bsrc * 2 + 1) * HW + q];
-          const float dist = decode_range(x0, p->sigma_mod);
+          const float dist = decode_range(x0, p->sigma_mod, geo.recip);
           double P[3];
           unproject(dist, b->cos_az[c], b->sin_az[c], b->cos_el[r], b->sin_el[r], P);
           double wx, wy, wz, ww = 1.0;
@@ -116,12 +116,12 @@ extern "C" int emul_langevin_reproject_step(const sdpc_step_params* p, const sdp
         int wa = w / HW, wp = w % HW;
         min_i = b->x[((size_t)((t / A) * A + wa) * 2 + 1) * HW + wp];
       }
-      Fused f = fuse_cell(cnt[cell], sum_d[cell], sum_i[cell], min_d, min_i, p->sigma_mod, p->allowance);
+      Fused f = fuse_cell(cnt[cell], sum_d[cell], sum_i[cell], min_d, min_i, p->sigma_mod, p->allowance, geo.recip);
       img[i0] = (float)(neg ? f.depth * -1.0 : f.depth);
       img[i1] = f.inten;
       sm[(size_t)t * HW + q] = f.filled && b->exist[q] && b->sky[(size_t)t * HW + q];
     }
-  const bool too_high = (mx * 6.0f) / p->sigma_mod > 50.0f;
+  const bool too_high = too_high_gate(mx, p->sigma_mod, geo.recip);
   if (b->too_high) *b->too_high = too_high;
   for (int t = t0; t < t0 + tn; ++t)
     for (int ch = 0; ch < 2; ++ch)

@@ -46,8 +46,8 @@ def _oracle(kind, case, sigma, setting, dev):
     return ni, x2, th, d
 
 
-def _cuda_step(kind, case, sigma, setting):
-    run = _runner(kind, case)
+def _cuda_step(kind, case, sigma, setting, recip=None):
+    run = _runner(kind, case, scalar_div_recip=recip)
     sm = sigma if sigma > 1 else 1
     if kind == "pose":
         p = run.params(0.0, 0.0, 0.0, case["coef"], sm, True, setting == 5, 10.0, False)
@@ -88,7 +88,7 @@ def test_step_bit_exact_vs_device_oracle(kind, sigma, setting):
 def test_step_vs_reference_golden(kind, file, tag, sigma, setting):
     g = np.load(os.path.join(G, file))
     case = cases.small_multiview(kind)
-    x, ni, run = _cuda_step(kind, case, sigma, setting)
+    x, ni, run = _cuda_step(kind, case, sigma, setting, recip=False)      # CPU-torch division semantics
     W, R = case["W"], run.geo.R
     dbg = {k: v.cpu().numpy() for k, v in run.debug.items()}
     flips = int(((W - 1 - dbg["col"] != g[tag + "colr"]) | (R - 1 - dbg["row"] != g[tag + "rowr"])).sum())
@@ -102,7 +102,7 @@ def test_step_vs_reference_golden(kind, file, tag, sigma, setting):
 def test_too_high_gate():
     g = np.load(os.path.join(G, "crossview_toohigh.npz"))
     case = cases.small_multiview("pose", outlier=True)
-    x, ni, run = _cuda_step("pose", case, 0.3, 5)
+    x, ni, run = _cuda_step("pose", case, 0.3, 5, recip=False)
     assert int(run.too_high.item()) == 1
     assert np.array_equal(x.cpu().numpy(), g["x_final"])
 
@@ -130,7 +130,7 @@ def test_update_bit_exact_and_nan_to_num():
 def test_full_size_vs_golden_checksums_and_properties():
     g = np.load(os.path.join(G, "crossview_full.npz"))
     case = cases.full_multiview()
-    x, ni, run = _cuda_step("pose", case, 0.3, 5)
+    x, ni, run = _cuda_step("pose", case, 0.3, 5, recip=False)
     dbg = run.debug
     s = cases.FULL_STRIDE
     colr = (1023 - dbg["col"]).cpu().numpy().astype(np.int64)
@@ -146,7 +146,7 @@ def test_full_size_vs_golden_checksums_and_properties():
     # properties: every valid candidate is counted exactly once; a winner is a valid candidate of its pixel
     assert int(cnt.sum()) == int(dbg["valid"].sum().item())
     # idempotence of the bookkeeping: a second call on the same input gives identical outputs (deterministic atomics)
-    x2, ni2, run2 = _cuda_step("pose", case, 0.3, 5)
+    x2, ni2, run2 = _cuda_step("pose", case, 0.3, 5, recip=False)
     assert torch.equal(ni, ni2) and torch.equal(x, x2)
 
 
