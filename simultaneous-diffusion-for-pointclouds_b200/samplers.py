@@ -15,6 +15,11 @@ from . import cabi
 from .step import StepRunner, translation_origins
 
 
+def _snap(t):
+    """CPU snapshot like the reference's `.to('cpu')`, but never an alias of a live buffer."""
+    return t.detach().to('cpu', copy=True)
+
+
 def _require_cuda(x):
     if not x.is_cuda:
         raise cabi.SdpcError("the B200 samplers need CUDA tensors: there is no CPU fallback")
@@ -99,7 +104,7 @@ def _simultaneous(variant, x_mod, refer_image, refer_mask, sky, minStepToShare, 
             else:
                 shard.step(run, p, b, x)
             if want_images:
-                snap = (new_images if shard is None else shard.gather_result(new_images)).to('cpu')
+                snap = _snap(new_images if shard is None else shard.gather_result(new_images))
                 if c in (0, 20, 110):
                     sharedImages.append(snap)
                 if c == L - 1:
@@ -117,7 +122,7 @@ def _simultaneous(variant, x_mod, refer_image, refer_mask, sky, minStepToShare, 
             xl = xl + sigmas[-1] ** 2 * scorenet(xl.contiguous(), last_noise) + grad_ref * grad_likelihood[sl]
         xl = xl + grad_ref * (-ml * (xl - rl))
         x[sl] = xl
-        images.append(shard.gather_result(x).to('cpu'))
+        images.append(_snap(shard.gather_result(x)))
         return images, targets, sharedImages
     if denoise:                                                 # KITTISampling.py:502-507 (stale grad_likelihood)
         last_noise = ((L - 1) * torch.ones(B, device=dev)).long()
@@ -130,7 +135,7 @@ def _simultaneous(variant, x_mod, refer_image, refer_mask, sky, minStepToShare, 
                                                               torch.median(torch.abs(x - refer))))
     grad_likelihood = -mask_f * (x - refer)
     x = x + grad_ref * grad_likelihood
-    images.append(x.to('cpu'))
+    images.append(_snap(x))
     return images, targets, sharedImages
 
 
@@ -184,20 +189,20 @@ def anneal_Langevin_dynamics_inpainting(x_mod, refer_image, refer_mask, scorenet
             keep_gl = last and (c == L - 1 or wants_print)
             b = run.buffers(x, grad, noise, grad_likelihood=grad_likelihood if keep_gl else None)
             run.update_only(p, b)
-            images.append(x.to('cpu'))
+            images.append(_snap(x))
         if wants_print:
             _report(verbose, c, step_size, sigma, grad, grad_likelihood, noise, x, refer, grad_ref)
     mask_d = refer_mask.to(dev)
     if denoise:
         last_noise = ((L - 1) * torch.ones(B, device=dev)).long()
         x = x + sigmas[-1] ** 2 * scorenet(x, last_noise) + grad_ref * grad_likelihood
-        images.append(x.to('cpu'))
+        images.append(_snap(x))
         print("grad_ref: {}, mean: {}, median: {}".format(grad_ref, torch.mean(torch.abs(x - refer)),
                                                           torch.median(torch.abs(x - refer))))
     grad_likelihood = -mask_d * (x - refer)
     x = x + grad_ref * grad_likelihood
-    images.append(x.to('cpu'))
+    images.append(_snap(x))
     print("grad_ref: {}, mean: {}, median: {}".format(grad_ref, torch.mean(torch.abs(x - refer)),
                                                       torch.median(torch.abs(x - refer))))
-    targets.append(refer.to('cpu'))
+    targets.append(_snap(refer))
     return images, targets

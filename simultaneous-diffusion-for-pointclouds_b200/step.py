@@ -35,6 +35,10 @@ class StepRunner:
                  debug=False, scalar_div_recip=None):
         B, Cn, H, W = x_shape
         assert Cn == 2
+        if B % group_size != 0:
+            raise ValueError(f"batch of {B} views is not a multiple of actualBatchSize={group_size}")
+        if exist is not None and exist.shape[0] < group_size:
+            raise ValueError(f"existMask has {exist.shape[0]} views, actualBatchSize={group_size} are indexed")
         self.lib = lib if lib is not None else cabi.load()
         self.device = device
         self.B, self.A, self.H, self.W = B, group_size, H, W

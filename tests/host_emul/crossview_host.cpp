@@ -11,11 +11,16 @@
 
 using namespace sdpc;
 
-extern "C" int emul_langevin_reproject_step(const sdpc_step_params* p, const sdpc_step_buffers* b) {
-  const int B = p->n_views, A = p->group_size, H = p->height, W = p->width, R = p->big_rows;
+// The emulation exports the product library's entry-point names (host pointers instead of device
+// pointers, `stream` ignored) so that StepRunner / ViewShard can be driven unchanged in CPU tests.
+extern "C" size_t sdpc_step_workspace_bytes(int, int, int, int) { return 256; }
+extern "C" const char* sdpc_last_error(void) { return "host emulation"; }
+
+extern "C" int sdpc_langevin_update(const sdpc_step_params* p, const sdpc_step_buffers* b, void* workspace, size_t,
+                                    void*) {
+  const int B = p->n_views, H = p->height, W = p->width;
   const int HW = H * W;
   const int t0 = p->tgt_first, tn = p->tgt_count ? p->tgt_count : B;
-  // update
   float mx = 0.0f;
   bool has_nan = false;
   for (int v = t0; v < t0 + tn; ++v)
@@ -32,7 +37,24 @@ extern "C" int emul_langevin_reproject_step(const sdpc_step_params* p, const sdp
         if (ch == 0) { if (o != o) has_nan = true; mx = std::max(mx, fabsf(o)); }
       }
   if (has_nan) mx = std::numeric_limits<float>::quiet_NaN();
-  if (!p->share) return 0;
+  *(float*)workspace = mx;
+  return 0;
+}
+
+extern "C" int sdpc_step_read_max(void* workspace, float* out_max, void*) { *out_max = *(float*)workspace; return 0; }
+extern "C" int sdpc_step_merge_max(void* workspace, const float* other, int n, void*) {
+  float m = *(float*)workspace;
+  for (int i = 0; i < n; ++i) { if (other[i] != other[i] || m != m) m = std::numeric_limits<float>::quiet_NaN(); else m = std::max(m, fabsf(other[i])); }
+  *(float*)workspace = m;
+  return 0;
+}
+
+extern "C" int sdpc_crossview_share(const sdpc_step_params* p, const sdpc_step_buffers* b, void* workspace, size_t,
+                                    void*) {
+  const int B = p->n_views, A = p->group_size, H = p->height, W = p->width, R = p->big_rows;
+  const int HW = H * W;
+  const int t0 = p->tgt_first, tn = p->tgt_count ? p->tgt_count : B;
+  const float mx = *(float*)workspace;
   GeoConsts geo{p->h_min, p->dh, p->big_row_min, p->dv, H, W, R, p->scalar_div_recip ? 1 : 0};
   const size_t cells = (size_t)B * R * W;
   std::vector<unsigned long long> zmin(cells, ~0ull);
@@ -132,4 +154,15 @@ extern "C" int emul_langevin_reproject_step(const sdpc_step_params* p, const sdp
         b->x[e] = b->x[e] + p->corr_coef * corr;
       }
   return 0;
+}
+
+extern "C" int sdpc_langevin_reproject_step(const sdpc_step_params* p, const sdpc_step_buffers* b, void* workspace,
+                                            size_t n, void* stream) {
+  if (int e = sdpc_langevin_update(p, b, workspace, n, stream)) return e;
+  return p->share ? sdpc_crossview_share(p, b, workspace, n, stream) : 0;
+}
+
+extern "C" int emul_langevin_reproject_step(const sdpc_step_params* p, const sdpc_step_buffers* b) {
+  float ws[64];
+  return sdpc_langevin_reproject_step(p, b, ws, sizeof(ws), nullptr);
 }

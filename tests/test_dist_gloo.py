@@ -1,0 +1,114 @@
+"""CPU, world_size 2, gloo: the view-sharded sampler (dist.ViewShard) equals the single-process run.
+
+The CUDA kernels are replaced by the g++ host emulation (tests/host_emul), which exports the product
+library's entry-point names; the host logic under test (target ranges, MAX all-reduce of the tooHigh
+gate, all-gather of the updated planes, sharded scoring, final gather) is the product's own code."""
+import ctypes as C
+import os
+import socket
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def _emul_lib(path):
+    import sdpc_b200  # noqa: F401
+    from sdpc_b200 import cabi
+    lib = C.CDLL(path)
+    P, I, SZ = C.c_void_p, C.c_int, C.c_size_t
+    for name, res, args in cabi.SYMBOLS:
+        if name.startswith("sdpc_step") or name.startswith("sdpc_langevin") or name.startswith("sdpc_crossview") \
+                or name == "sdpc_last_error":
+            if hasattr(lib, name):
+                fn = getattr(lib, name)
+                fn.restype, fn.argtypes = res, args
+    return lib
+
+
+def _run(kind, group_size, shard, lib, outlier=False):
+    import sdpc_b200  # noqa: F401
+    from sdpc_b200 import samplers
+    from tests.golden import cases
+    case = cases.small_multiview(kind, outlier=outlier)
+    if group_size > case["exist"].shape[0]:
+        case["exist"] = case["exist"].repeat(group_size // case["exist"].shape[0], 1, 1)
+    sig = cases.short_sigmas()
+    score = cases.fake_score(sig)
+    noise = iter(cases.noise_list(case["x"].shape, 8, 77))
+    orig = torch.randn_like
+    torch.randn_like = lambda t, *a, **k: next(noise)
+    try:
+        if kind == "pose":
+            im, _, _ = samplers.anneal_Langevin_dynamics_inpainting_simultaneous_basic_kitti(
+                case["x"], case["refer"], case["mask"], case["sky"], None, 1, 5, 10, score, sig, case["fromWorld"],
+                case["toWorld"], group_size, n_steps_each=2, step_lr=6.2e-6, existMask=case["exist"], denoise=True,
+                verbose=False, grad_ref=1, correlation_coefficient=0.01, shard=shard, _lib=lib)
+        else:
+            im, _, _ = samplers.anneal_Langevin_dynamics_inpainting_simultaneous_basic(
+                case["x"], case["refer"], case["mask"], case["sky"], None, 1, 7, score, sig, case["mods"], group_size,
+                n_steps_each=2, step_lr=6.2e-6, existMask=case["exist"], denoise=True, verbose=False, grad_ref=1,
+                correlation_coefficient=0.01, shard=shard, _lib=lib)
+    finally:
+        torch.randn_like = orig
+    return im
+
+
+def _worker(rank, world, port, libpath, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import sdpc_b200  # noqa: F401
+    from sdpc_b200.dist import ViewShard
+    lib = _emul_lib(libpath)
+    res = {}
+    # B = 4 views.  A = 2: every group lives on one rank (no gather); A = 4: the group spans both ranks (gather).
+    for tag, kind, A in (("pose_a2", "pose", 2), ("trans_a2", "trans", 2), ("pose_a4", "pose", 4)):
+        shard = ViewShard(4, A)
+        assert shard.needs_gather == (A == 4)
+        im = _run(kind, A, shard, lib)
+        res[tag] = [t.numpy() for t in im]
+    if rank == 0:
+        np.savez(os.path.join(out_dir, "sharded.npz"), **{f"{k}_{i}": a for k, v in res.items() for i, a in enumerate(v)})
+    dist.destroy_process_group()
+
+
+@pytest.fixture(scope="module")
+def emul_path():
+    out = os.path.join(tempfile.mkdtemp(prefix="sdpc_emul_"), "libemul.so")
+    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-o", out,
+                           os.path.join(ROOT, "tests", "host_emul", "crossview_host.cpp")])
+    return out
+
+
+def test_sharded_sampler_matches_single_process(emul_path):
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    out_dir = tempfile.mkdtemp(prefix="sdpc_gloo_")
+    mp.spawn(_worker, args=(2, port, emul_path, out_dir), nprocs=2, join=True)
+    got = np.load(os.path.join(out_dir, "sharded.npz"))
+    lib = _emul_lib(emul_path)
+    for tag, kind, A in (("pose_a2", "pose", 2), ("trans_a2", "trans", 2), ("pose_a4", "pose", 4)):
+        ref = _run(kind, A, None, lib)
+        for i, t in enumerate(ref):
+            assert np.array_equal(got[f"{tag}_{i}"], t.numpy()), (tag, i)
+
+
+def test_single_process_emulation_matches_reference_golden(emul_path):
+    """the same host path, unsharded, against the reference's golden trajectory (CPU division semantics)."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "sampler_pose.npz"))
+    im = _run("pose", 2, None, _emul_lib(emul_path))
+    assert len(im) == int(g["n_images"])
+    for i, t in enumerate(im):
+        assert int((np.abs(t.numpy() - g[f"images{i}"]) > 2e-4).sum()) <= 16
