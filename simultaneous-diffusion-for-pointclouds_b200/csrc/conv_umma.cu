@@ -31,6 +31,9 @@ constexpr int kRowBytes = 128;                  // bytes of K per smem row (one 
 constexpr int kABytes = kTileM * kRowBytes;     // 16 KiB
 constexpr int kThreads = 192;
 constexpr int kSmemBudget = 200 * 1024;
+constexpr int kBarrierBytes = 256;
+constexpr int kStgPitch = 36;                   // floats per staged pixel row (32 + 4 pad: conflict-free float4 access)
+constexpr int kStgFloats = 32 * kStgPitch;      // per epilogue warp
 
 template <int N_TILE>
 struct UmmaCfg {
@@ -38,7 +41,7 @@ struct UmmaCfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = kSmemBudget / kStageBytes;          // 4 (N=256) / 6 (N=128)
   static constexpr int kTmemCols = 2 * N_TILE;                       // 512 / 256
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + kBarrierBytes + 4 * kStgFloats * 4;
 };
 
 template <typename T, int N_TILE>
@@ -140,16 +143,22 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
   } else {
     // ------------------------------------------------------------ epilogue (warps 2..5)
+    // TMEM gives each thread one pixel (lane) x 32 channels.  Storing that directly would touch 32
+    // different 128-byte lines per instruction with 16 useful bytes each; instead every 32x32 chunk is
+    // transposed through a padded shared-memory tile so that 8 consecutive lanes cover one pixel's
+    // 128 contiguous bytes: all global loads (residual) and stores (raw / operand) are line-coalesced.
     const int quad = warp & 3;                               // TMEM lane quadrant this warp may read
-    const int m = quad * 32 + lane;                          // row of the tile = pixel
+    float* stg = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes + kBarrierBytes) + (warp - 2) * kStgFloats;
+    const int cq = lane & 7;                                 // channel quad within the 32-channel chunk
+    const int psub = lane >> 3;                              // pixel within a group of 4
     int local = 0;
     for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++local) {
       const int ab = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
       const int n = tile / tiles_per_img;
       const int rem = tile - n * tiles_per_img;
-      const int h = (rem / g.tiles_w) * g.BH + m / g.BW;
-      const int w = (rem % g.tiles_w) * g.BW + m % g.BW;
+      const int h0 = (rem / g.tiles_w) * g.BH;
+      const int w0 = (rem % g.tiles_w) * g.BW;
       mbar_wait(acc_full + ab, acc_phase);
       __syncwarp();
       tc_fence_after();
@@ -159,14 +168,57 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         uint32_t r[32];
         tmem_ld_32x32(t_addr + c0, r);
         tmem_ld_wait();
-        float v[32];
+        if (c0 + 32 == N_TILE) {                             // accumulator fully read: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(acc_empty + ab);
+        }
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-        epi_store<T, 32>(e, g, n, h, w, c0, v);
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(stg + lane * kStgPitch + j * 4) =
+              make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                          __uint_as_float(r[4 * j + 3]));
+        __syncwarp();
+        const int ch = c0 + cq * 4;
+        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (e.bias) bias4 = *reinterpret_cast<const float4*>(e.bias + ch);
+        size_t pix[8];
+        int hh[8], ww[8];
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int m = quad * 32 + it * 4 + psub;
+          hh[it] = h0 + m / g.BW;
+          ww[it] = w0 + m % g.BW;
+          pix[it] = (((size_t)n * g.H + hh[it]) * g.W + ww[it]) * g.Cout + ch;
+        }
+        float4 res[8];
+        if (e.residual) {
+#pragma unroll
+          for (int it = 0; it < 8; ++it) res[it] = *reinterpret_cast<const float4*>(e.residual + pix[it]);
+        }
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          float4 v = *reinterpret_cast<const float4*>(stg + (it * 4 + psub) * kStgPitch + cq * 4);
+          v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
+          if (e.out_acc) *reinterpret_cast<float4*>(e.out_acc + pix[it]) = v;
+          if (e.residual) { v.x += res[it].x; v.y += res[it].y; v.z += res[it].z; v.w += res[it].w; }
+          if (e.out_raw) *reinterpret_cast<float4*>(e.out_raw + pix[it]) = v;
+          if (e.out_op) {
+            float o[4] = {v.x, v.y, v.z, v.w};
+            if (e.op_elu) {
+              const bool red = e.op_tf32 != 0;
+              o[0] = elu_sel<T>(o[0], red); o[1] = elu_sel<T>(o[1], red); o[2] = elu_sel<T>(o[2], red); o[3] = elu_sel<T>(o[3], red);
+            }
+            const int P = e.op_pad, Hp = g.H + 2 * P, Wp = g.W + 2 * P;
+            const HaloPos d = halo_pos(hh[it], ww[it], g.H, g.W, P);
+            for_each_halo_pos(d, [&](int hp, int wp) {
+              store_op4<T>(reinterpret_cast<T*>(e.out_op) + (((size_t)n * Hp + hp) * Wp + wp) * g.Cout + ch, o,
+                           e.op_tf32 != 0);
+            });
+          }
+        }
+        __syncwarp();                                        // staging tile is reused by the next chunk
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(acc_empty + ab);
     }
   }
 

@@ -21,23 +21,25 @@ __device__ __forceinline__ float linspace01(int i, int steps) {
 }
 
 template <int NGF>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(NGF)
 begin_conv_kernel(const float* __restrict__ x, const float* __restrict__ wgt, const float* __restrict__ bias,
                   float* __restrict__ out, int N, int H, int W) {
+  // one thread per output channel (its 36 weights live in registers), 64 pixels of one row per block;
+  // the 36-value input patches are staged k-major in shared memory and read as broadcast float4s.
   constexpr int K = 36;
-  __shared__ float sw[K][NGF];
-  __shared__ float sin_[64][K + 1];
+  __shared__ __align__(16) float sin_[K][64];
   const int tiles_w = W / 64;
   const int blk = blockIdx.x;
   const int w0 = (blk % tiles_w) * 64;
   const int h = (blk / tiles_w) % H;
   const int n = blk / (tiles_w * H);
-  for (int i = threadIdx.x; i < K * NGF; i += blockDim.x) {
-    const int co = i / K, k = i % K;                 // wgt is [co][ci][kh][kw] = [co][k]
-    sw[k][co] = wgt[i];
-  }
-  for (int i = threadIdx.x; i < 64 * K; i += blockDim.x) {
-    const int p = i / K, k = i % K;
+  const int c = threadIdx.x;
+  float wr[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) wr[k] = wgt[c * K + k];          // wgt is [co][ci][kh][kw] = [co][k]
+  const float bc = bias[c];
+  for (int i = threadIdx.x; i < 64 * K; i += NGF) {
+    const int k = i / 64, p = i % 64;
     const int ci = k / 9, kh = (k % 9) / 3, kw = k % 3;
     const int hh = h + kh - 1, ww = w0 + p + kw - 1;
     float v = 0.0f;
@@ -46,15 +48,26 @@ begin_conv_kernel(const float* __restrict__ x, const float* __restrict__ wgt, co
       else if (ci == 2) v = linspace01(ww, W);
       else v = linspace01(hh, H);
     }
-    sin_[p][k] = v;
+    sin_[k][p] = v;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 64 * NGF; i += blockDim.x) {
-    const int p = i / NGF, c = i % NGF;
-    float acc = 0.0f;
+  float* orow = out + (((size_t)n * H + h) * W + w0) * NGF + c;
+#pragma unroll 1
+  for (int p0 = 0; p0 < 64; p0 += 8) {
+    float acc[8];
 #pragma unroll
-    for (int k = 0; k < K; ++k) acc = fmaf(sin_[p][k], sw[k][c], acc);
-    out[(((size_t)n * H + h) * W + w0 + p) * NGF + c] = acc + bias[c];
+    for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(&sin_[k][p0]);
+      const float4 b = *reinterpret_cast<const float4*>(&sin_[k][p0 + 4]);
+      acc[0] = fmaf(a.x, wr[k], acc[0]); acc[1] = fmaf(a.y, wr[k], acc[1]);
+      acc[2] = fmaf(a.z, wr[k], acc[2]); acc[3] = fmaf(a.w, wr[k], acc[3]);
+      acc[4] = fmaf(b.x, wr[k], acc[4]); acc[5] = fmaf(b.y, wr[k], acc[5]);
+      acc[6] = fmaf(b.z, wr[k], acc[6]); acc[7] = fmaf(b.w, wr[k], acc[7]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) orow[(size_t)(p0 + i) * NGF] = acc[i] + bc;
   }
 }
 
@@ -126,41 +139,77 @@ __device__ __forceinline__ void store_op8(T* dst, const float* v, bool tf32) {
   store_op4<T>(dst + 4, v + 4, tf32);
 }
 
+// One thread: 8 channels x 4 consecutive pixels of a row (all loads issued before use).  With
+// HALO_ZERO the halo is not written here: the buffer's border is cleared by zero_halo_kernel.
 template <typename T>
 __global__ void __launch_bounds__(256)
 to_operand_kernel(const float* __restrict__ in, const float* __restrict__ coef, T* __restrict__ out, int N, int H,
                   int W, int C, int P, int mode, int halo, int tf32) {
-  const int Hp = H + 2 * P, Wp = W + 2 * P, C8 = C / 8;
-  const size_t total = (size_t)N * Hp * Wp * C8;
+  const int C8 = C / 8, W4 = W / 4;
+  const size_t total = (size_t)N * H * W4 * C8;
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int c8 = (int)(i % C8);
   size_t t = i / C8;
-  const int wp = (int)(t % Wp); t /= Wp;
-  const int hp = (int)(t % Hp);
-  const int n = (int)(t / Hp);
-  int h = hp - P, w = wp - P;
-  float v[8];
-  const bool outside = h < 0 || h >= H || w < 0 || w >= W;
-  if (outside && halo == HALO_ZERO) {
+  const int w0 = (int)(t % W4) * 4; t /= W4;
+  const int h = (int)(t % H);
+  const int n = (int)(t / H);
+  const int Hp = H + 2 * P, Wp = W + 2 * P;
+  const float* src = in + (((size_t)n * H + h) * W + w0) * C + c8 * 8;
+  float4 a[4], b[4];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = 0.0f;
-  } else {
-    h = (h % H + H) % H;
-    w = (w % W + W) % W;
-    const float* src = in + (((size_t)n * H + h) * W + w) * C + c8 * 8;
-    const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
-    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  for (int j = 0; j < 4; ++j) {
+    a[j] = *reinterpret_cast<const float4*>(src + (size_t)j * C);
+    b[j] = *reinterpret_cast<const float4*>(src + (size_t)j * C + 4);
+  }
+  float mu[8], ga[8], be[8];
+  if (mode == OP_NORM_ELU) {
+    const float* cf = coef + ((size_t)n * C + c8 * 8) * 3;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { mu[k] = cf[k * 3]; ga[k] = cf[k * 3 + 1]; be[k] = cf[k * 3 + 2]; }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float v[8] = {a[j].x, a[j].y, a[j].z, a[j].w, b[j].x, b[j].y, b[j].z, b[j].w};
     if (mode == OP_NORM_ELU) {
-      const float* cf = coef + ((size_t)n * C + c8 * 8) * 3;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) v[k] = elu1(cf[k * 3 + 1] * (v[k] - cf[k * 3]) + cf[k * 3 + 2]);
+      for (int k = 0; k < 8; ++k) v[k] = elu_sel<T>(ga[k] * (v[k] - mu[k]) + be[k], tf32 != 0);
     } else if (mode == OP_ELU) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) v[k] = elu1(v[k]);
+      for (int k = 0; k < 8; ++k) v[k] = elu_sel<T>(v[k], tf32 != 0);
+    }
+    const int w = w0 + j;
+    if (halo == HALO_ZERO) {
+      store_op8<T>(out + (((size_t)n * Hp + h + P) * Wp + w + P) * C + c8 * 8, v, tf32 != 0);
+    } else {
+      const HaloPos d = halo_pos(h, w, H, W, P);
+      for_each_halo_pos(d, [&](int hp, int wp) {
+        store_op8<T>(out + (((size_t)n * Hp + hp) * Wp + wp) * C + c8 * 8, v, tf32 != 0);
+      });
     }
   }
-  store_op8<T>(out + i * 8, v, tf32 != 0);
+}
+
+// zero the P-wide border of a padded NHWC tensor (zero-padded convolutions)
+template <typename T>
+__global__ void __launch_bounds__(256)
+zero_halo_kernel(T* __restrict__ out, int N, int H, int W, int C, int P) {
+  const int Hp = H + 2 * P, Wp = W + 2 * P, C8 = C / 8;
+  const int border = Hp * Wp - H * W;                 // border pixels per image
+  const size_t total = (size_t)N * border * C8;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c8 = (int)(i % C8);
+  size_t t = i / C8;
+  int bidx = (int)(t % border);
+  const int n = (int)(t / border);
+  int hp, wp;
+  const int top = P * Wp;
+  if (bidx < top) { hp = bidx / Wp; wp = bidx % Wp; }
+  else if (bidx < 2 * top) { bidx -= top; hp = H + P + bidx / Wp; wp = bidx % Wp; }
+  else { bidx -= 2 * top; hp = P + bidx / (2 * P); const int q = bidx % (2 * P); wp = q < P ? q : W + q; }
+  float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  store_op8<T>(out + (((size_t)n * Hp + hp) * Wp + wp) * C + c8 * 8, z, false);
 }
 
 // CRP stage (layers.py:76-83): out_op = [ELU](maxpool5(in)) with circular halo for the conv that
@@ -170,40 +219,58 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 maxpool5_kernel(const float* __restrict__ in, float* __restrict__ x0_out, T* __restrict__ out, int N, int H, int W,
                 int C, int P, int elu_in, int tf32) {
-  const int Hp = H + 2 * P, Wp = W + 2 * P, C8 = C / 8;
-  const size_t total = (size_t)N * Hp * Wp * C8;
+  // one thread: 8 channels x 4 consecutive output pixels of a row.  Column maxima over the (clipped)
+  // 5 rows are formed once for the 8 columns the strip needs, then combined 5 at a time.
+  const int C8 = C / 8, W4 = W / 4;
+  const size_t total = (size_t)N * H * W4 * C8;
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int c8 = (int)(i % C8);
   size_t t = i / C8;
-  const int wp = (int)(t % Wp); t /= Wp;
-  const int hp = (int)(t % Hp);
-  const int n = (int)(t / Hp);
-  const bool interior = hp >= P && hp < H + P && wp >= P && wp < W + P;
-  const int h = ((hp - P) % H + H) % H, w = ((wp - P) % W + W) % W;
-  float m[8];
+  const int w0 = (int)(t % W4) * 4; t /= W4;
+  const int h = (int)(t % H);
+  const int n = (int)(t / H);
+  const int h_lo = max(h - 2, 0), h_hi = min(h + 2, H - 1);
+  float cm[8][8];                                        // [column w0-2+j][channel]
 #pragma unroll
-  for (int k = 0; k < 8; ++k) m[k] = -INFINITY;
-  const int h_lo = max(h - 2, 0), h_hi = min(h + 2, H - 1), w_lo = max(w - 2, 0), w_hi = min(w + 2, W - 1);
-  for (int hh = h_lo; hh <= h_hi; ++hh)
-    for (int ww = w_lo; ww <= w_hi; ++ww) {
-      const float* src = in + (((size_t)n * H + hh) * W + ww) * C + c8 * 8;
-      const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
-      m[0] = fmaxf(m[0], a.x); m[1] = fmaxf(m[1], a.y); m[2] = fmaxf(m[2], a.z); m[3] = fmaxf(m[3], a.w);
-      m[4] = fmaxf(m[4], b.x); m[5] = fmaxf(m[5], b.y); m[6] = fmaxf(m[6], b.z); m[7] = fmaxf(m[7], b.w);
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) cm[j][k] = -INFINITY;
+  for (int hh = h_lo; hh <= h_hi; ++hh) {
+    const float* row = in + (((size_t)n * H + hh) * W) * C + c8 * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int ww = w0 - 2 + j;
+      if (ww >= 0 && ww < W) {
+        const float4 a = *reinterpret_cast<const float4*>(row + (size_t)ww * C);
+        const float4 b = *reinterpret_cast<const float4*>(row + (size_t)ww * C + 4);
+        cm[j][0] = fmaxf(cm[j][0], a.x); cm[j][1] = fmaxf(cm[j][1], a.y); cm[j][2] = fmaxf(cm[j][2], a.z);
+        cm[j][3] = fmaxf(cm[j][3], a.w); cm[j][4] = fmaxf(cm[j][4], b.x); cm[j][5] = fmaxf(cm[j][5], b.y);
+        cm[j][6] = fmaxf(cm[j][6], b.z); cm[j][7] = fmaxf(cm[j][7], b.w);
+      }
     }
-  if (elu_in) {
-#pragma unroll
-    for (int k = 0; k < 8; ++k) m[k] = elu1(m[k]);
   }
-  store_op8<T>(out + i * 8, m, tf32 != 0);
-  if (x0_out && interior) {
-    const size_t o = (((size_t)n * H + h) * W + w) * C + c8 * 8;
-    const float4 a = *reinterpret_cast<const float4*>(in + o), b = *reinterpret_cast<const float4*>(in + o + 4);
-    float4 ea = make_float4(elu1(a.x), elu1(a.y), elu1(a.z), elu1(a.w));
-    float4 eb = make_float4(elu1(b.x), elu1(b.y), elu1(b.z), elu1(b.w));
-    *reinterpret_cast<float4*>(x0_out + o) = ea;
-    *reinterpret_cast<float4*>(x0_out + o + 4) = eb;
+  const int Hp = H + 2 * P, Wp = W + 2 * P;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float m[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      m[k] = fmaxf(fmaxf(fmaxf(cm[j][k], cm[j + 1][k]), fmaxf(cm[j + 2][k], cm[j + 3][k])), cm[j + 4][k]);
+      if (elu_in) m[k] = elu_sel<T>(m[k], tf32 != 0);
+    }
+    const int w = w0 + j;
+    const HaloPos d = halo_pos(h, w, H, W, P);
+    for_each_halo_pos(d, [&](int hp, int wp) {
+      store_op8<T>(out + (((size_t)n * Hp + hp) * Wp + wp) * C + c8 * 8, m, tf32 != 0);
+    });
+    if (x0_out) {
+      const size_t o = (((size_t)n * H + h) * W + w) * C + c8 * 8;
+      const float4 a = *reinterpret_cast<const float4*>(in + o), b = *reinterpret_cast<const float4*>(in + o + 4);
+      const bool red = tf32 != 0;
+      *reinterpret_cast<float4*>(x0_out + o) = make_float4(elu_sel<T>(a.x, red), elu_sel<T>(a.y, red), elu_sel<T>(a.z, red), elu_sel<T>(a.w, red));
+      *reinterpret_cast<float4*>(x0_out + o + 4) = make_float4(elu_sel<T>(b.x, red), elu_sel<T>(b.y, red), elu_sel<T>(b.z, red), elu_sel<T>(b.w, red));
+    }
   }
 }
 
@@ -284,36 +351,55 @@ __global__ void __launch_bounds__(256)
 end_conv_kernel(const float* __restrict__ op, const float* __restrict__ wgt, const float* __restrict__ bias,
                 const float* __restrict__ sigmas, const int64_t* __restrict__ labels, float* __restrict__ out, int N,
                 int H, int W) {
+  // one warp: 8 consecutive pixels of a row; a lane owns 4 input channels.  The 3 x 10 input columns
+  // are loaded once and reused by the 9 taps of the 8 outputs.
   static_assert(NGF == 128, "one float4 per lane");
-  __shared__ float sw[2][9][NGF];
+  __shared__ __align__(16) float sw[2][9][NGF];
   for (int i = threadIdx.x; i < 2 * 9 * NGF; i += blockDim.x) {
     const int co = i / (9 * NGF), r = i % (9 * NGF), tap = r / NGF, ci = r % NGF;
     sw[co][tap][ci] = wgt[((size_t)co * NGF + ci) * 9 + tap];
   }
   __syncthreads();
   const int lane = threadIdx.x & 31;
-  const size_t pix = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (pix >= (size_t)N * H * W) return;
-  const int w = (int)(pix % W), h = (int)((pix / W) % H), n = (int)(pix / ((size_t)W * H));
+  const size_t strip = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int W8 = W / 8;
+  if (strip >= (size_t)N * H * W8) return;
+  const int w0 = (int)(strip % W8) * 8, h = (int)((strip / W8) % H), n = (int)(strip / ((size_t)W8 * H));
   const int Hp = H + 2, Wp = W + 2;
-  float a0 = 0.0f, a1 = 0.0f;
+  float a0[8], a1[8];
 #pragma unroll
-  for (int tap = 0; tap < 9; ++tap) {
-    const float4 v = *reinterpret_cast<const float4*>(
-        op + (((size_t)n * Hp + h + tap / 3) * Wp + w + tap % 3) * NGF + lane * 4);
-    const float4 w0 = *reinterpret_cast<const float4*>(&sw[0][tap][lane * 4]);
-    const float4 w1 = *reinterpret_cast<const float4*>(&sw[1][tap][lane * 4]);
-    a0 += v.x * w0.x + v.y * w0.y + v.z * w0.z + v.w * w0.w;
-    a1 += v.x * w1.x + v.y * w1.y + v.z * w1.z + v.w * w1.w;
+  for (int i = 0; i < 8; ++i) a0[i] = a1[i] = 0.0f;
+#pragma unroll
+  for (int kh = 0; kh < 3; ++kh) {
+    float4 col[10];
+    const float* row = op + (((size_t)n * Hp + h + kh) * Wp + w0) * NGF + lane * 4;
+#pragma unroll
+    for (int j = 0; j < 10; ++j) col[j] = *reinterpret_cast<const float4*>(row + (size_t)j * NGF);
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw) {
+      const float4 w0v = *reinterpret_cast<const float4*>(&sw[0][kh * 3 + kw][lane * 4]);
+      const float4 w1v = *reinterpret_cast<const float4*>(&sw[1][kh * 3 + kw][lane * 4]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 v = col[i + kw];
+        a0[i] += v.x * w0v.x + v.y * w0v.y + v.z * w0v.z + v.w * w0v.w;
+        a1[i] += v.x * w1v.x + v.y * w1v.y + v.z * w1v.z + v.w * w1v.w;
+      }
+    }
   }
-  for (int o = 16; o > 0; o >>= 1) {
-    a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-    a1 += __shfl_xor_sync(0xffffffffu, a1, o);
-  }
-  if (lane == 0) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    for (int o = 16; o > 0; o >>= 1) {
+      a0[i] += __shfl_xor_sync(0xffffffffu, a0[i], o);
+      a1[i] += __shfl_xor_sync(0xffffffffu, a1[i], o);
+    }
+  if (lane < 8) {
     const float s = sigmas[labels[n]];
-    out[(((size_t)n * 2 + 0) * H + h) * W + w] = (a0 + bias[0]) / s;
-    out[(((size_t)n * 2 + 1) * H + h) * W + w] = (a1 + bias[1]) / s;
+    float v0 = a0[0], v1 = a1[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) if (lane == i) { v0 = a0[i]; v1 = a1[i]; }
+    out[(((size_t)n * 2 + 0) * H + h) * W + w0 + lane] = (v0 + bias[0]) / s;
+    out[(((size_t)n * 2 + 1) * H + h) * W + w0 + lane] = (v1 + bias[1]) / s;
   }
 }
 

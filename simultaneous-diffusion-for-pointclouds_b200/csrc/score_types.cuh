@@ -32,6 +32,13 @@ struct EpiParams {
 };
 
 __device__ __forceinline__ float elu1(float v) { return v > 0.0f ? v : expm1f(v); }
+// ex2.approx based ELU for the reduced-precision arms (abs error ~1e-7, far below bf16/tf32 rounding);
+// the fp32 arm keeps expm1f.
+template <typename T>
+__device__ __forceinline__ float elu_sel(float v, bool reduced) {
+  if (sizeof(T) == 2 || reduced) return v > 0.0f ? v : __expf(v) - 1.0f;
+  return elu1(v);
+}
 
 __device__ __forceinline__ float round_tf32(float v) {
   uint32_t r;
@@ -55,6 +62,29 @@ __device__ __forceinline__ void store_op4<__nv_bfloat16>(__nv_bfloat16* dst, con
   o.x = *reinterpret_cast<uint32_t*>(&a);
   o.y = *reinterpret_cast<uint32_t*>(&b);
   *reinterpret_cast<uint2*>(dst) = o;
+}
+
+// Positions a pixel (h,w) of an HxW image occupies in a tensor padded by P with circular wrap: its
+// interior position (h+P, w+P) plus at most one duplicate row and one duplicate column on the opposite
+// border (H, W >= 2P, so a pixel is never near both borders of an axis).  hb / wb are -1 when absent.
+struct HaloPos { int ha, hb, wa, wb; };
+__device__ __forceinline__ HaloPos halo_pos(int h, int w, int H, int W, int P) {
+  HaloPos d;
+  d.ha = h + P;
+  d.wa = w + P;
+  d.hb = (h < P) ? h + P + H : ((h >= H - P) ? h + P - H : -1);
+  d.wb = (w < P) ? w + P + W : ((w >= W - P) ? w + P - W : -1);
+  return d;
+}
+// f(hp, wp) for every position the pixel owns
+template <typename F>
+__device__ __forceinline__ void for_each_halo_pos(const HaloPos& d, F f) {
+  f(d.ha, d.wa);
+  if (d.wb >= 0) f(d.ha, d.wb);
+  if (d.hb >= 0) {
+    f(d.hb, d.wa);
+    if (d.wb >= 0) f(d.hb, d.wb);
+  }
 }
 
 // Store NV (multiple of 4) consecutive output channels [c0, c0+NV) of pixel (n,h,w).
@@ -90,23 +120,15 @@ __device__ __forceinline__ void epi_store(const EpiParams& e, const ConvGeom& g,
   if (e.out_op) {
     if (e.op_elu) {
 #pragma unroll
-      for (int i = 0; i < NV; ++i) v[i] = elu1(v[i]);
+      for (int i = 0; i < NV; ++i) v[i] = elu_sel<T>(v[i], e.op_tf32 != 0);
     }
     const int P = e.op_pad, Hp = g.H + 2 * P, Wp = g.W + 2 * P;
-    // interior position plus the circular-halo duplicates this pixel owns
-    int hs[3], ws[3], nh = 0, nw = 0;
-    hs[nh++] = h + P;
-    if (h < P) hs[nh++] = h + P + g.H;
-    if (h >= g.H - P) hs[nh++] = h + P - g.H;
-    ws[nw++] = w + P;
-    if (w < P) ws[nw++] = w + P + g.W;
-    if (w >= g.W - P) ws[nw++] = w + P - g.W;
-    for (int a = 0; a < nh; ++a)
-      for (int b = 0; b < nw; ++b) {
-        T* d = reinterpret_cast<T*>(e.out_op) + (((size_t)n * Hp + hs[a]) * Wp + ws[b]) * g.Cout + c0;
+    const HaloPos d = halo_pos(h, w, g.H, g.W, P);
+    for_each_halo_pos(d, [&](int hp, int wp) {
+      T* dst = reinterpret_cast<T*>(e.out_op) + (((size_t)n * Hp + hp) * Wp + wp) * g.Cout + c0;
 #pragma unroll
-        for (int i = 0; i < NV; i += 4) store_op4<T>(d + i, v + i, e.op_tf32 != 0);
-      }
+      for (int i = 0; i < NV; i += 4) store_op4<T>(dst + i, v + i, e.op_tf32 != 0);
+    });
   }
 }
 

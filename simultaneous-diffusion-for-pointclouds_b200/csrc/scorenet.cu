@@ -249,12 +249,15 @@ struct Builder {
     const float* in = (const float*)x.ptr;
     T* o = (T*)out.ptr;
     const int n = N, H = x.H, W = x.W, C = x.C, P = out.pad;
-    const size_t total = (size_t)n * (H + 2 * P) * (W + 2 * P) * (C / 8);
+    const size_t total = (size_t)n * H * (W / 4) * (C / 8);
+    const size_t border = (size_t)n * ((size_t)(H + 2 * P) * (W + 2 * P) - (size_t)H * W) * (C / 8);
+    const bool zero = halo == HALO_ZERO && P > 0;
     push([=](cudaStream_t s, const float*, const int64_t*, float*) -> int {
+      if (zero) zero_halo_kernel<T><<<blocks(border), 256, 0, s>>>(o, n, H, W, C, P);
       to_operand_kernel<T><<<blocks(total), 256, 0, s>>>(in, coef, o, n, H, W, C, P, mode, halo, tf32);
       SDPC_CUDA(cudaGetLastError());
       return SDPC_OK;
-    });
+    }, zero ? 2 : 1);
   }
   Buf to_operand(const Buf& x, const float* coef, int pad, int mode, int halo, bool force_fp32 = false) {
     Buf out = force_fp32 ? alloc(N, x.H, x.W, x.C, pad, 4) : operand(x.H, x.W, x.C, pad);
@@ -272,7 +275,7 @@ struct Builder {
     float* x0 = x0_out ? (float*)x0_out->ptr : nullptr;
     const int n = N, H = x.H, W = x.W, C = x.C;
     const int tf32 = h->cfg.precision == SDPC_PREC_TF32;
-    const size_t total = (size_t)n * (H + 2) * (W + 2) * (C / 8);
+    const size_t total = (size_t)n * H * (W / 4) * (C / 8);
     void* o = out.ptr;
     const int elem = out.elem, ei = elu_in ? 1 : 0;
     push([=](cudaStream_t s, const float*, const int64_t*, float*) -> int {
@@ -351,8 +354,9 @@ struct Builder {
     return to_operand(x, coef_ptr(r), pad, OP_NORM_ELU, halo, force_fp32);
   }
 
-  // ResidualBlock (layers.py:401-456); does not release `x`.
-  Buf residual_block(const std::string& pre, const Buf& x, ResKind kind, int dil) {
+  // ResidualBlock (layers.py:401-456); does not release `x`.  If `elu_op` is given (plain / dilated blocks),
+  // the last convolution's epilogue also emits ELU(out) as an operand with halo 1 for the RCU that reads it.
+  Buf residual_block(const std::string& pre, const Buf& x, ResKind kind, int dil, Buf* elu_op = nullptr) {
     const int d = dil ? dil : 1;
     Buf sc;                                             // shortcut branch (raw)
     if (kind == RES_DILATED) {
@@ -387,7 +391,8 @@ struct Builder {
       Buf a2 = norm_elu_operand(t1, pre + ".normalize2", d, HALO_CIRC);
       release(t1);
       out = raw(x.H, x.W, h->convs.at(pre + ".conv2.weight").Cout);
-      conv(a2, pre + ".conv2.weight", d, true, kind == RES_DILATED ? &sc : &x, &out, nullptr, nullptr, false);
+      if (elu_op) *elu_op = operand(out.H, out.W, out.C, 1);
+      conv(a2, pre + ".conv2.weight", d, true, kind == RES_DILATED ? &sc : &x, &out, nullptr, elu_op, true);
       release(a2);
       if (kind == RES_DILATED) release(sc);
     }
@@ -412,32 +417,43 @@ struct Builder {
     });
   }
 
-  // RCUBlock (layers.py:112-134).  `x` is not released; returns a new raw buffer.
-  Buf rcu(const std::string& pre, const Buf& x, int n_blocks) {
+  // RCUBlock (layers.py:112-134).  `x` is not released.
+  //   first_op : ELU(x) operand (halo 1) if a producer already emitted it (consumed here), else built here
+  //   final    : RCU_RAW  -> returns the raw output
+  //              RCU_RAW_ELU -> returns raw and also *final_op = ELU(out) operand for a following RCU
+  //              RCU_OP_COPY -> only *final_op = out as an operand (MSF conv input); returns an invalid Buf
+  enum { RCU_RAW = 0, RCU_RAW_ELU = 1, RCU_OP_COPY = 2 };
+  Buf rcu(const std::string& pre, const Buf& x, int n_blocks, Buf* first_op = nullptr, int final = RCU_RAW,
+          Buf* final_op = nullptr) {
     Buf cur = x;
     bool cur_owned = false;
-    Buf a = to_operand(x, nullptr, 1, OP_ELU, HALO_CIRC);
+    Buf a = first_op ? *first_op : to_operand(x, nullptr, 1, OP_ELU, HALO_CIRC);
+    if (first_op) first_op->bytes = 0;                    // ownership moves here
     for (int b = 1; b <= n_blocks; ++b) {
       const std::string p1 = pre + "." + std::to_string(b) + "_1_conv.weight", p2 = pre + "." + std::to_string(b) + "_2_conv.weight";
       Buf a2 = operand(x.H, x.W, x.C, 1);
       conv(a, p1, 1, false, nullptr, nullptr, nullptr, &a2, true);       // ELU fused, feeds conv 2 directly
       release(a);
-      Buf nxt = raw(x.H, x.W, x.C);
       const bool more = b < n_blocks;
-      Buf an;
-      if (more) an = operand(x.H, x.W, x.C, 1);
-      conv(a2, p2, 1, false, &cur, &nxt, nullptr, more ? &an : nullptr, true);   // + block input (residual)
+      const bool want_raw = more || final != RCU_OP_COPY;
+      const bool want_op = more || final != RCU_RAW;
+      const bool op_elu = more || final == RCU_RAW_ELU;
+      Buf nxt, an;
+      if (want_raw) nxt = raw(x.H, x.W, x.C);
+      if (want_op) an = operand(x.H, x.W, x.C, 1);
+      conv(a2, p2, 1, false, &cur, want_raw ? &nxt : nullptr, nullptr, want_op ? &an : nullptr, op_elu);   // + block input
       release(a2);
       if (cur_owned) release(cur);
       cur = nxt;
       cur_owned = true;
       a = an;
     }
+    if (final_op) *final_op = a;
     return cur;
   }
 
-  // CRPBlock (layers.py:62-83); releases `hbuf`.
-  Buf crp(const std::string& pre, Buf& hbuf) {
+  // CRPBlock (layers.py:62-83); releases `hbuf`.  *elu_op = ELU(out) operand for the RCU that follows.
+  Buf crp(const std::string& pre, Buf& hbuf, Buf* elu_op) {
     Buf x0 = raw(hbuf.H, hbuf.W, hbuf.C);
     Buf p0 = maxpool(hbuf, true, &x0);                 // x0 = ELU(h); p0 = maxpool(x0)
     release(hbuf);
@@ -448,24 +464,26 @@ struct Builder {
     Buf p1 = maxpool(path1, false, nullptr);
     release(path1);
     Buf x2 = raw(x1.H, x1.W, x1.C);
-    conv(p1, pre + ".convs.1.weight", 1, false, &x1, &x2, nullptr, nullptr, false);
+    *elu_op = operand(x1.H, x1.W, x1.C, 1);
+    conv(p1, pre + ".convs.1.weight", 1, false, &x1, &x2, nullptr, elu_op, true);
     release(p1);
     release(x1);
     return x2;
   }
 
   // RefineBlock (layers.py:214-249) with MSFBlock (layers.py:165-184); inputs are not released.
-  Buf refine(const std::string& pre, std::vector<const Buf*> xs, int features, int outH, int outW, bool start, bool end) {
-    std::vector<Buf> hs;
-    for (size_t i = 0; i < xs.size(); ++i) hs.push_back(rcu(pre + ".adapt_convs." + std::to_string(i), *xs[i], 2));
+  //   in_ops[i] : ELU(xs[i]) operand already emitted by the producer of xs[i] (or null)
+  //   out_op    : if non-null, also emit ELU(out) as an operand for the next refine block's adapt RCU
+  Buf refine(const std::string& pre, std::vector<const Buf*> xs, std::vector<Buf*> in_ops, int features, int outH,
+             int outW, bool start, bool end, Buf* out_op) {
     Buf hsum;
     if (start) {
-      hsum = hs[0];
+      hsum = rcu(pre + ".adapt_convs.0", *xs[0], 2, in_ops[0], RCU_RAW, nullptr);
     } else {
       std::vector<Buf> ms;
-      for (size_t i = 0; i < hs.size(); ++i) {
-        Buf mi = to_operand(hs[i], nullptr, 1, OP_COPY, HALO_CIRC);
-        release(hs[i]);
+      for (size_t i = 0; i < xs.size(); ++i) {
+        Buf mi;                                                 // adapt RCU output directly as the MSF conv operand
+        rcu(pre + ".adapt_convs." + std::to_string(i), *xs[i], 2, in_ops[i], RCU_OP_COPY, &mi);
         Buf si = raw(mi.H, mi.W, features);
         const bool chain = i > 0 && ms[i - 1].H == si.H;       // same resolution: accumulate in the epilogue
         conv(mi, pre + ".msf.convs." + std::to_string(i) + ".weight", 1, true, chain ? &ms[i - 1] : nullptr, &si, nullptr,
@@ -494,9 +512,10 @@ struct Builder {
       }
     }
     tap(pre + ".msf", hsum);
-    Buf c = crp(pre + ".crp", hsum);
+    Buf c_op;
+    Buf c = crp(pre + ".crp", hsum, &c_op);
     tap(pre + ".crp", c);
-    Buf out = rcu(pre + ".output_convs", c, end ? 3 : 1);
+    Buf out = rcu(pre + ".output_convs", c, end ? 3 : 1, &c_op, out_op ? RCU_RAW_ELU : RCU_RAW, out_op);
     release(c);
     tap(pre, out);
     return out;
@@ -512,35 +531,37 @@ struct Builder {
       const float *wg = h->P("begin_conv.weight"), *bs = h->P("begin_conv.bias");
       const int n = N;
       push([=](cudaStream_t s, const float* x, const int64_t*, float*) -> int {
-        begin_conv_kernel<128><<<n * H * (W / 64), 256, 0, s>>>(x, wg, bs, o, n, H, W);
+        begin_conv_kernel<128><<<n * H * (W / 64), 128, 0, s>>>(x, wg, bs, o, n, H, W);
         SDPC_CUDA(cudaGetLastError());
         return SDPC_OK;
       });
     }
     flops += 2.0 * H * W * g * (c.channels + 2) * 9;
     tap("begin_conv", r0);
+    // l*_op / r*_op: ELU(layer) operands emitted by the producing convolution for the refine blocks' RCUs
+    Buf l1_op, l2_op, l3_op, l4_op, r1_op, r2_op, r3_op;
     Buf t = residual_block("res1.0", r0, RES_PLAIN, 0);
     release(r0);
-    Buf l1 = residual_block("res1.1", t, RES_PLAIN, 0);
+    Buf l1 = residual_block("res1.1", t, RES_PLAIN, 0, &l1_op);
     release(t);
     t = residual_block("res2.0", l1, RES_DOWN_POOL, 0);
-    Buf l2 = residual_block("res2.1", t, RES_PLAIN, 0);
+    Buf l2 = residual_block("res2.1", t, RES_PLAIN, 0, &l2_op);
     release(t);
     t = residual_block("res3.0", l2, RES_DILATED, 2);
-    Buf l3 = residual_block("res3.1", t, RES_PLAIN, 2);
+    Buf l3 = residual_block("res3.1", t, RES_PLAIN, 2, &l3_op);
     release(t);
     t = residual_block("res4.0", l3, RES_DILATED, 4);
-    Buf l4 = residual_block("res4.1", t, RES_PLAIN, 4);
+    Buf l4 = residual_block("res4.1", t, RES_PLAIN, 4, &l4_op);
     release(t);
-    Buf r1 = refine("refine1", {&l4}, 2 * g, l4.H, l4.W, true, false);
+    Buf r1 = refine("refine1", {&l4}, {&l4_op}, 2 * g, l4.H, l4.W, true, false, &r1_op);
     release(l4);
-    Buf r2 = refine("refine2", {&l3, &r1}, 2 * g, l3.H, l3.W, false, false);
+    Buf r2 = refine("refine2", {&l3, &r1}, {&l3_op, &r1_op}, 2 * g, l3.H, l3.W, false, false, &r2_op);
     release(l3);
     release(r1);
-    Buf r3 = refine("refine3", {&l2, &r2}, g, l2.H, l2.W, false, false);
+    Buf r3 = refine("refine3", {&l2, &r2}, {&l2_op, &r2_op}, g, l2.H, l2.W, false, false, &r3_op);
     release(l2);
     release(r2);
-    Buf r4 = refine("refine4", {&l1, &r3}, g, l1.H, l1.W, false, true);
+    Buf r4 = refine("refine4", {&l1, &r3}, {&l1_op, &r3_op}, g, l1.H, l1.W, false, true, nullptr);
     release(l1);
     release(r3);
     Buf fin = norm_elu_operand(r4, "normalizer", 1, HALO_ZERO, /*force_fp32=*/true);
@@ -551,8 +572,8 @@ struct Builder {
       const float *wg = h->P("end_conv.weight"), *bs = h->P("end_conv.bias"), *sg = h->P("sigmas");
       const int n = N;
       push([=](cudaStream_t s, const float*, const int64_t* labels, float* out) -> int {
-        const size_t pix = (size_t)n * H * W;
-        end_conv_kernel<128><<<(unsigned)((pix + 7) / 8), 256, 0, s>>>(op, wg, bs, sg, labels, out, n, H, W);
+        const size_t strips = (size_t)n * H * (W / 8);
+        end_conv_kernel<128><<<(unsigned)((strips + 7) / 8), 256, 0, s>>>(op, wg, bs, sg, labels, out, n, H, W);
         SDPC_CUDA(cudaGetLastError());
         return SDPC_OK;
       });
