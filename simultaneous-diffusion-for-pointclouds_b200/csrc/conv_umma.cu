@@ -159,6 +159,23 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const int rem = tile - n * tiles_per_img;
       const int h0 = (rem / g.tiles_w) * g.BH;
       const int w0 = (rem % g.tiles_w) * g.BW;
+      // per-tile, per-lane addressing of the 8 pixels this lane touches in every chunk (hoisted out of the
+      // channel loop): element offsets into the raw tensors and into the padded operand tensor, plus the
+      // deltas to the circular-halo duplicates the pixel owns (0 = none).
+      uint32_t raw_off[8], op_off[8];
+      int32_t dup_w[8], dup_h[8];
+      {
+        const int P = e.op_pad, Wp = g.W + 2 * P, Hp = g.H + 2 * P;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int m = quad * 32 + it * 4 + psub;
+          const int h = h0 + m / g.BW, w = w0 + m % g.BW;
+          raw_off[it] = (uint32_t)((((size_t)n * g.H + h) * g.W + w) * g.Cout);
+          op_off[it] = (uint32_t)((((size_t)n * Hp + h + P) * Wp + w + P) * g.Cout);
+          dup_w[it] = (w < P) ? g.W * g.Cout : ((w >= g.W - P) ? -g.W * g.Cout : 0);
+          dup_h[it] = (h < P) ? g.H * Wp * g.Cout : ((h >= g.H - P) ? -g.H * Wp * g.Cout : 0);
+        }
+      }
       mbar_wait(acc_full + ab, acc_phase);
       __syncwarp();
       tc_fence_after();
@@ -182,39 +199,35 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int ch = c0 + cq * 4;
         float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (e.bias) bias4 = *reinterpret_cast<const float4*>(e.bias + ch);
-        size_t pix[8];
-        int hh[8], ww[8];
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int m = quad * 32 + it * 4 + psub;
-          hh[it] = h0 + m / g.BW;
-          ww[it] = w0 + m % g.BW;
-          pix[it] = (((size_t)n * g.H + hh[it]) * g.W + ww[it]) * g.Cout + ch;
-        }
         float4 res[8];
         if (e.residual) {
+          const float* rp = e.residual + ch;
 #pragma unroll
-          for (int it = 0; it < 8; ++it) res[it] = *reinterpret_cast<const float4*>(e.residual + pix[it]);
+          for (int it = 0; it < 8; ++it) res[it] = *reinterpret_cast<const float4*>(rp + raw_off[it]);
         }
+        float* const acc_p = e.out_acc ? e.out_acc + ch : nullptr;
+        float* const raw_p = e.out_raw ? e.out_raw + ch : nullptr;
+        T* const op_p = e.out_op ? reinterpret_cast<T*>(e.out_op) + ch : nullptr;
+        const bool red = e.op_tf32 != 0;
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
           float4 v = *reinterpret_cast<const float4*>(stg + (it * 4 + psub) * kStgPitch + cq * 4);
           v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
-          if (e.out_acc) *reinterpret_cast<float4*>(e.out_acc + pix[it]) = v;
+          if (acc_p) *reinterpret_cast<float4*>(acc_p + raw_off[it]) = v;
           if (e.residual) { v.x += res[it].x; v.y += res[it].y; v.z += res[it].z; v.w += res[it].w; }
-          if (e.out_raw) *reinterpret_cast<float4*>(e.out_raw + pix[it]) = v;
-          if (e.out_op) {
+          if (raw_p) *reinterpret_cast<float4*>(raw_p + raw_off[it]) = v;
+          if (op_p) {
             float o[4] = {v.x, v.y, v.z, v.w};
             if (e.op_elu) {
-              const bool red = e.op_tf32 != 0;
               o[0] = elu_sel<T>(o[0], red); o[1] = elu_sel<T>(o[1], red); o[2] = elu_sel<T>(o[2], red); o[3] = elu_sel<T>(o[3], red);
             }
-            const int P = e.op_pad, Hp = g.H + 2 * P, Wp = g.W + 2 * P;
-            const HaloPos d = halo_pos(hh[it], ww[it], g.H, g.W, P);
-            for_each_halo_pos(d, [&](int hp, int wp) {
-              store_op4<T>(reinterpret_cast<T*>(e.out_op) + (((size_t)n * Hp + hp) * Wp + wp) * g.Cout + ch, o,
-                           e.op_tf32 != 0);
-            });
+            T* d = op_p + op_off[it];
+            store_op4<T>(d, o, red);
+            if (dup_w[it]) store_op4<T>(d + dup_w[it], o, red);
+            if (dup_h[it]) {
+              store_op4<T>(d + dup_h[it], o, red);
+              if (dup_w[it]) store_op4<T>(d + dup_h[it] + dup_w[it], o, red);
+            }
           }
         }
         __syncwarp();                                        // staging tile is reused by the next chunk
