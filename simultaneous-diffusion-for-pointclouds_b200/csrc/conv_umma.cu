@@ -44,7 +44,12 @@ struct UmmaCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + kBarrierBytes + 4 * kStgFloats * 4;
 };
 
-template <typename T, int N_TILE>
+// SWAP = false: D[pixel (M=128), cout (N=Cout)]      = X_tile . W^T      (Cout = 256 layers)
+// SWAP = true : D[cout  (M=128), pixel (N=256)]      = W . X_tile^T      (Cout = 128 layers)
+//   A 128x128 MMA reads (128+128) rows of operands per 128x128 MACs and is bound by shared-memory
+//   bandwidth; putting the weights on the M side lets a 128-output-channel layer run the same
+//   128x256 instruction shape as the 256-channel layers (256 pixels per tile on the N side).
+template <typename T, int N_TILE, bool SWAP>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const ConvGeom g, const EpiParams e) {
@@ -105,8 +110,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             uint8_t* sa = smem + stage * Cfg::kStageBytes;
             uint8_t* sb = sa + kABytes;
             mbar_arrive_expect_tx(full_bar + stage, Cfg::kStageBytes);
-            tma_load_4d(sa, &tmap_a, full_bar + stage, kc * kBK, w0 + g.in_pad + dx, h0 + g.in_pad + dy, n);
-            tma_load_3d(sb, &tmap_b, full_bar + stage, kc * kBK, 0, tap);
+            // activations and weights land in the M-side (128 rows) or N-side (N_TILE rows) slot
+            tma_load_4d(SWAP ? sb : sa, &tmap_a, full_bar + stage, kc * kBK, w0 + g.in_pad + dx, h0 + g.in_pad + dy, n);
+            tma_load_3d(SWAP ? sa : sb, &tmap_b, full_bar + stage, kc * kBK, 0, tap);
             if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
           }
         }
@@ -159,22 +165,21 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const int rem = tile - n * tiles_per_img;
       const int h0 = (rem / g.tiles_w) * g.BH;
       const int w0 = (rem % g.tiles_w) * g.BW;
-      // per-tile, per-lane addressing of the 8 pixels this lane touches in every chunk (hoisted out of the
-      // channel loop): element offsets into the raw tensors and into the padded operand tensor, plus the
-      // deltas to the circular-halo duplicates the pixel owns (0 = none).
+      // element offsets of a tile pixel m into the raw tensors / the padded operand tensor, plus the deltas to
+      // the circular-halo duplicates it owns (0 = none).  BW is a power of two (g.bw_shift).
+      const int P = e.op_pad, Wp = g.W + 2 * P, Hp = g.H + 2 * P;
+      auto pixel_offsets = [&](int m, uint32_t& ro, uint32_t& oo, int32_t& dw, int32_t& dh) {
+        const int h = h0 + (m >> g.bw_shift), w = w0 + (m & (g.BW - 1));
+        ro = (uint32_t)((((size_t)n * g.H + h) * g.W + w) * g.Cout);
+        oo = (uint32_t)((((size_t)n * Hp + h + P) * Wp + w + P) * g.Cout);
+        dw = (w < P) ? g.W * g.Cout : ((w >= g.W - P) ? -g.W * g.Cout : 0);
+        dh = (h < P) ? g.H * Wp * g.Cout : ((h >= g.H - P) ? -g.H * Wp * g.Cout : 0);
+      };
       uint32_t raw_off[8], op_off[8];
       int32_t dup_w[8], dup_h[8];
-      {
-        const int P = e.op_pad, Wp = g.W + 2 * P, Hp = g.H + 2 * P;
+      if constexpr (!SWAP) {                                 // lane's 8 pixels are the same for every channel chunk
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int m = quad * 32 + it * 4 + psub;
-          const int h = h0 + m / g.BW, w = w0 + m % g.BW;
-          raw_off[it] = (uint32_t)((((size_t)n * g.H + h) * g.W + w) * g.Cout);
-          op_off[it] = (uint32_t)((((size_t)n * Hp + h + P) * Wp + w + P) * g.Cout);
-          dup_w[it] = (w < P) ? g.W * g.Cout : ((w >= g.W - P) ? -g.W * g.Cout : 0);
-          dup_h[it] = (h < P) ? g.H * Wp * g.Cout : ((h >= g.H - P) ? -g.H * Wp * g.Cout : 0);
-        }
+        for (int it = 0; it < 8; ++it) pixel_offsets(quad * 32 + it * 4 + psub, raw_off[it], op_off[it], dup_w[it], dup_h[it]);
       }
       mbar_wait(acc_full + ab, acc_phase);
       __syncwarp();
@@ -190,13 +195,24 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           __syncwarp();
           if (lane == 0) mbar_arrive(acc_empty + ab);
         }
+        int ch;
+        if constexpr (!SWAP) {
+          // thread = pixel, registers = 32 channels: rows of the staging tile are pixels
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<float4*>(stg + lane * kStgPitch + j * 4) =
-              make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
-                          __uint_as_float(r[4 * j + 3]));
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(stg + lane * kStgPitch + j * 4) =
+                make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                            __uint_as_float(r[4 * j + 3]));
+          ch = c0 + cq * 4;
+        } else {
+          // thread = output channel (quad*32 + lane), registers = 32 pixels: write the transpose
+#pragma unroll
+          for (int j = 0; j < 32; ++j) stg[j * kStgPitch + lane] = __uint_as_float(r[j]);
+          ch = quad * 32 + cq * 4;
+#pragma unroll
+          for (int it = 0; it < 8; ++it) pixel_offsets(c0 + it * 4 + psub, raw_off[it], op_off[it], dup_w[it], dup_h[it]);
+        }
         __syncwarp();
-        const int ch = c0 + cq * 4;
         float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (e.bias) bias4 = *reinterpret_cast<const float4*>(e.bias + ch);
         float4 res[8];
@@ -281,31 +297,34 @@ int make_tmap(CUtensorMap* out, void* base, int elem_bytes, int rank, const uint
   return SDPC_OK;
 }
 
-template <typename T, int N_TILE>
+template <typename T, int N_TILE, bool SWAP>
 static int launch_t(const UmmaConvLaunch& L, cudaStream_t stream) {
   using Cfg = UmmaCfg<N_TILE>;
   static bool attr_set = false;
   if (!attr_set) {
-    SDPC_CUDA(cudaFuncSetAttribute(conv_umma_kernel<T, N_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    SDPC_CUDA(cudaFuncSetAttribute(conv_umma_kernel<T, N_TILE, SWAP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    Cfg::kSmemBytes));
     attr_set = true;
   }
   int grid = L.geom.num_tiles < L.num_sms ? L.geom.num_tiles : L.num_sms;
-  conv_umma_kernel<T, N_TILE><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(L.tmap_a, L.tmap_b, L.geom, L.epi);
+  conv_umma_kernel<T, N_TILE, SWAP><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(L.tmap_a, L.tmap_b, L.geom, L.epi);
   SDPC_CUDA(cudaGetLastError());
   return SDPC_OK;
 }
 
+// tile_pixels(Cout): pixels per tile the kernel variant for this Cout uses (the host builds the TMA box from it)
+int conv_umma_tile_pixels(int Cout) { return Cout == 128 ? 256 : 128; }
+
 int conv_umma_launch(const UmmaConvLaunch& L, cudaStream_t stream) {
   const ConvGeom& g = L.geom;
   const int bk = 128 / L.elem_bytes;
-  if (g.BW * g.BH != kTileM || g.Cin % bk != 0 || (g.Cout != 128 && g.Cout != 256))
+  if (g.BW * g.BH != conv_umma_tile_pixels(g.Cout) || (1 << g.bw_shift) != g.BW || g.Cin % bk != 0 ||
+      (g.Cout != 128 && g.Cout != 256))
     return set_error(SDPC_ERR_UNSUPPORTED, "conv_umma: unsupported shape Cin=%d Cout=%d tile=%dx%d", g.Cin, g.Cout,
                      g.BH, g.BW);
-  if (L.elem_bytes == 2) {
-    return g.Cout == 256 ? launch_t<__nv_bfloat16, 256>(L, stream) : launch_t<__nv_bfloat16, 128>(L, stream);
-  }
-  return g.Cout == 256 ? launch_t<float, 256>(L, stream) : launch_t<float, 128>(L, stream);
+  if (L.elem_bytes == 2)
+    return g.Cout == 256 ? launch_t<__nv_bfloat16, 256, false>(L, stream) : launch_t<__nv_bfloat16, 256, true>(L, stream);
+  return g.Cout == 256 ? launch_t<float, 256, false>(L, stream) : launch_t<float, 256, true>(L, stream);
 }
 
 }  // namespace sdpc

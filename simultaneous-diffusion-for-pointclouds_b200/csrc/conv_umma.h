@@ -20,5 +20,6 @@ struct UmmaConvLaunch {
 // rank-`rank` tiled tensor map with 128-byte swizzle; dims/box innermost first.
 int make_tmap(CUtensorMap* out, void* base, int elem_bytes, int rank, const uint64_t* dims, const uint32_t* box);
 int conv_umma_launch(const UmmaConvLaunch& L, cudaStream_t stream);
+int conv_umma_tile_pixels(int Cout);   // 128 (Cout = 256) or 256 (Cout = 128, swapped operands)
 
 }  // namespace sdpc

@@ -215,61 +215,83 @@ zero_halo_kernel(T* __restrict__ out, int N, int H, int W, int C, int P) {
 // CRP stage (layers.py:76-83): out_op = [ELU](maxpool5(in)) with circular halo for the conv that
 // follows; MaxPool2d(5,1,2) itself pads with -inf, i.e. the window is clipped at the image border.
 // ELU is monotone, so ELU(maxpool(x)) == maxpool(ELU(x)).  Optionally also emits x0 = ELU(in).
+constexpr int kPoolRows = 8;      // output rows per thread (rolling 5-row window)
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 maxpool5_kernel(const float* __restrict__ in, float* __restrict__ x0_out, T* __restrict__ out, int N, int H, int W,
                 int C, int P, int elu_in, int tf32) {
-  // one thread: 8 channels x 4 consecutive output pixels of a row.  Column maxima over the (clipped)
-  // 5 rows are formed once for the 8 columns the strip needs, then combined 5 at a time.
-  const int C8 = C / 8, W4 = W / 4;
-  const size_t total = (size_t)N * H * W4 * C8;
+  // One thread: 8 channels x 2 adjacent columns x kPoolRows output rows.  For every input row of the band
+  // (kPoolRows + 4 rows) it loads the 6 columns the two outputs need once, reduces them to two horizontal
+  // 5-maxima and keeps the last five such rows in a register ring; an output is the max over the ring.
+  // Each input element is fetched (kPoolRows+4)/kPoolRows * 3 = 4.5 times instead of 25.
+  const int C8 = C / 8, W2 = W / 2, HB = H / kPoolRows;
+  const size_t total = (size_t)N * HB * W2 * C8;
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int c8 = (int)(i % C8);
   size_t t = i / C8;
-  const int w0 = (int)(t % W4) * 4; t /= W4;
-  const int h = (int)(t % H);
-  const int n = (int)(t / H);
-  const int h_lo = max(h - 2, 0), h_hi = min(h + 2, H - 1);
-  float cm[8][8];                                        // [column w0-2+j][channel]
-#pragma unroll
-  for (int j = 0; j < 8; ++j)
-#pragma unroll
-    for (int k = 0; k < 8; ++k) cm[j][k] = -INFINITY;
-  for (int hh = h_lo; hh <= h_hi; ++hh) {
-    const float* row = in + (((size_t)n * H + hh) * W) * C + c8 * 8;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int ww = w0 - 2 + j;
-      if (ww >= 0 && ww < W) {
-        const float4 a = *reinterpret_cast<const float4*>(row + (size_t)ww * C);
-        const float4 b = *reinterpret_cast<const float4*>(row + (size_t)ww * C + 4);
-        cm[j][0] = fmaxf(cm[j][0], a.x); cm[j][1] = fmaxf(cm[j][1], a.y); cm[j][2] = fmaxf(cm[j][2], a.z);
-        cm[j][3] = fmaxf(cm[j][3], a.w); cm[j][4] = fmaxf(cm[j][4], b.x); cm[j][5] = fmaxf(cm[j][5], b.y);
-        cm[j][6] = fmaxf(cm[j][6], b.z); cm[j][7] = fmaxf(cm[j][7], b.w);
-      }
-    }
-  }
+  const int w0 = (int)(t % W2) * 2; t /= W2;
+  const int h0 = (int)(t % HB) * kPoolRows;
+  const int n = (int)(t / HB);
   const int Hp = H + 2 * P, Wp = W + 2 * P;
+  const bool red = tf32 != 0;
+  float hm[5][2][8];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    float m[8];
+  for (int rr = 0; rr < kPoolRows + 4; ++rr) {
+    const int hh = h0 - 2 + rr;
+    const int slot = rr % 5;
+    if (hh >= 0 && hh < H) {
+      const float* row = in + (((size_t)n * H + hh) * W) * C + c8 * 8;
+      float col[6][8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      m[k] = fmaxf(fmaxf(fmaxf(cm[j][k], cm[j + 1][k]), fmaxf(cm[j + 2][k], cm[j + 3][k])), cm[j + 4][k]);
-      if (elu_in) m[k] = elu_sel<T>(m[k], tf32 != 0);
+      for (int j = 0; j < 6; ++j) {
+        const int ww = w0 - 2 + j;
+        if (ww >= 0 && ww < W) {
+          const float4 a = *reinterpret_cast<const float4*>(row + (size_t)ww * C);
+          const float4 b = *reinterpret_cast<const float4*>(row + (size_t)ww * C + 4);
+          col[j][0] = a.x; col[j][1] = a.y; col[j][2] = a.z; col[j][3] = a.w;
+          col[j][4] = b.x; col[j][5] = b.y; col[j][6] = b.z; col[j][7] = b.w;
+        } else {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) col[j][k] = -INFINITY;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float mid = fmaxf(fmaxf(col[1][k], col[2][k]), fmaxf(col[3][k], col[4][k]));
+        hm[slot][0][k] = fmaxf(mid, col[0][k]);
+        hm[slot][1][k] = fmaxf(mid, col[5][k]);
+      }
+      if (x0_out && rr >= 2 && rr < kPoolRows + 2) {        // hh is one of this thread's output rows: x0 = ELU(in)
+#pragma unroll
+        for (int p2 = 0; p2 < 2; ++p2) {
+          float* d = x0_out + (((size_t)n * H + hh) * W + w0 + p2) * C + c8 * 8;
+          *reinterpret_cast<float4*>(d) = make_float4(elu_sel<T>(col[2 + p2][0], red), elu_sel<T>(col[2 + p2][1], red),
+                                                      elu_sel<T>(col[2 + p2][2], red), elu_sel<T>(col[2 + p2][3], red));
+          *reinterpret_cast<float4*>(d + 4) = make_float4(elu_sel<T>(col[2 + p2][4], red), elu_sel<T>(col[2 + p2][5], red),
+                                                          elu_sel<T>(col[2 + p2][6], red), elu_sel<T>(col[2 + p2][7], red));
+        }
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) hm[slot][0][k] = hm[slot][1][k] = -INFINITY;
     }
-    const int w = w0 + j;
-    const HaloPos d = halo_pos(h, w, H, W, P);
-    for_each_halo_pos(d, [&](int hp, int wp) {
-      store_op8<T>(out + (((size_t)n * Hp + hp) * Wp + wp) * C + c8 * 8, m, tf32 != 0);
-    });
-    if (x0_out) {
-      const size_t o = (((size_t)n * H + h) * W + w) * C + c8 * 8;
-      const float4 a = *reinterpret_cast<const float4*>(in + o), b = *reinterpret_cast<const float4*>(in + o + 4);
-      const bool red = tf32 != 0;
-      *reinterpret_cast<float4*>(x0_out + o) = make_float4(elu_sel<T>(a.x, red), elu_sel<T>(a.y, red), elu_sel<T>(a.z, red), elu_sel<T>(a.w, red));
-      *reinterpret_cast<float4*>(x0_out + o + 4) = make_float4(elu_sel<T>(b.x, red), elu_sel<T>(b.y, red), elu_sel<T>(b.z, red), elu_sel<T>(b.w, red));
+    if (rr >= 4) {
+      const int h = h0 + rr - 4;
+#pragma unroll
+      for (int p2 = 0; p2 < 2; ++p2) {
+        float m[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          m[k] = fmaxf(fmaxf(fmaxf(hm[0][p2][k], hm[1][p2][k]), fmaxf(hm[2][p2][k], hm[3][p2][k])), hm[4][p2][k]);
+          if (elu_in) m[k] = elu_sel<T>(m[k], red);
+        }
+        const HaloPos d = halo_pos(h, w0 + p2, H, W, P);
+        for_each_halo_pos(d, [&](int hp, int wp) {
+          store_op8<T>(out + (((size_t)n * Hp + hp) * Wp + wp) * C + c8 * 8, m, red);
+        });
+      }
     }
   }
 }

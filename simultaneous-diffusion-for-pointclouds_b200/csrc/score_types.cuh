@@ -15,7 +15,8 @@ struct ConvGeom {
   int taps;           // 9 (3x3) or 1 (1x1)
   int dil;            // dilation of the 3x3
   int in_pad;         // halo of the input operand (>= dil for 3x3)
-  int BW, BH;         // pixel tile: BH rows x BW columns, BW*BH == tile M
+  int BW, BH;         // pixel tile: BH rows x BW columns (BW a power of two, BW*BH = pixels per tile)
+  int bw_shift;       // log2(BW)
   int tiles_w, tiles_h, num_tiles;
 };
 

@@ -275,7 +275,7 @@ struct Builder {
     float* x0 = x0_out ? (float*)x0_out->ptr : nullptr;
     const int n = N, H = x.H, W = x.W, C = x.C;
     const int tf32 = h->cfg.precision == SDPC_PREC_TF32;
-    const size_t total = (size_t)n * H * (W / 4) * (C / 8);
+    const size_t total = (size_t)n * (H / kPoolRows) * (W / 2) * (C / 8);
     void* o = out.ptr;
     const int elem = out.elem, ei = elu_in ? 1 : 0;
     push([=](cudaStream_t s, const float*, const int64_t*, float*) -> int {
@@ -296,8 +296,11 @@ struct Builder {
     if (dry()) return;
     ConvGeom g;
     g.N = N; g.H = in.H; g.W = in.W; g.Cin = cw.Cin; g.Cout = cw.Cout; g.taps = cw.taps; g.dil = dil; g.in_pad = in.pad;
-    g.BW = in.W < 128 ? in.W : 128;
-    g.BH = 128 / g.BW;
+    const int tile_px = (h->cfg.precision == SDPC_PREC_FP32) ? 128 : conv_umma_tile_pixels(cw.Cout);
+    g.BW = in.W < tile_px ? in.W : tile_px;
+    g.BH = tile_px / g.BW;
+    g.bw_shift = 0;
+    while ((1 << g.bw_shift) < g.BW) ++g.bw_shift;
     g.tiles_w = in.W / g.BW;
     g.tiles_h = in.H / g.BH;
     g.num_tiles = N * g.tiles_w * g.tiles_h;
@@ -623,8 +626,8 @@ extern "C" int sdpc_score_create(const sdpc_score_config* cfg, sdpc_score_t** ou
   if (cfg->channels != 2) return set_error(SDPC_ERR_UNSUPPORTED, "channels must be 2");
   if (cfg->ngf != 128) return set_error(SDPC_ERR_UNSUPPORTED, "ngf must be 128 (the only LiDAR configuration)");
   if (cfg->precision < 0 || cfg->precision > 2) return set_error(SDPC_ERR_ARG, "unknown precision %d", cfg->precision);
-  if (cfg->height < 16 || cfg->width < 64 || cfg->width % 64 || cfg->height % 8 || (cfg->width & (cfg->width - 1)))
-    return set_error(SDPC_ERR_UNSUPPORTED, "need H %% 8 == 0, H >= 16, W a power of two >= 64 (got %dx%d)", cfg->height, cfg->width);
+  if (cfg->height < 16 || cfg->width < 64 || cfg->width % 64 || cfg->height % 16 || (cfg->width & (cfg->width - 1)))
+    return set_error(SDPC_ERR_UNSUPPORTED, "need H %% 16 == 0, W a power of two >= 64 (got %dx%d)", cfg->height, cfg->width);
   if (cfg->num_classes <= 0 || cfg->max_views <= 0) return set_error(SDPC_ERR_ARG, "num_classes/max_views must be positive");
   int dev = 0;
   SDPC_CUDA(cudaGetDevice(&dev));
