@@ -29,11 +29,11 @@ using namespace sm100;
 constexpr int kTileM = 128;
 constexpr int kRowBytes = 128;                  // bytes of K per smem row (one swizzle span)
 constexpr int kABytes = kTileM * kRowBytes;     // 16 KiB
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;                  // 2 pipeline warps + 8 epilogue warps
 constexpr int kSmemBudget = 200 * 1024;
 constexpr int kBarrierBytes = 256;
-constexpr int kStgPitch = 36;                   // floats per staged pixel row (32 + 4 pad: conflict-free float4 access)
-constexpr int kStgFloats = 32 * kStgPitch;      // per epilogue warp
+constexpr int kStgFloats = 32 * 32;             // per epilogue warp: 32 pixels x 32 channels, XOR-swizzled float4 slots
+constexpr int kEpiWarps = 8;
 
 template <int N_TILE>
 struct UmmaCfg {
@@ -41,7 +41,7 @@ struct UmmaCfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = kSmemBudget / kStageBytes;          // 4 (N=256) / 6 (N=128)
   static constexpr int kTmemCols = 2 * N_TILE;                       // 512 / 256
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + kBarrierBytes + 4 * kStgFloats * 4;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + kBarrierBytes + kEpiWarps * kStgFloats * 4;
 };
 
 // SWAP = false: D[pixel (M=128), cout (N=Cout)]      = X_tile . W^T      (Cout = 256 layers)
@@ -76,7 +76,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
     for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, kEpiWarps); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -148,15 +148,19 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
     }
   } else {
-    // ------------------------------------------------------------ epilogue (warps 2..5)
-    // TMEM gives each thread one pixel (lane) x 32 channels.  Storing that directly would touch 32
-    // different 128-byte lines per instruction with 16 useful bytes each; instead every 32x32 chunk is
-    // transposed through a padded shared-memory tile so that 8 consecutive lanes cover one pixel's
+    // ------------------------------------------------------------ epilogue (warps 2..9)
+    // Eight warps: two per TMEM lane quadrant (a warp may only read lanes 32*(warp%4)..+31), taking the even
+    // and the odd 32-column chunks of the accumulator.  TMEM hands a thread one row x 32 columns; storing that
+    // directly would touch 32 different 128-byte lines per instruction.  Every 32x32 chunk is therefore
+    // transposed through an XOR-swizzled shared-memory tile so that 8 consecutive lanes cover one pixel's
     // 128 contiguous bytes: all global loads (residual) and stores (raw / operand) are line-coalesced.
     const int quad = warp & 3;                               // TMEM lane quadrant this warp may read
+    const int half = (warp - 2) >> 2;                        // 0: even chunks, 1: odd chunks
     float* stg = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes + kBarrierBytes) + (warp - 2) * kStgFloats;
     const int cq = lane & 7;                                 // channel quad within the 32-channel chunk
     const int psub = lane >> 3;                              // pixel within a group of 4
+    // staging tile: 32 rows (pixels) x 8 float4 (32 channels); float4 slot of (row, c4) = row*8 + (c4 ^ (row & 7))
+    auto stg_slot = [](int row, int c4) { return (row << 3) + (c4 ^ (row & 7)); };
     int local = 0;
     for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++local) {
       const int ab = local & 1;
@@ -186,48 +190,52 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + ab * N_TILE;
 #pragma unroll 1
-      for (int c0 = 0; c0 < N_TILE; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32(t_addr + c0, r);
-        tmem_ld_wait();
-        if (c0 + 32 == N_TILE) {                             // accumulator fully read: hand it back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(acc_empty + ab);
-        }
+      for (int c0 = half * 32; c0 < N_TILE; c0 += 64) {
         int ch;
         if constexpr (!SWAP) {
-          // thread = pixel, registers = 32 channels: rows of the staging tile are pixels
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<float4*>(stg + lane * kStgPitch + j * 4) =
-                make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
-                            __uint_as_float(r[4 * j + 3]));
           ch = c0 + cq * 4;
         } else {
-          // thread = output channel (quad*32 + lane), registers = 32 pixels: write the transpose
-#pragma unroll
-          for (int j = 0; j < 32; ++j) stg[j * kStgPitch + lane] = __uint_as_float(r[j]);
           ch = quad * 32 + cq * 4;
 #pragma unroll
           for (int it = 0; it < 8; ++it) pixel_offsets(c0 + it * 4 + psub, raw_off[it], op_off[it], dup_w[it], dup_h[it]);
         }
-        __syncwarp();
-        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (e.bias) bias4 = *reinterpret_cast<const float4*>(e.bias + ch);
+        // issue the residual loads first: their latency overlaps the TMEM read and the staging round trip
         float4 res[8];
         if (e.residual) {
           const float* rp = e.residual + ch;
 #pragma unroll
           for (int it = 0; it < 8; ++it) res[it] = *reinterpret_cast<const float4*>(rp + raw_off[it]);
         }
+        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (e.bias) bias4 = *reinterpret_cast<const float4*>(e.bias + ch);
+        uint32_t r[32];
+        tmem_ld_32x32(t_addr + c0, r);
+        tmem_ld_wait();
+        if (c0 + 64 >= N_TILE) {                             // this warp's last chunk: its part of the accumulator is read
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(acc_empty + ab);
+        }
+        float4* stg4 = reinterpret_cast<float4*>(stg);
+        if constexpr (!SWAP) {
+          // thread = pixel (row = lane), registers = 32 channels
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            stg4[stg_slot(lane, j)] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                                  __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+        } else {
+          // thread = output channel (column = lane), registers = 32 pixels: write the transpose
+#pragma unroll
+          for (int j = 0; j < 32; ++j) stg[stg_slot(j, lane >> 2) * 4 + (lane & 3)] = __uint_as_float(r[j]);
+        }
+        __syncwarp();
         float* const acc_p = e.out_acc ? e.out_acc + ch : nullptr;
         float* const raw_p = e.out_raw ? e.out_raw + ch : nullptr;
         T* const op_p = e.out_op ? reinterpret_cast<T*>(e.out_op) + ch : nullptr;
         const bool red = e.op_tf32 != 0;
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
-          float4 v = *reinterpret_cast<const float4*>(stg + (it * 4 + psub) * kStgPitch + cq * 4);
+          float4 v = stg4[stg_slot(it * 4 + psub, cq)];
           v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
           if (acc_p) *reinterpret_cast<float4*>(acc_p + raw_off[it]) = v;
           if (e.residual) { v.x += res[it].x; v.y += res[it].y; v.z += res[it].z; v.w += res[it].w; }
