@@ -185,6 +185,28 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
         for (int it = 0; it < 8; ++it) pixel_offsets(quad * 32 + it * 4 + psub, raw_off[it], op_off[it], dup_w[it], dup_h[it]);
       }
+      // fused InstanceNorm++ statistics of the value written to out_raw: per lane 4 channels, summed over the
+      // lane's pixels, then over the 4 lanes sharing a channel quad, then one fp64 atomic per channel.
+      float ssum[4] = {0.f, 0.f, 0.f, 0.f}, ssq[4] = {0.f, 0.f, 0.f, 0.f};
+      auto flush_stats = [&](int ch) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          ssum[k] += __shfl_xor_sync(0xffffffffu, ssum[k], 8);
+          ssq[k] += __shfl_xor_sync(0xffffffffu, ssq[k], 8);
+          ssum[k] += __shfl_xor_sync(0xffffffffu, ssum[k], 16);
+          ssq[k] += __shfl_xor_sync(0xffffffffu, ssq[k], 16);
+        }
+        if (psub == 0) {
+          double* sp = e.stats + ((size_t)n * g.Cout + ch) * 2;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            atomicAdd(sp + 2 * k, (double)ssum[k]);
+            atomicAdd(sp + 2 * k + 1, (double)ssq[k]);
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) ssum[k] = ssq[k] = 0.f;
+      };
       mbar_wait(acc_full + ab, acc_phase);
       __syncwarp();
       tc_fence_after();
@@ -240,6 +262,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           if (acc_p) *reinterpret_cast<float4*>(acc_p + raw_off[it]) = v;
           if (e.residual) { v.x += res[it].x; v.y += res[it].y; v.z += res[it].z; v.w += res[it].w; }
           if (raw_p) *reinterpret_cast<float4*>(raw_p + raw_off[it]) = v;
+          if (e.stats) {
+            ssum[0] += v.x; ssum[1] += v.y; ssum[2] += v.z; ssum[3] += v.w;
+            ssq[0] = fmaf(v.x, v.x, ssq[0]); ssq[1] = fmaf(v.y, v.y, ssq[1]);
+            ssq[2] = fmaf(v.z, v.z, ssq[2]); ssq[3] = fmaf(v.w, v.w, ssq[3]);
+          }
           if (op_p) {
             float o[4] = {v.x, v.y, v.z, v.w};
             if (e.op_elu) {
@@ -254,8 +281,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             }
           }
         }
+        if constexpr (!SWAP) { if (e.stats) flush_stats(ch); }     // every chunk covers different channels
         __syncwarp();                                        // staging tile is reused by the next chunk
       }
+      if constexpr (SWAP) { if (e.stats) flush_stats(quad * 32 + cq * 4); }   // chunks were pixels of the same channels
     }
   }
 

@@ -8,6 +8,8 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include <stdlib.h>
+
 #include <functional>
 #include <map>
 #include <string>
@@ -52,6 +54,18 @@ struct Plan {
   size_t stats_off = 0, stats_bytes = 0;
   int n_kernels = 0;          // kernels (and memsets) one forward launches
   double umma_flops = 0.0;    // 2*M*N*K summed over the tensor-core convolution launches
+  // fixed staging buffers inside the workspace so that the launch sequence can be replayed as a CUDA graph
+  float* x_in = nullptr;
+  int64_t* labels_in = nullptr;
+  float* out_buf = nullptr;
+  size_t io_bytes = 0;
+  int eager_runs = 0;
+  cudaGraphExec_t graph_exec = nullptr;
+  void reset_graph() {
+    if (graph_exec) cudaGraphExecDestroy(graph_exec);
+    graph_exec = nullptr;
+    eager_runs = 0;
+  }
 };
 
 }  // namespace sdpc
@@ -62,6 +76,8 @@ struct sdpc_score {
   sdpc_score_config cfg;
   int num_sms = 148;
   bool keep_all = false;
+  bool use_graph = true;      // replay the forward as a CUDA graph (cfg.reserved bit 1 or SDPC_NO_GRAPH=1 disables)
+  cudaStream_t cap_stream = nullptr;
   std::vector<ParamSlot> params;
   std::map<std::string, int> index;
   std::map<std::string, ConvW> convs;
@@ -212,10 +228,19 @@ struct Builder {
   // ---- norm: statistics + coefficients -------------------------------------------------
   size_t stats_cursor = 0;
   struct NormRef { size_t stats_off, coef_off; };
-  NormRef norm(const Buf& x, const std::string& pre) {
+  // slot for [N][C][2] doubles; a convolution epilogue can fill it (fused statistics) instead of stats_kernel
+  struct StatsRef { size_t off = (size_t)-1; bool valid() const { return off != (size_t)-1; } };
+  StatsRef new_stats(int C) {
+    StatsRef r;
+    r.off = stats_cursor;
+    stats_cursor += al((size_t)N * C * 2 * sizeof(double));
+    return r;
+  }
+  bool can_fuse_stats() const { return h->cfg.precision != SDPC_PREC_FP32; }
+  NormRef norm(const Buf& x, const std::string& pre, const StatsRef* have = nullptr) {
     NormRef r;
-    r.stats_off = stats_cursor;
-    stats_cursor += al((size_t)N * x.C * 2 * sizeof(double));
+    const bool fused = have && have->valid();
+    r.stats_off = fused ? have->off : new_stats(x.C).off;
     r.coef_off = stats_cursor;
     stats_cursor += al((size_t)N * x.C * 3 * sizeof(float));
     if (dry()) return r;
@@ -233,12 +258,14 @@ struct Builder {
     const float *al_ = h->P(pre + ".alpha"), *ga = h->P(pre + ".gamma"), *be = h->P(pre + ".beta");
     const int n = N;
     push([=](cudaStream_t s, const float*, const int64_t*, float*) -> int {
-      stats_kernel<<<dim3(chunks, n), 256, smem, s>>>(in, stats, HW, C, ppb);
-      SDPC_CUDA(cudaGetLastError());
+      if (!fused) {
+        stats_kernel<<<dim3(chunks, n), 256, smem, s>>>(in, stats, HW, C, ppb);
+        SDPC_CUDA(cudaGetLastError());
+      }
       norm_finalize_kernel<<<n, C, 0, s>>>(stats, al_, ga, be, coef, HW, C);
       SDPC_CUDA(cudaGetLastError());
       return SDPC_OK;
-    }, 2);
+    }, fused ? 1 : 2);
     return r;
   }
   const float* coef_ptr(const NormRef& r) const { return dry() ? nullptr : (const float*)(base + plan->stats_off + r.coef_off); }
@@ -290,7 +317,8 @@ struct Builder {
   // ---- convolution ----------------------------------------------------------------------
   // in: operand with halo (>= dil); epilogue pointers taken from the given buffers.
   void conv(const Buf& in, const std::string& wname, int dil, bool use_bias, const Buf* residual, Buf* out_raw,
-            Buf* out_acc, Buf* out_op, bool op_elu) {
+            Buf* out_acc, Buf* out_op, bool op_elu, StatsRef* stats_out = nullptr) {
+    if (stats_out) *stats_out = (can_fuse_stats() && out_raw) ? new_stats(h->convs.at(wname).Cout) : StatsRef();
     const ConvW& cw = h->convs.at(wname);
     flops += 2.0 * (double)in.H * in.W * cw.Cout * cw.Cin * cw.taps;
     if (dry()) return;
@@ -313,6 +341,7 @@ struct Builder {
     e.op_pad = out_op ? out_op->pad : 0;
     e.op_elu = op_elu ? 1 : 0;
     e.op_tf32 = h->cfg.precision == SDPC_PREC_TF32;
+    e.stats = (stats_out && stats_out->valid()) ? (double*)(base + plan->stats_off + stats_out->off) : nullptr;
     if (cw.taps == 9 && in.pad < dil) { status = set_error(SDPC_ERR_STATE, "plan: halo %d < dilation %d for %s", in.pad, dil, wname.c_str()); return; }
     if (h->cfg.precision == SDPC_PREC_FP32) {
       const float* inp = (const float*)in.ptr;
@@ -352,14 +381,18 @@ struct Builder {
   }
 
   // ---- blocks ---------------------------------------------------------------------------
-  Buf norm_elu_operand(const Buf& x, const std::string& npre, int pad, int halo, bool force_fp32 = false) {
-    NormRef r = norm(x, npre);
+  Buf norm_elu_operand(const Buf& x, const std::string& npre, int pad, int halo, bool force_fp32 = false,
+                       const StatsRef* have = nullptr) {
+    NormRef r = norm(x, npre, have);
     return to_operand(x, coef_ptr(r), pad, OP_NORM_ELU, halo, force_fp32);
   }
 
   // ResidualBlock (layers.py:401-456); does not release `x`.  If `elu_op` is given (plain / dilated blocks),
   // the last convolution's epilogue also emits ELU(out) as an operand with halo 1 for the RCU that reads it.
-  Buf residual_block(const std::string& pre, const Buf& x, ResKind kind, int dil, Buf* elu_op = nullptr) {
+  //   x_stats   : statistics of `x` already accumulated by its producer (or null -> stats_kernel)
+  //   out_stats : receives the slot the last convolution fills with the statistics of the block output
+  Buf residual_block(const std::string& pre, const Buf& x, ResKind kind, int dil, Buf* elu_op = nullptr,
+                     const StatsRef* x_stats = nullptr, StatsRef* out_stats = nullptr) {
     const int d = dil ? dil : 1;
     Buf sc;                                             // shortcut branch (raw)
     if (kind == RES_DILATED) {
@@ -368,13 +401,14 @@ struct Builder {
       conv(xs, pre + ".shortcut.weight", d, true, nullptr, &sc, nullptr, nullptr, false);
       release(xs);
     }
-    Buf a1 = norm_elu_operand(x, pre + ".normalize1", d, HALO_CIRC);
+    Buf a1 = norm_elu_operand(x, pre + ".normalize1", d, HALO_CIRC, false, x_stats);
     Buf t1 = raw(x.H, x.W, h->convs.at(pre + ".conv1.weight").Cout);
-    conv(a1, pre + ".conv1.weight", d, true, nullptr, &t1, nullptr, nullptr, false);
+    StatsRef t1_stats;
+    conv(a1, pre + ".conv1.weight", d, true, nullptr, &t1, nullptr, nullptr, false, &t1_stats);
     release(a1);
     Buf out;
     if (kind == RES_DOWN_POOL) {
-      Buf a2 = norm_elu_operand(t1, pre + ".normalize2", 1, HALO_ZERO);
+      Buf a2 = norm_elu_operand(t1, pre + ".normalize2", 1, HALO_ZERO, false, &t1_stats);
       release(t1);
       const int co = h->convs.at(pre + ".conv2.conv.weight").Cout;
       Buf t2 = raw(x.H, x.W, co);
@@ -391,11 +425,11 @@ struct Builder {
       release(t2);
       release(s2);
     } else {
-      Buf a2 = norm_elu_operand(t1, pre + ".normalize2", d, HALO_CIRC);
+      Buf a2 = norm_elu_operand(t1, pre + ".normalize2", d, HALO_CIRC, false, &t1_stats);
       release(t1);
       out = raw(x.H, x.W, h->convs.at(pre + ".conv2.weight").Cout);
       if (elu_op) *elu_op = operand(out.H, out.W, out.C, 1);
-      conv(a2, pre + ".conv2.weight", d, true, kind == RES_DILATED ? &sc : &x, &out, nullptr, elu_op, true);
+      conv(a2, pre + ".conv2.weight", d, true, kind == RES_DILATED ? &sc : &x, &out, nullptr, elu_op, true, out_stats);
       release(a2);
       if (kind == RES_DILATED) release(sc);
     }
@@ -427,7 +461,7 @@ struct Builder {
   //              RCU_OP_COPY -> only *final_op = out as an operand (MSF conv input); returns an invalid Buf
   enum { RCU_RAW = 0, RCU_RAW_ELU = 1, RCU_OP_COPY = 2 };
   Buf rcu(const std::string& pre, const Buf& x, int n_blocks, Buf* first_op = nullptr, int final = RCU_RAW,
-          Buf* final_op = nullptr) {
+          Buf* final_op = nullptr, StatsRef* final_stats = nullptr) {
     Buf cur = x;
     bool cur_owned = false;
     Buf a = first_op ? *first_op : to_operand(x, nullptr, 1, OP_ELU, HALO_CIRC);
@@ -444,7 +478,8 @@ struct Builder {
       Buf nxt, an;
       if (want_raw) nxt = raw(x.H, x.W, x.C);
       if (want_op) an = operand(x.H, x.W, x.C, 1);
-      conv(a2, p2, 1, false, &cur, want_raw ? &nxt : nullptr, nullptr, want_op ? &an : nullptr, op_elu);   // + block input
+      conv(a2, p2, 1, false, &cur, want_raw ? &nxt : nullptr, nullptr, want_op ? &an : nullptr, op_elu,
+           more ? nullptr : final_stats);                                                                  // + block input
       release(a2);
       if (cur_owned) release(cur);
       cur = nxt;
@@ -478,7 +513,7 @@ struct Builder {
   //   in_ops[i] : ELU(xs[i]) operand already emitted by the producer of xs[i] (or null)
   //   out_op    : if non-null, also emit ELU(out) as an operand for the next refine block's adapt RCU
   Buf refine(const std::string& pre, std::vector<const Buf*> xs, std::vector<Buf*> in_ops, int features, int outH,
-             int outW, bool start, bool end, Buf* out_op) {
+             int outW, bool start, bool end, Buf* out_op, StatsRef* out_stats = nullptr) {
     Buf hsum;
     if (start) {
       hsum = rcu(pre + ".adapt_convs.0", *xs[0], 2, in_ops[0], RCU_RAW, nullptr);
@@ -518,7 +553,7 @@ struct Builder {
     Buf c_op;
     Buf c = crp(pre + ".crp", hsum, &c_op);
     tap(pre + ".crp", c);
-    Buf out = rcu(pre + ".output_convs", c, end ? 3 : 1, &c_op, out_op ? RCU_RAW_ELU : RCU_RAW, out_op);
+    Buf out = rcu(pre + ".output_convs", c, end ? 3 : 1, &c_op, out_op ? RCU_RAW_ELU : RCU_RAW, out_op, out_stats);
     release(c);
     tap(pre, out);
     return out;
@@ -528,6 +563,13 @@ struct Builder {
   void build() {
     const sdpc_score_config& c = h->cfg;
     const int H = c.height, W = c.width, g = c.ngf;
+    {   // persistent I/O staging (never released): x, labels, out
+      Buf xin = alloc(N, H, W, c.channels, 0, 4), lab = alloc(N, 1, 1, 2, 0, 4), ob = alloc(N, H, W, c.channels, 0, 4);
+      plan->x_in = (float*)xin.ptr;
+      plan->labels_in = (int64_t*)lab.ptr;
+      plan->out_buf = (float*)ob.ptr;
+      plan->io_bytes = (size_t)N * c.channels * H * W * sizeof(float);
+    }
     Buf r0 = raw(H, W, g);
     if (!dry()) {
       float* o = (float*)r0.ptr;
@@ -543,18 +585,19 @@ struct Builder {
     tap("begin_conv", r0);
     // l*_op / r*_op: ELU(layer) operands emitted by the producing convolution for the refine blocks' RCUs
     Buf l1_op, l2_op, l3_op, l4_op, r1_op, r2_op, r3_op;
-    Buf t = residual_block("res1.0", r0, RES_PLAIN, 0);
+    StatsRef st_a, st_b;                               // statistics of the running trunk tensor, filled by its producer
+    Buf t = residual_block("res1.0", r0, RES_PLAIN, 0, nullptr, nullptr, &st_a);
     release(r0);
-    Buf l1 = residual_block("res1.1", t, RES_PLAIN, 0, &l1_op);
+    Buf l1 = residual_block("res1.1", t, RES_PLAIN, 0, &l1_op, &st_a, &st_b);
     release(t);
-    t = residual_block("res2.0", l1, RES_DOWN_POOL, 0);
-    Buf l2 = residual_block("res2.1", t, RES_PLAIN, 0, &l2_op);
+    t = residual_block("res2.0", l1, RES_DOWN_POOL, 0, nullptr, &st_b, nullptr);    // output comes from the pooling kernel
+    Buf l2 = residual_block("res2.1", t, RES_PLAIN, 0, &l2_op, nullptr, &st_a);
     release(t);
-    t = residual_block("res3.0", l2, RES_DILATED, 2);
-    Buf l3 = residual_block("res3.1", t, RES_PLAIN, 2, &l3_op);
+    t = residual_block("res3.0", l2, RES_DILATED, 2, nullptr, &st_a, &st_b);
+    Buf l3 = residual_block("res3.1", t, RES_PLAIN, 2, &l3_op, &st_b, &st_a);
     release(t);
-    t = residual_block("res4.0", l3, RES_DILATED, 4);
-    Buf l4 = residual_block("res4.1", t, RES_PLAIN, 4, &l4_op);
+    t = residual_block("res4.0", l3, RES_DILATED, 4, nullptr, &st_a, &st_b);
+    Buf l4 = residual_block("res4.1", t, RES_PLAIN, 4, &l4_op, &st_b, nullptr);
     release(t);
     Buf r1 = refine("refine1", {&l4}, {&l4_op}, 2 * g, l4.H, l4.W, true, false, &r1_op);
     release(l4);
@@ -564,10 +607,11 @@ struct Builder {
     Buf r3 = refine("refine3", {&l2, &r2}, {&l2_op, &r2_op}, g, l2.H, l2.W, false, false, &r3_op);
     release(l2);
     release(r2);
-    Buf r4 = refine("refine4", {&l1, &r3}, {&l1_op, &r3_op}, g, l1.H, l1.W, false, true, nullptr);
+    StatsRef st_r4;
+    Buf r4 = refine("refine4", {&l1, &r3}, {&l1_op, &r3_op}, g, l1.H, l1.W, false, true, nullptr, &st_r4);
     release(l1);
     release(r3);
-    Buf fin = norm_elu_operand(r4, "normalizer", 1, HALO_ZERO, /*force_fp32=*/true);
+    Buf fin = norm_elu_operand(r4, "normalizer", 1, HALO_ZERO, /*force_fp32=*/true, &st_r4);
     release(r4);
     flops += 2.0 * H * W * c.channels * g * 9;
     if (!dry()) {
@@ -598,6 +642,7 @@ static int build_plan(sdpc_score* h, int n_views, char* ws, size_t ws_bytes, Pla
   char* aligned = (char*)(((uintptr_t)ws + 1023) & ~(uintptr_t)1023);
   plan->ops.clear();
   plan->taps.clear();
+  plan->reset_graph();
   plan->n_kernels = 1;
   plan->umma_flops = 0.0;
   plan->ws = ws;
@@ -639,6 +684,7 @@ extern "C" int sdpc_score_create(const sdpc_score_config* cfg, sdpc_score_t** ou
   h->cfg = *cfg;
   h->num_sms = prop.multiProcessorCount;
   h->keep_all = (cfg->reserved & 1) != 0;
+  h->use_graph = (cfg->reserved & 2) == 0 && getenv("SDPC_NO_GRAPH") == nullptr;
   h->params = inventory(*cfg);
   for (size_t i = 0; i < h->params.size(); ++i) h->index[h->params[i].name] = (int)i;
   *out = h;
@@ -647,6 +693,8 @@ extern "C" int sdpc_score_create(const sdpc_score_config* cfg, sdpc_score_t** ou
 
 extern "C" int sdpc_score_destroy(sdpc_score_t* h) {
   if (!h) return SDPC_OK;
+  h->plan.reset_graph();
+  if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   for (auto& p : h->params) if (p.dev) cudaFree(p.dev);
   for (auto& kv : h->convs) { if (kv.second.w_tc) cudaFree(kv.second.w_tc); if (kv.second.w_simt) cudaFree(kv.second.w_simt); }
   delete h;
@@ -737,8 +785,38 @@ extern "C" int sdpc_score_forward(sdpc_score_t* h, const float* x, const int64_t
     h->plan.bytes = need;
   }
   cudaStream_t stream = (cudaStream_t)stream_;
-  for (auto& op : h->plan.ops)
-    if (int st = op(stream, x, labels, out)) return st;
+  Plan& pl = h->plan;
+  if (!h->use_graph || h->profiling || h->keep_all) {          // eager launches on the caller's buffers
+    for (auto& op : pl.ops)
+      if (int st = op(stream, x, labels, out)) return st;
+  } else {
+    // graph path: the kernels only ever see the fixed staging buffers, so one captured graph serves every call
+    SDPC_CUDA(cudaMemcpyAsync(pl.x_in, x, pl.io_bytes, cudaMemcpyDeviceToDevice, stream));
+    SDPC_CUDA(cudaMemcpyAsync(pl.labels_in, labels, (size_t)n_views * sizeof(int64_t), cudaMemcpyDeviceToDevice, stream));
+    if (!pl.graph_exec && pl.eager_runs < 1) {               // first call: eager (sets function attributes, warms up)
+      for (auto& op : pl.ops)
+        if (int st = op(stream, pl.x_in, pl.labels_in, pl.out_buf)) return st;
+      ++pl.eager_runs;
+    } else {
+      if (!pl.graph_exec) {
+        // capture on a private stream: the caller's stream may be the legacy default stream, which cannot capture
+        if (!h->cap_stream) SDPC_CUDA(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
+        cudaGraph_t graph = nullptr;
+        SDPC_CUDA(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
+        int st = SDPC_OK;
+        for (auto& op : pl.ops)
+          if ((st = op(h->cap_stream, pl.x_in, pl.labels_in, pl.out_buf))) break;
+        cudaError_t ce = cudaStreamEndCapture(h->cap_stream, &graph);
+        if (st) { if (graph) cudaGraphDestroy(graph); return st; }
+        if (ce != cudaSuccess) return set_error(SDPC_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+        ce = cudaGraphInstantiate(&pl.graph_exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ce != cudaSuccess) { pl.graph_exec = nullptr; return set_error(SDPC_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(ce)); }
+      }
+      SDPC_CUDA(cudaGraphLaunch(pl.graph_exec, stream));
+    }
+    SDPC_CUDA(cudaMemcpyAsync(out, pl.out_buf, pl.io_bytes, cudaMemcpyDeviceToDevice, stream));
+  }
   h->last_launches = h->plan.n_kernels;
   return SDPC_OK;
 }
