@@ -186,7 +186,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         for (int it = 0; it < 8; ++it) pixel_offsets(quad * 32 + it * 4 + psub, raw_off[it], op_off[it], dup_w[it], dup_h[it]);
       }
       // fused InstanceNorm++ statistics of the value written to out_raw: per lane 4 channels, summed over the
-      // lane's pixels, then over the 4 lanes sharing a channel quad, then one fp64 atomic per channel.
+      // lane's pixels, then over the 4 lanes sharing a channel quad; the warp's partial goes to its own slot
+      // [tile][part][Cout][2] (no atomics, every slot written exactly once; norm_finalize sums the slots).
       float ssum[4] = {0.f, 0.f, 0.f, 0.f}, ssq[4] = {0.f, 0.f, 0.f, 0.f};
       auto flush_stats = [&](int ch) {
 #pragma unroll
@@ -197,12 +198,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           ssq[k] += __shfl_xor_sync(0xffffffffu, ssq[k], 16);
         }
         if (psub == 0) {
-          double* sp = e.stats + ((size_t)n * g.Cout + ch) * 2;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            atomicAdd(sp + 2 * k, (double)ssum[k]);
-            atomicAdd(sp + 2 * k + 1, (double)ssq[k]);
-          }
+          const int part = SWAP ? half : quad;
+          float* sp = e.stats + (((size_t)tile * (SWAP ? 2 : 4) + part) * g.Cout + ch) * 2;
+          *reinterpret_cast<float4*>(sp) = make_float4(ssum[0], ssq[0], ssum[1], ssq[1]);
+          *reinterpret_cast<float4*>(sp + 4) = make_float4(ssum[2], ssq[2], ssum[3], ssq[3]);
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) ssum[k] = ssq[k] = 0.f;

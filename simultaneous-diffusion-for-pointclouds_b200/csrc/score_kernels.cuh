@@ -99,6 +99,33 @@ stats_kernel(const float* __restrict__ in, double* __restrict__ stats, int HW, i
   }
 }
 
+// Sum the per-tile partial statistics written by the convolution epilogues
+// (parts: [N][parts_per_view][C][2] floats) into stats [N][C][2] doubles.
+// grid (C/32, N), block 256 = 8 part-groups x 32 channels.
+__global__ void __launch_bounds__(256)
+stats_reduce_parts_kernel(const float* __restrict__ parts, double* __restrict__ stats, int parts_per_view, int C) {
+  __shared__ double red[8][32][2];
+  const int cl = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl, n = blockIdx.y;
+  const float2* p = reinterpret_cast<const float2*>(parts) + (size_t)n * parts_per_view * C + c;
+  double S = 0.0, Q = 0.0;
+#pragma unroll 8
+  for (int j = grp; j < parts_per_view; j += 8) {
+    const float2 v = p[(size_t)j * C];
+    S += (double)v.x;
+    Q += (double)v.y;
+  }
+  red[grp][cl][0] = S;
+  red[grp][cl][1] = Q;
+  __syncthreads();
+  if (grp == 0) {
+#pragma unroll
+    for (int k = 1; k < 8; ++k) { S += red[k][cl][0]; Q += red[k][cl][1]; }
+    stats[((size_t)n * C + c) * 2] = S;
+    stats[((size_t)n * C + c) * 2 + 1] = Q;
+  }
+}
+
 // coef[n][c] = {mean, a, b}: out = a*(x-mean) + b with a = gamma*rstd, b = gamma*alpha*mean_n + beta
 __global__ void norm_finalize_kernel(const double* __restrict__ stats, const float* __restrict__ alpha,
                                      const float* __restrict__ gamma, const float* __restrict__ beta,

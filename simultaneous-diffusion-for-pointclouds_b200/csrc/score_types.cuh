@@ -30,7 +30,8 @@ struct EpiParams {
   int op_pad;
   int op_elu;             // 1: ELU before the operand store
   int op_tf32;            // 1: round the fp32 operand to tf32 (rna)
-  double* stats;          // [N][Cout][2] sum / sum of squares of the out_raw values (InstanceNorm++), or null
+  float* stats;           // per-tile partial sums [tile][parts][Cout][2] (sum, sum of squares) of the out_raw
+                          // values for InstanceNorm++ (parts = 4 pixel quadrants, or 2 chunk parities when swapped), or null
 };
 
 __device__ __forceinline__ float elu1(float v) { return v > 0.0f ? v : expm1f(v); }

@@ -228,19 +228,27 @@ struct Builder {
   // ---- norm: statistics + coefficients -------------------------------------------------
   size_t stats_cursor = 0;
   struct NormRef { size_t stats_off, coef_off; };
-  // slot for [N][C][2] doubles; a convolution epilogue can fill it (fused statistics) instead of stats_kernel
-  struct StatsRef { size_t off = (size_t)-1; bool valid() const { return off != (size_t)-1; } };
+  // statistics slot: [N][C][2] doubles filled by stats_kernel (parts_per_view == 0), or per-tile partials
+  // [N][parts_per_view][C][2] floats written by a convolution epilogue (fused statistics)
+  struct StatsRef { size_t off = (size_t)-1; int parts_per_view = 0; bool valid() const { return off != (size_t)-1; } };
   StatsRef new_stats(int C) {
     StatsRef r;
     r.off = stats_cursor;
     stats_cursor += al((size_t)N * C * 2 * sizeof(double));
     return r;
   }
+  StatsRef new_part_stats(int C, int parts_per_view) {
+    StatsRef r;
+    r.off = stats_cursor;
+    r.parts_per_view = parts_per_view;
+    stats_cursor += al((size_t)N * parts_per_view * C * 2 * sizeof(float));
+    return r;
+  }
   bool can_fuse_stats() const { return h->cfg.precision != SDPC_PREC_FP32; }
   NormRef norm(const Buf& x, const std::string& pre, const StatsRef* have = nullptr) {
     NormRef r;
     const bool fused = have && have->valid();
-    r.stats_off = fused ? have->off : new_stats(x.C).off;
+    r.stats_off = new_stats(x.C).off;                     // [N][C][2] doubles (filled by stats_kernel or the reducer)
     r.coef_off = stats_cursor;
     stats_cursor += al((size_t)N * x.C * 3 * sizeof(float));
     if (dry()) return r;
@@ -254,18 +262,19 @@ struct Builder {
     const size_t smem = (size_t)groups * C * 2 * sizeof(double);
     char* sbase = base + plan->stats_off;
     double* stats = (double*)(sbase + r.stats_off);
+    const float* parts = fused ? (const float*)(sbase + have->off) : nullptr;
+    const int ppv = fused ? have->parts_per_view : 0;
     float* coef = (float*)(sbase + r.coef_off);
     const float *al_ = h->P(pre + ".alpha"), *ga = h->P(pre + ".gamma"), *be = h->P(pre + ".beta");
     const int n = N;
     push([=](cudaStream_t s, const float*, const int64_t*, float*) -> int {
-      if (!fused) {
-        stats_kernel<<<dim3(chunks, n), 256, smem, s>>>(in, stats, HW, C, ppb);
-        SDPC_CUDA(cudaGetLastError());
-      }
+      if (!fused) stats_kernel<<<dim3(chunks, n), 256, smem, s>>>(in, stats, HW, C, ppb);
+      else stats_reduce_parts_kernel<<<dim3(C / 32, n), 256, 0, s>>>(parts, stats, ppv, C);
+      SDPC_CUDA(cudaGetLastError());
       norm_finalize_kernel<<<n, C, 0, s>>>(stats, al_, ga, be, coef, HW, C);
       SDPC_CUDA(cudaGetLastError());
       return SDPC_OK;
-    }, fused ? 1 : 2);
+    }, 2);
     return r;
   }
   const float* coef_ptr(const NormRef& r) const { return dry() ? nullptr : (const float*)(base + plan->stats_off + r.coef_off); }
@@ -318,7 +327,15 @@ struct Builder {
   // in: operand with halo (>= dil); epilogue pointers taken from the given buffers.
   void conv(const Buf& in, const std::string& wname, int dil, bool use_bias, const Buf* residual, Buf* out_raw,
             Buf* out_acc, Buf* out_op, bool op_elu, StatsRef* stats_out = nullptr) {
-    if (stats_out) *stats_out = (can_fuse_stats() && out_raw) ? new_stats(h->convs.at(wname).Cout) : StatsRef();
+    if (stats_out) {
+      *stats_out = StatsRef();
+      if (can_fuse_stats() && out_raw) {
+        const int co = h->convs.at(wname).Cout;
+        const int tile_px = conv_umma_tile_pixels(co);
+        const int parts = co == 128 ? 2 : 4;
+        *stats_out = new_part_stats(co, (in.H * in.W / tile_px) * parts);
+      }
+    }
     const ConvW& cw = h->convs.at(wname);
     flops += 2.0 * (double)in.H * in.W * cw.Cout * cw.Cin * cw.taps;
     if (dry()) return;
@@ -341,7 +358,7 @@ struct Builder {
     e.op_pad = out_op ? out_op->pad : 0;
     e.op_elu = op_elu ? 1 : 0;
     e.op_tf32 = h->cfg.precision == SDPC_PREC_TF32;
-    e.stats = (stats_out && stats_out->valid()) ? (double*)(base + plan->stats_off + stats_out->off) : nullptr;
+    e.stats = (stats_out && stats_out->valid()) ? (float*)(base + plan->stats_off + stats_out->off) : nullptr;
     if (cw.taps == 9 && in.pad < dil) { status = set_error(SDPC_ERR_STATE, "plan: halo %d < dilation %d for %s", in.pad, dil, wname.c_str()); return; }
     if (h->cfg.precision == SDPC_PREC_FP32) {
       const float* inp = (const float*)in.ptr;
