@@ -242,83 +242,72 @@ zero_halo_kernel(T* __restrict__ out, int N, int H, int W, int C, int P) {
 // CRP stage (layers.py:76-83): out_op = [ELU](maxpool5(in)) with circular halo for the conv that
 // follows; MaxPool2d(5,1,2) itself pads with -inf, i.e. the window is clipped at the image border.
 // ELU is monotone, so ELU(maxpool(x)) == maxpool(ELU(x)).  Optionally also emits x0 = ELU(in).
-constexpr int kPoolRows = 8;      // output rows per thread (rolling 5-row window)
+constexpr int kPoolTH = 8, kPoolTW = 16, kPoolCB = 32;     // output tile: 8 rows x 16 columns x 32 channels per block
+constexpr int kPoolSmemBytes = ((kPoolTH + 4) + kPoolTH) * (kPoolTW + 4) * (kPoolCB / 4) * 16;
 
 template <typename T>
 __global__ void __launch_bounds__(256)
 maxpool5_kernel(const float* __restrict__ in, float* __restrict__ x0_out, T* __restrict__ out, int N, int H, int W,
                 int C, int P, int elu_in, int tf32) {
-  // One thread: 8 channels x 2 adjacent columns x kPoolRows output rows.  For every input row of the band
-  // (kPoolRows + 4 rows) it loads the 6 columns the two outputs need once, reduces them to two horizontal
-  // 5-maxima and keeps the last five such rows in a register ring; an output is the max over the ring.
-  // Each input element is fetched (kPoolRows+4)/kPoolRows * 3 = 4.5 times instead of 25.
-  const int C8 = C / 8, W2 = W / 2, HB = H / kPoolRows;
-  const size_t total = (size_t)N * HB * W2 * C8;
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int c8 = (int)(i % C8);
-  size_t t = i / C8;
-  const int w0 = (int)(t % W2) * 2; t /= W2;
-  const int h0 = (int)(t % HB) * kPoolRows;
-  const int n = (int)(t / HB);
-  const int Hp = H + 2 * P, Wp = W + 2 * P;
-  const bool red = tf32 != 0;
-  float hm[5][2][8];
+  // Shared-memory tiled, separable 5x5 max (window clipped at the image border = MaxPool2d's -inf padding):
+  // load the (8+4) x (16+4) x 32-channel input patch once (128-byte pixel segments, coalesced), take the
+  // vertical 5-max, then the horizontal 5-max, and store the operand (with its circular-halo duplicates).
+  extern __shared__ float4 pool_smem[];                                   // kPoolSmemBytes (> 48 KB: opt-in)
+  float4 (*tin)[kPoolTW + 4][kPoolCB / 4] = reinterpret_cast<float4 (*)[kPoolTW + 4][kPoolCB / 4]>(pool_smem);
+  float4 (*tv)[kPoolTW + 4][kPoolCB / 4] =
+      reinterpret_cast<float4 (*)[kPoolTW + 4][kPoolCB / 4]>(pool_smem + (kPoolTH + 4) * (kPoolTW + 4) * (kPoolCB / 4));
+  const int CBn = C / kPoolCB, TWn = W / kPoolTW, THn = H / kPoolTH;
+  int b = blockIdx.x;
+  const int cb = b % CBn; b /= CBn;
+  const int tw = b % TWn; b /= TWn;
+  const int th = b % THn;
+  const int n = b / THn;
+  const int h0 = th * kPoolTH, w0 = tw * kPoolTW, c0 = cb * kPoolCB;
+  const float4 ninf = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+  for (int i = threadIdx.x; i < (kPoolTH + 4) * (kPoolTW + 4) * 8; i += 256) {
+    const int c4 = i & 7, px = i >> 3;
+    const int r = px / (kPoolTW + 4), cc = px % (kPoolTW + 4);
+    const int hh = h0 - 2 + r, ww = w0 - 2 + cc;
+    float4 v = ninf;
+    if (hh >= 0 && hh < H && ww >= 0 && ww < W)
+      v = *reinterpret_cast<const float4*>(in + (((size_t)n * H + hh) * W + ww) * C + c0 + c4 * 4);
+    tin[r][cc][c4] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kPoolTH * (kPoolTW + 4) * 8; i += 256) {
+    const int c4 = i & 7, px = i >> 3;
+    const int r = px / (kPoolTW + 4), cc = px % (kPoolTW + 4);
+    float4 m = tin[r][cc][c4];
 #pragma unroll
-  for (int rr = 0; rr < kPoolRows + 4; ++rr) {
-    const int hh = h0 - 2 + rr;
-    const int slot = rr % 5;
-    if (hh >= 0 && hh < H) {
-      const float* row = in + (((size_t)n * H + hh) * W) * C + c8 * 8;
-      float col[6][8];
-#pragma unroll
-      for (int j = 0; j < 6; ++j) {
-        const int ww = w0 - 2 + j;
-        if (ww >= 0 && ww < W) {
-          const float4 a = *reinterpret_cast<const float4*>(row + (size_t)ww * C);
-          const float4 b = *reinterpret_cast<const float4*>(row + (size_t)ww * C + 4);
-          col[j][0] = a.x; col[j][1] = a.y; col[j][2] = a.z; col[j][3] = a.w;
-          col[j][4] = b.x; col[j][5] = b.y; col[j][6] = b.z; col[j][7] = b.w;
-        } else {
-#pragma unroll
-          for (int k = 0; k < 8; ++k) col[j][k] = -INFINITY;
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float mid = fmaxf(fmaxf(col[1][k], col[2][k]), fmaxf(col[3][k], col[4][k]));
-        hm[slot][0][k] = fmaxf(mid, col[0][k]);
-        hm[slot][1][k] = fmaxf(mid, col[5][k]);
-      }
-      if (x0_out && rr >= 2 && rr < kPoolRows + 2) {        // hh is one of this thread's output rows: x0 = ELU(in)
-#pragma unroll
-        for (int p2 = 0; p2 < 2; ++p2) {
-          float* d = x0_out + (((size_t)n * H + hh) * W + w0 + p2) * C + c8 * 8;
-          *reinterpret_cast<float4*>(d) = make_float4(elu_sel<T>(col[2 + p2][0], red), elu_sel<T>(col[2 + p2][1], red),
-                                                      elu_sel<T>(col[2 + p2][2], red), elu_sel<T>(col[2 + p2][3], red));
-          *reinterpret_cast<float4*>(d + 4) = make_float4(elu_sel<T>(col[2 + p2][4], red), elu_sel<T>(col[2 + p2][5], red),
-                                                          elu_sel<T>(col[2 + p2][6], red), elu_sel<T>(col[2 + p2][7], red));
-        }
-      }
-    } else {
-#pragma unroll
-      for (int k = 0; k < 8; ++k) hm[slot][0][k] = hm[slot][1][k] = -INFINITY;
+    for (int k = 1; k < 5; ++k) {
+      const float4 v = tin[r + k][cc][c4];
+      m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
     }
-    if (rr >= 4) {
-      const int h = h0 + rr - 4;
+    tv[r][cc][c4] = m;
+  }
+  __syncthreads();
+  const bool red = tf32 != 0;
+  const int Hp = H + 2 * P, Wp = W + 2 * P;
+  for (int i = threadIdx.x; i < kPoolTH * kPoolTW * 8; i += 256) {
+    const int c4 = i & 7, px = i >> 3;
+    const int r = px / kPoolTW, cc = px % kPoolTW;
+    float4 m = tv[r][cc][c4];
 #pragma unroll
-      for (int p2 = 0; p2 < 2; ++p2) {
-        float m[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          m[k] = fmaxf(fmaxf(fmaxf(hm[0][p2][k], hm[1][p2][k]), fmaxf(hm[2][p2][k], hm[3][p2][k])), hm[4][p2][k]);
-          if (elu_in) m[k] = elu_sel<T>(m[k], red);
-        }
-        const HaloPos d = halo_pos(h, w0 + p2, H, W, P);
-        for_each_halo_pos(d, [&](int hp, int wp) {
-          store_op8<T>(out + (((size_t)n * Hp + hp) * Wp + wp) * C + c8 * 8, m, red);
-        });
-      }
+    for (int k = 1; k < 5; ++k) {
+      const float4 v = tv[r][cc + k][c4];
+      m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+    }
+    float o[4] = {m.x, m.y, m.z, m.w};
+    if (elu_in) { o[0] = elu_sel<T>(o[0], red); o[1] = elu_sel<T>(o[1], red); o[2] = elu_sel<T>(o[2], red); o[3] = elu_sel<T>(o[3], red); }
+    const int h = h0 + r, w = w0 + cc;
+    const HaloPos d = halo_pos(h, w, H, W, P);
+    for_each_halo_pos(d, [&](int hp, int wp) {
+      store_op4<T>(out + (((size_t)n * Hp + hp) * Wp + wp) * C + c0 + c4 * 4, o, red);
+    });
+    if (x0_out) {
+      const float4 a = tin[r + 2][cc + 2][c4];
+      *reinterpret_cast<float4*>(x0_out + (((size_t)n * H + h) * W + w) * C + c0 + c4 * 4) =
+          make_float4(elu_sel<T>(a.x, red), elu_sel<T>(a.y, red), elu_sel<T>(a.z, red), elu_sel<T>(a.w, red));
     }
   }
 }

@@ -307,16 +307,18 @@ struct Builder {
   Buf maxpool(const Buf& x, bool elu_in, Buf* x0_out) {
     Buf out = operand(x.H, x.W, x.C, 1);
     if (dry()) return out;
+    cudaFuncSetAttribute(maxpool5_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPoolSmemBytes);
+    cudaFuncSetAttribute(maxpool5_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPoolSmemBytes);
     const float* in = (const float*)x.ptr;
     float* x0 = x0_out ? (float*)x0_out->ptr : nullptr;
     const int n = N, H = x.H, W = x.W, C = x.C;
     const int tf32 = h->cfg.precision == SDPC_PREC_TF32;
-    const size_t total = (size_t)n * (H / kPoolRows) * (W / 2) * (C / 8);
+    const unsigned nblk = (unsigned)((size_t)n * (H / kPoolTH) * (W / kPoolTW) * (C / kPoolCB));
     void* o = out.ptr;
     const int elem = out.elem, ei = elu_in ? 1 : 0;
     push([=](cudaStream_t s, const float*, const int64_t*, float*) -> int {
-      if (elem == 2) maxpool5_kernel<__nv_bfloat16><<<blocks(total), 256, 0, s>>>(in, x0, (__nv_bfloat16*)o, n, H, W, C, 1, ei, tf32);
-      else maxpool5_kernel<float><<<blocks(total), 256, 0, s>>>(in, x0, (float*)o, n, H, W, C, 1, ei, tf32);
+      if (elem == 2) maxpool5_kernel<__nv_bfloat16><<<nblk, 256, kPoolSmemBytes, s>>>(in, x0, (__nv_bfloat16*)o, n, H, W, C, 1, ei, tf32);
+      else maxpool5_kernel<float><<<nblk, 256, kPoolSmemBytes, s>>>(in, x0, (float*)o, n, H, W, C, 1, ei, tf32);
       SDPC_CUDA(cudaGetLastError());
       return SDPC_OK;
     });
