@@ -169,7 +169,7 @@ __device__ __forceinline__ void store_op8(T* dst, const float* v, bool tf32) {
 // One thread: 8 channels x 4 consecutive pixels of a row (all loads issued before use).  With
 // HALO_ZERO the halo is not written here: the buffer's border is cleared by zero_halo_kernel.
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 to_operand_kernel(const float* __restrict__ in, const float* __restrict__ coef, T* __restrict__ out, int N, int H,
                   int W, int C, int P, int mode, int halo, int tf32) {
   const int C8 = C / 8, W4 = W / 4;
@@ -264,48 +264,58 @@ maxpool5_kernel(const float* __restrict__ in, float* __restrict__ x0_out, T* __r
   const int n = b / THn;
   const int h0 = th * kPoolTH, w0 = tw * kPoolTW, c0 = cb * kPoolCB;
   const float4 ninf = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-  for (int i = threadIdx.x; i < (kPoolTH + 4) * (kPoolTW + 4) * 8; i += 256) {
-    const int c4 = i & 7, px = i >> 3;
-    const int r = px / (kPoolTW + 4), cc = px % (kPoolTW + 4);
-    const int hh = h0 - 2 + r, ww = w0 - 2 + cc;
-    float4 v = ninf;
-    if (hh >= 0 && hh < H && ww >= 0 && ww < W)
-      v = *reinterpret_cast<const float4*>(in + (((size_t)n * H + hh) * W + ww) * C + c0 + c4 * 4);
-    tin[r][cc][c4] = v;
+  // fixed thread roles (no integer divisions): c4 = float4 channel group, (pr, pc) = pixel sub-position;
+  // a thread covers rows pr (+8) and columns pc + 4j.
+  const int c4 = threadIdx.x & 7, pc = (threadIdx.x >> 3) & 3, pr = threadIdx.x >> 5;
+#pragma unroll
+  for (int rr = 0; rr < 2; ++rr) {
+    const int r = pr + 8 * rr;
+    if (r < kPoolTH + 4) {
+      const int hh = h0 - 2 + r;
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        const int cc = pc + 4 * j, ww = w0 - 2 + cc;
+        float4 v = ninf;
+        if (hh >= 0 && hh < H && ww >= 0 && ww < W)
+          v = *reinterpret_cast<const float4*>(in + (((size_t)n * H + hh) * W + ww) * C + c0 + c4 * 4);
+        tin[r][cc][c4] = v;
+      }
+    }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < kPoolTH * (kPoolTW + 4) * 8; i += 256) {
-    const int c4 = i & 7, px = i >> 3;
-    const int r = px / (kPoolTW + 4), cc = px % (kPoolTW + 4);
-    float4 m = tin[r][cc][c4];
+#pragma unroll
+  for (int j = 0; j < 5; ++j) {
+    const int cc = pc + 4 * j;
+    float4 m = tin[pr][cc][c4];
 #pragma unroll
     for (int k = 1; k < 5; ++k) {
-      const float4 v = tin[r + k][cc][c4];
+      const float4 v = tin[pr + k][cc][c4];
       m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
     }
-    tv[r][cc][c4] = m;
+    tv[pr][cc][c4] = m;
   }
   __syncthreads();
   const bool red = tf32 != 0;
   const int Hp = H + 2 * P, Wp = W + 2 * P;
-  for (int i = threadIdx.x; i < kPoolTH * kPoolTW * 8; i += 256) {
-    const int c4 = i & 7, px = i >> 3;
-    const int r = px / kPoolTW, cc = px % kPoolTW;
-    float4 m = tv[r][cc][c4];
+  const int h = h0 + pr;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int cc = pc + 4 * j;
+    float4 m = tv[pr][cc][c4];
 #pragma unroll
     for (int k = 1; k < 5; ++k) {
-      const float4 v = tv[r][cc + k][c4];
+      const float4 v = tv[pr][cc + k][c4];
       m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
     }
     float o[4] = {m.x, m.y, m.z, m.w};
     if (elu_in) { o[0] = elu_sel<T>(o[0], red); o[1] = elu_sel<T>(o[1], red); o[2] = elu_sel<T>(o[2], red); o[3] = elu_sel<T>(o[3], red); }
-    const int h = h0 + r, w = w0 + cc;
+    const int w = w0 + cc;
     const HaloPos d = halo_pos(h, w, H, W, P);
     for_each_halo_pos(d, [&](int hp, int wp) {
       store_op4<T>(out + (((size_t)n * Hp + hp) * Wp + wp) * C + c0 + c4 * 4, o, red);
     });
     if (x0_out) {
-      const float4 a = tin[r + 2][cc + 2][c4];
+      const float4 a = tin[pr + 2][cc + 2][c4];
       *reinterpret_cast<float4*>(x0_out + (((size_t)n * H + h) * W + w) * C + c0 + c4 * 4) =
           make_float4(elu_sel<T>(a.x, red), elu_sel<T>(a.y, red), elu_sel<T>(a.z, red), elu_sel<T>(a.w, red));
     }
