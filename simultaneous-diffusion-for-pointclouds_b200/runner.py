@@ -1,0 +1,233 @@
+"""Sampling runners: thin re-host of the callers of the hot path.
+
+Mirrors `sample()` of LiDARGen/runners/ncsn_runner_kitti_simultaneous.py:461-924 (Line.yml, pose-matrix
+sampler) and LiDARGen/runners/ncsn_runner_AllForOne.py:466-1000 (Inpainting.yml / Densification.yml,
+translation sampler): checkpoint + EMA loading, existTotal mask preprocessing, the `doThis` ablation loop
+with the reference's hard-coded hyper-parameters, output post-processing and .npy naming.  It is a boundary
+row of SURVEY.md 8 (keep the API), not a kernel target; the data source is the synthetic generator unless
+`b200.data_root` points at KITTI-360 (the dataset readers themselves are out of scope).
+"""
+import logging
+import os
+import time
+
+import numpy as np
+import torch
+
+from .ema import EMAHelper
+from .samplers import (anneal_Langevin_dynamics_inpainting, anneal_Langevin_dynamics_inpainting_simultaneous_basic,
+                       anneal_Langevin_dynamics_inpainting_simultaneous_basic_kitti)
+from .scorenet import NCSN_LiDAR_small
+from .sigmas import get_sigmas
+from .synthetic_data import SyntheticMultiView
+
+__all__ = ["NCSNRunnerKITTISimultaneous", "NCSNRunnerAllForOne", "get_model"]
+
+
+def get_model(config):
+    """every LiDAR dataset maps to NCSN_LiDAR_small (ncsn_runner_kitti_simultaneous.py:33-52)."""
+    prec = getattr(getattr(config, "b200", None), "precision", None)
+    return NCSN_LiDAR_small(config, precision=prec).to(config.device)
+
+
+def inverse_data_transform(config, X):
+    """datasets/__init__.py:203-215 for logit_transform=False, rescaled=False: clamp to [0, 1]."""
+    return torch.clamp(X, 0.0, 1.0)
+
+
+def _erode(mask, iterations):
+    """scipy.ndimage.binary_erosion(border_value=1) with the default cross structuring element."""
+    try:
+        import scipy.ndimage
+        return scipy.ndimage.binary_erosion(mask, border_value=1, iterations=iterations)
+    except Exception:                                       # pragma: no cover
+        m = mask.copy()
+        for _ in range(iterations):
+            p = np.pad(m, 1, constant_values=True)
+            m = p[1:-1, 1:-1] & p[:-2, 1:-1] & p[2:, 1:-1] & p[1:-1, :-2] & p[1:-1, 2:]
+        return m
+
+
+def exist_mask(config, batch_size):
+    """ncsn_runner_kitti_simultaneous.py:527-533: threshold at max/3, 4x erosion of rows 2.., tile."""
+    path = getattr(getattr(config, "b200", None), "exist_mask", None) or "/data/existTotalLiDARGenSettings.npy"
+    H, W = config.data.image_size, config.data.image_width
+    if os.path.exists(path) and np.load(path).shape == (H, W):
+        vals = np.load(path)
+    else:                                                   # synthetic: sensor drop-outs near the image border rows
+        r = np.random.Generator(np.random.PCG64(7))
+        vals = r.uniform(0.4, 1.0, size=(H, W)) * 8601.0
+        vals[: max(1, H // 16)] *= 0.2
+    vals = vals > np.max(vals) / 3
+    vals[2:] = _erode(vals[2:], 4)
+    vals = np.tile(np.expand_dims(vals, 0), (batch_size, 1, 1))
+    return torch.from_numpy(vals).to(config.device)
+
+
+def _to_grid_layout(x):
+    """[B,2,H,W] -> channel-major [2B,3,H,W] as the runners save it (ncsn_runner_kitti_simultaneous.py:848-870)."""
+    x = x.transpose(1, 0)
+    x = x.reshape((x.size(1) * x.size(0), 1, x.size(2), x.size(3)))
+    return torch.cat((x, x, x), 1)
+
+
+class _Base:
+    def __init__(self, args, config):
+        self.args, self.config = args, config
+        args.log_sample_path = os.path.join(args.log_path, "samples") if hasattr(args, "log_path") else None
+
+    # ---- model -----------------------------------------------------------------------------------
+    def load_score(self):
+        cfg = self.config
+        score = torch.nn.DataParallel(get_model(cfg), device_ids=[torch.device(cfg.device).index or 0])
+        ckpt = getattr(getattr(cfg, "b200", None), "checkpoint", None)
+        if ckpt:
+            states = torch.load(ckpt, map_location=cfg.device)
+            score.load_state_dict(states[0], strict=True)
+            if cfg.model.ema:
+                ema_helper = EMAHelper(mu=cfg.model.ema_rate)
+                ema_helper.register(score)
+                ema_helper.load_state_dict(states[-1])
+                ema_helper.ema(score)
+        else:
+            logging.info("no b200.checkpoint configured: random-init weights (offline run)")
+        score.eval()
+        return score
+
+    def dataset(self, mode):
+        cfg = self.config
+        return SyntheticMultiView(cfg.data.image_size, cfg.data.image_width, cfg.sampling.batch_size,
+                                  cfg.sampling.actualBatchSize, mode=mode, seed=self.args.seed)
+
+    def save_outputs(self, doThis, saveNum, n_views, all_outputs):
+        cfg = self.config
+        shp = (n_views, cfg.data.channels, cfg.data.image_size, cfg.data.image_width)
+        sample = inverse_data_transform(cfg, all_outputs[-1].view(*shp))
+        masked = _to_grid_layout(sample)
+        np.save(os.path.join(self.args.image_folder,
+                             str(doThis) + '_' + saveNum + '_Masked_completion_{}.pth'.format(cfg.sampling.ckpt_id)),
+                masked.cpu().detach().numpy())
+        return masked
+
+
+class NCSNRunnerKITTISimultaneous(_Base):
+    """Line.yml: `KITTI360_im_8batch`, pose-matrix sampler (main.py:191-192)."""
+
+    def sample(self):
+        cfg, args = self.config, self.args
+        score = self.load_score()
+        sigmas = get_sigmas(cfg).cpu().numpy()
+        A, Bsz = cfg.sampling.actualBatchSize, cfg.sampling.batch_size
+        data = self.dataset("line")
+        existVals = exist_mask(cfg, Bsz)
+        n_batches = int(getattr(getattr(cfg, "b200", None), "max_batches", 1) or 1)
+        timeTaken = np.zeros(max(A, n_batches))
+        for batchesToDo in range(n_batches):
+            (refer_images_full, refer_mask_full, refer_sky, refer_indices_full, toWorld_full, fromWorld_full, goalImages,
+             toOGView, saveNumArray) = data.batch(batchesToDo)
+            G = Bsz // A
+            saveNum = "".join(str(saveNumArray[p * A].cpu().detach().numpy()) + "_" for p in range(G))
+            np.save(os.path.join(args.image_folder, "toWorld_" + saveNum), toWorld_full.cpu().detach())
+            np.save(os.path.join(args.image_folder, "fromWorld_" + saveNum), toOGView.cpu().detach())
+            for doThis in range(A):
+                startStep, correlation_co, gradRef, allowance, setting = 2, 0.01, 1, 10, 5      # :574-579
+                dev = cfg.device
+                refer = refer_images_full.float().to(dev)
+                refer_mask = refer_mask_full.int().to(dev)
+                sky, idx = refer_sky.clone(), refer_indices_full.clone()
+                toWorld, fromWorld = toWorld_full.clone(), fromWorld_full.clone()
+                init_samples = torch.rand(Bsz, cfg.data.channels, cfg.data.image_size, cfg.data.image_width, device=dev)
+                if doThis == 0:
+                    tag = '_{}.pth'.format(cfg.sampling.ckpt_id)
+                    np.save(os.path.join(args.image_folder, str(doThis) + '_' + saveNum + '_Input_completion' + tag),
+                            _to_grid_layout(inverse_data_transform(cfg, refer_images_full * refer_mask_full)).numpy())
+                    np.save(os.path.join(args.image_folder, str(doThis) + '_' + saveNum + '_GT_completion' + tag),
+                            _to_grid_layout(inverse_data_transform(cfg, goalImages)).numpy())
+                    np.save(os.path.join(args.image_folder, str(doThis) + '_' + saveNum + '_SKY' + tag),
+                            refer_sky.clone().cpu().detach().numpy())
+                start_time = time.time()
+                if doThis == A - 1:                                                           # LiDARGen baseline arm
+                    n_views = Bsz
+                    all_outputs, _ = anneal_Langevin_dynamics_inpainting(
+                        init_samples, refer, refer_mask, score, sigmas, cfg.sampling.n_steps_each, cfg.sampling.step_lr,
+                        denoise=cfg.sampling.denoise, grad_ref=1, sampling_step=4)
+                else:
+                    k = doThis + 2 if doThis < A - 2 else A                                   # views kept per group
+
+                    def keep(t, shape):
+                        t = torch.reshape(t, (G, A, -1))
+                        return torch.reshape(t[:, :k], (G * k,) + shape)
+                    img = (cfg.data.channels, cfg.data.image_size, cfg.data.image_width)
+                    one = (1, cfg.data.image_size, cfg.data.image_width)
+                    n_views = G * k
+                    all_outputs, _, _ = anneal_Langevin_dynamics_inpainting_simultaneous_basic_kitti(
+                        keep(init_samples, img), keep(refer, img), keep(refer_mask, img), keep(sky, one), keep(idx, one),
+                        startStep, setting, allowance, score, sigmas, keep(fromWorld, (4, 4)), keep(toWorld, (4, 4)), k,
+                        cfg.sampling.n_steps_each, cfg.sampling.step_lr, existMask=existVals,
+                        denoise=cfg.sampling.denoise, grad_ref=gradRef, correlation_coefficient=correlation_co,
+                        sampling_step=4)
+                torch.cuda.synchronize()
+                timeTaken[doThis] += (time.time() - start_time)
+                print("--- %s seconds ---" % (timeTaken[doThis] / (batchesToDo + 1)))
+                np.save(os.path.join(args.image_folder, str(doThis) + '_' + saveNum + '_TimeTaken.npy'), timeTaken[doThis])
+                self.save_outputs(doThis, saveNum, n_views, all_outputs)
+        return 0
+
+
+class NCSNRunnerAllForOne(_Base):
+    """Inpainting.yml / Densification.yml: translation sampler (ncsn_runner_AllForOne.py:466-1000)."""
+
+    def sample(self):
+        cfg, args = self.config, self.args
+        score = self.load_score()
+        sigmas = get_sigmas(cfg).cpu().numpy()
+        A, Bsz = cfg.sampling.actualBatchSize, cfg.sampling.batch_size
+        dens = cfg.data.dataset == 'KITTI360_im_simultaneous_densification'
+        data = self.dataset("densification" if dens else "allforone")
+        existVals = exist_mask(cfg, Bsz)
+        n_batches = int(getattr(getattr(cfg, "b200", None), "max_batches", 1) or 1)
+        timeTaken = np.zeros(max(A, n_batches))
+        for batchesToDo in range(n_batches):
+            (refer_images_full, refer_mask_full, refer_sky, refer_indices_full, toWorld_full, fromWorld_full, goalImages,
+             toOGView, saveNumArray) = data.batch(batchesToDo)
+            G = Bsz // A
+            saveNum = "".join(str(saveNumArray[p * A].cpu().detach().numpy()) + "_" for p in range(G))
+            np.save(os.path.join(args.image_folder, "toWorld_" + saveNum), toWorld_full.cpu().detach())
+            np.save(os.path.join(args.image_folder, "fromWorld_" + saveNum), toOGView.cpu().detach())
+            endPoint, toAdd = (2, A - 2) if dens else (A, 0)                                   # :555-558
+            for doThis in range(endPoint):
+                startStep, correlation_co, gradRef, setting = 2, 0.01, 1, 7                    # :585-594
+                dev = cfg.device
+                modifiersToGive = torch.from_numpy(np.array(cfg.data.modifications)).to(dev)
+                refer = refer_images_full.float().to(dev)
+                refer_mask = refer_mask_full.int().to(dev)
+                sky, idx = refer_sky.clone(), refer_indices_full.clone()
+                init_samples = torch.rand(Bsz, cfg.data.channels, cfg.data.image_size, cfg.data.image_width, device=dev)
+                img = (cfg.data.channels, cfg.data.image_size, cfg.data.image_width)
+                one = (1, cfg.data.image_size, cfg.data.image_width)
+
+                def keep(t, shape, k):
+                    t = torch.reshape(t, (G, A, -1))
+                    return torch.reshape(t[:, :k], (G * k,) + shape)
+                start_time = time.time()
+                if doThis + toAdd == A - 1:                                                    # baseline on view 0 of each group
+                    n_views = G
+                    all_outputs, _ = anneal_Langevin_dynamics_inpainting(
+                        keep(init_samples, img, 1), keep(refer, img, 1), keep(refer_mask, img, 1), score, sigmas,
+                        cfg.sampling.n_steps_each, cfg.sampling.step_lr, denoise=cfg.sampling.denoise, grad_ref=1,
+                        sampling_step=4)
+                else:
+                    k = doThis + 2 if doThis + toAdd < A - 2 else A
+                    n_views = G * k
+                    all_outputs, _, _ = anneal_Langevin_dynamics_inpainting_simultaneous_basic(
+                        keep(init_samples, img, k), keep(refer, img, k), keep(refer_mask, img, k), keep(sky, one, k),
+                        keep(idx, one, k), startStep, setting, score, sigmas, modifiersToGive, k,
+                        cfg.sampling.n_steps_each, cfg.sampling.step_lr, existMask=existVals,
+                        denoise=cfg.sampling.denoise, grad_ref=gradRef, correlation_coefficient=correlation_co,
+                        sampling_step=4)
+                torch.cuda.synchronize()
+                timeTaken[doThis] += (time.time() - start_time)
+                print("--- %s seconds ---" % (timeTaken[doThis] / (batchesToDo + 1)))
+                np.save(os.path.join(args.image_folder, str(doThis) + '_' + saveNum + '_TimeTaken.npy'), timeTaken[doThis])
+                self.save_outputs(doThis, saveNum, n_views, all_outputs)
+        return 0
