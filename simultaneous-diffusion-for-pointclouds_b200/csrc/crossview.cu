@@ -36,6 +36,8 @@ struct StepWorkspace {
   long long* sum_d;             // [B*R*W] fixed-point 2^-40
   long long* sum_i;             // [B*R*W] fixed-point 2^-32
   unsigned int* cnt;            // [B*R*W]
+  unsigned long long* zpack;    // [B*R*W] (log-range bits with the low key_shift bits replaced by the source id)
+  unsigned int* flag;           // [1]   set when a packed winner could not be confirmed -> exact winner pass runs
   float* shared_img;            // [B,2,H,W] newImages when the caller does not ask for them
   uint8_t* shared_mask;         // [B,H,W]   imageMask & existMask[0] & sky
   size_t cells;
@@ -53,6 +55,7 @@ static size_t workspace_layout(int B, int H, int R, int W, char* base, StepWorks
   size_t o_sd = take(cells * 8);
   size_t o_si = take(cells * 8);
   size_t o_cnt = take(cells * 4);
+  size_t o_zpack = take(cells * 8);
   size_t o_img = take((size_t)B * 2 * H * W * 4);
   size_t o_msk = take((size_t)B * H * W);
   if (ws) {
@@ -64,6 +67,8 @@ static size_t workspace_layout(int B, int H, int R, int W, char* base, StepWorks
     ws->sum_d = (long long*)(base + o_sd);
     ws->sum_i = (long long*)(base + o_si);
     ws->cnt = (unsigned int*)(base + o_cnt);
+    ws->zpack = (unsigned long long*)(base + o_zpack);
+    ws->flag = (unsigned int*)(base + o_max + 64);
     ws->cells = cells;
   }
   return off;
@@ -148,6 +153,7 @@ struct ScatterArgs {
   GeoConsts geo;
   int A, variant, sky_filter, tgt_first, tgt_count;
   float sigma_mod, min_depth_thr;
+  int key_shift;                // low bits of the packed key that hold the source id
 };
 
 template <int PASS>
@@ -160,6 +166,7 @@ __global__ void __launch_bounds__(256) scatter_kernel(ScatterArgs a) {
   const int t_lo = max(g * a.A, a.tgt_first);
   const int t_hi = min((g + 1) * a.A, a.tgt_first + a.tgt_count);
   if (t_lo >= t_hi) return;
+  if (PASS == 1 && *a.ws.flag == 0) return;   // every packed winner was confirmed: nothing to do
 
   __shared__ double s_to[16];
   __shared__ double s_from[kMaxGroup * 12];
@@ -228,6 +235,7 @@ __global__ void __launch_bounds__(256) scatter_kernel(ScatterArgs a) {
     const unsigned long long key = (unsigned long long)__double_as_longlong(cd.nd);   // nd >= 0: monotone
     if (PASS == 0) {
       atomicMin(a.ws.zmin + cell, key);
+      atomicMin(a.ws.zpack + cell, ((key >> a.key_shift) << a.key_shift) | (unsigned long long)src_id);
       atomicAdd(a.ws.cnt + cell, 1u);
       atomicAdd((unsigned long long*)(a.ws.sum_d + cell), (unsigned long long)depth_to_fixed(cd.nd));
       atomicAdd((unsigned long long*)(a.ws.sum_i + cell), (unsigned long long)inten_fx);
@@ -235,6 +243,145 @@ __global__ void __launch_bounds__(256) scatter_kernel(ScatterArgs a) {
       if (a.ws.zmin[cell] == key) atomicMin(a.ws.winner + cell, src_id);
     }
   }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// production scatter: compacted valid source pixels, fp32-guarded re-projection, packed winner key
+// ------------------------------------------------------------------------------------------
+constexpr int kChunk = 1024;      // source pixels per block (4 per thread)
+
+__global__ void __launch_bounds__(256) scatter_fast_kernel(ScatterArgs a) {
+  const int HW = a.geo.H * a.geo.W;
+  const int src_a = blockIdx.y, g = blockIdx.z, b = g * a.A + src_a;
+  const int t_lo = max(g * a.A, a.tgt_first);
+  const int t_hi = min((g + 1) * a.A, a.tgt_first + a.tgt_count);
+  if (t_lo >= t_hi) return;
+  __shared__ double s_to[16];
+  __shared__ double s_from[kMaxGroup * 12];
+  __shared__ float s_org[kMaxGroup * 3];
+  __shared__ unsigned short s_list[kChunk];
+  __shared__ int s_wsum[8];
+  if (a.variant == SDPC_VARIANT_POSE) {
+    if (threadIdx.x < 16) s_to[threadIdx.x] = a.to_world[(size_t)b * 16 + threadIdx.x];
+    for (int i = threadIdx.x; i < (t_hi - t_lo) * 12; i += blockDim.x)
+      s_from[i] = a.from_world[(size_t)(t_lo + i / 12) * 16 + (i % 12)];
+  } else {
+    for (int i = threadIdx.x; i < a.A * 3; i += blockDim.x) s_org[i] = a.origins[i];
+  }
+  // ---- phase 1: warp-vote / prefix compaction of the source pixels that may contribute
+  const int base = blockIdx.x * kChunk;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uchar4 ex = *reinterpret_cast<const uchar4*>(a.exist + (size_t)src_a * HW + base + threadIdx.x * 4);
+  uchar4 sk = make_uchar4(1, 1, 1, 1);
+  if (a.sky_filter) sk = *reinterpret_cast<const uchar4*>(a.sky + (size_t)b * HW + base + threadIdx.x * 4);
+  const unsigned v = (ex.x && sk.x ? 1u : 0u) | (ex.y && sk.y ? 2u : 0u) | (ex.z && sk.z ? 4u : 0u) | (ex.w && sk.w ? 8u : 0u);
+  const int mine = __popc(v);
+  int incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int n = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += n;
+  }
+  if (lane == 31) s_wsum[warp] = incl;
+  __syncthreads();
+  int off = incl - mine, total = 0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) {
+    if (w < warp) off += s_wsum[w];
+    total += s_wsum[w];
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (v & (1u << k)) s_list[off++] = (unsigned short)(threadIdx.x * 4 + k);
+  __syncthreads();
+  // ---- phase 2: every lane works on a contributing pixel
+  const size_t grid_cells = (size_t)a.geo.R * a.geo.W;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int p = base + s_list[i];
+    const int r = p / a.geo.W, c = p - r * a.geo.W;
+    const float x0 = a.x[((size_t)b * 2) * HW + p];
+    const float x1 = a.x[((size_t)b * 2 + 1) * HW + p];
+    const float dist = decode_range(x0, a.sigma_mod, a.geo.recip);
+    double P[3];
+    unproject(dist, a.cos_az[c], a.sin_az[c], a.cos_el[r], a.sin_el[r], P);
+    double wx, wy, wz, ww = 1.0;
+    if (a.variant == SDPC_VARIANT_POSE) {
+      wx = dot4(s_to + 0, P[0], P[1], P[2], 1.0);
+      wy = dot4(s_to + 4, P[0], P[1], P[2], 1.0);
+      wz = dot4(s_to + 8, P[0], P[1], P[2], 1.0);
+      ww = dot4(s_to + 12, P[0], P[1], P[2], 1.0);
+    } else {
+      wx = P[0] + (double)s_org[src_a * 3 + 0];
+      wy = P[1] + (double)s_org[src_a * 3 + 1];
+      wz = P[2] + (double)s_org[src_a * 3 + 2];
+    }
+    const long long inten_fx = inten_to_fixed(x1);
+    const unsigned src_id = (unsigned)(src_a * HW + p);
+    for (int t = t_lo; t < t_hi; ++t) {
+      double qx, qy, qz;
+      if (a.variant == SDPC_VARIANT_POSE) {
+        const double* m = s_from + (t - t_lo) * 12;
+        qx = dot4(m + 0, wx, wy, wz, ww);
+        qy = dot4(m + 4, wx, wy, wz, ww);
+        qz = dot4(m + 8, wx, wy, wz, ww);
+      } else {
+        const int ta = t - g * a.A;
+        qx = wx - (double)s_org[ta * 3 + 0];
+        qy = wy - (double)s_org[ta * 3 + 1];
+        qz = wz - (double)s_org[ta * 3 + 2];
+      }
+      const Candidate cd = reproject_fast(qx, qy, qz, a.sigma_mod, a.geo);
+      bool ok = in_grid(cd, a.geo);
+      if (a.min_depth_thr >= 0.0f) ok = ok && (cd.nd > (double)a.min_depth_thr);
+      if (!ok) continue;
+      const size_t cell = (size_t)t * grid_cells + (size_t)cd.row * a.geo.W + cd.col;
+      const unsigned long long key = (unsigned long long)__double_as_longlong(cd.nd);
+      atomicMin(a.ws.zmin + cell, key);
+      atomicMin(a.ws.zpack + cell, ((key >> a.key_shift) << a.key_shift) | (unsigned long long)src_id);
+      atomicAdd(a.ws.cnt + cell, 1u);
+      atomicAdd((unsigned long long*)(a.ws.sum_d + cell), (unsigned long long)depth_to_fixed(cd.nd));
+      atomicAdd((unsigned long long*)(a.ws.sum_i + cell), (unsigned long long)inten_fx);
+    }
+  }
+}
+
+// Confirm the packed winners: for every filled cell recompute the exact log-range of the source the packed key
+// names; if it is the cell minimum that source is the (smallest-id) nearest candidate, otherwise raise the flag
+// that makes the exact winner pass run.
+__global__ void __launch_bounds__(256) verify_winner_kernel(ScatterArgs a) {
+  const int HW = a.geo.H * a.geo.W;
+  const size_t grid_cells = (size_t)a.geo.R * a.geo.W;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)a.tgt_count * grid_cells) return;
+  const int t = a.tgt_first + (int)(i / grid_cells);
+  const size_t cell = (size_t)a.tgt_first * grid_cells + i;
+  if (a.ws.cnt[cell] == 0) return;
+  const unsigned id = (unsigned)(a.ws.zpack[cell] & ((1ull << a.key_shift) - 1ull));
+  const int g = t / a.A, src_a = id / HW, p = id - src_a * HW, b = g * a.A + src_a;
+  const int r = p / a.geo.W, c = p - r * a.geo.W;
+  const float dist = decode_range(a.x[((size_t)b * 2) * HW + p], a.sigma_mod, a.geo.recip);
+  double P[3], qx, qy, qz;
+  unproject(dist, a.cos_az[c], a.sin_az[c], a.cos_el[r], a.sin_el[r], P);
+  if (a.variant == SDPC_VARIANT_POSE) {
+    const double* tw = a.to_world + (size_t)b * 16;
+    const double wx = dot4(tw + 0, P[0], P[1], P[2], 1.0), wy = dot4(tw + 4, P[0], P[1], P[2], 1.0);
+    const double wz = dot4(tw + 8, P[0], P[1], P[2], 1.0), ww = dot4(tw + 12, P[0], P[1], P[2], 1.0);
+    const double* m = a.from_world + (size_t)t * 16;
+    qx = dot4(m + 0, wx, wy, wz, ww);
+    qy = dot4(m + 4, wx, wy, wz, ww);
+    qz = dot4(m + 8, wx, wy, wz, ww);
+  } else {
+    const int ta = t - g * a.A;
+    qx = (P[0] + (double)a.origins[src_a * 3 + 0]) - (double)a.origins[ta * 3 + 0];
+    qy = (P[1] + (double)a.origins[src_a * 3 + 1]) - (double)a.origins[ta * 3 + 1];
+    qz = (P[2] + (double)a.origins[src_a * 3 + 2]) - (double)a.origins[ta * 3 + 2];
+  }
+  const double xy = qx * qx + qy * qy;
+  double nd = log2(sqrt(xy + qz * qz) + 1.0);
+  nd = sdiv(nd, 6.0, a.geo.recip) * (double)a.sigma_mod;
+  if ((unsigned long long)__double_as_longlong(nd) == a.ws.zmin[cell]) a.ws.winner[cell] = id;
+  else atomicOr(a.ws.flag, 1u);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -413,6 +560,8 @@ extern "C" int sdpc_crossview_share(const sdpc_step_params* p, const sdpc_step_b
   SDPC_CUDA(cudaMemsetAsync(ws.sum_d + first, 0, n * 8, stream));
   SDPC_CUDA(cudaMemsetAsync(ws.sum_i + first, 0, n * 8, stream));
   SDPC_CUDA(cudaMemsetAsync(ws.cnt + first, 0, n * 4, stream));
+  SDPC_CUDA(cudaMemsetAsync(ws.zpack + first, 0xFF, n * 8, stream));
+  SDPC_CUDA(cudaMemsetAsync(ws.flag, 0, sizeof(unsigned), stream));
 
   ScatterArgs sa;
   sa.x = b->x; sa.sky = b->sky; sa.exist = b->exist;
@@ -427,10 +576,21 @@ extern "C" int sdpc_crossview_share(const sdpc_step_params* p, const sdpc_step_b
   sa.A = p->group_size; sa.variant = p->variant; sa.sky_filter = p->sky_filter;
   sa.tgt_first = p->tgt_first; sa.tgt_count = tcount;
   sa.sigma_mod = p->sigma_mod; sa.min_depth_thr = p->min_depth_thr;
+  sa.key_shift = 1;
+  while ((1 << sa.key_shift) < p->group_size * HW) ++sa.key_shift;
+  if (p->key_shift_override > sa.key_shift && p->key_shift_override < 52) sa.key_shift = p->key_shift_override;
   dim3 grid((HW + 255) / 256, p->group_size, p->n_views / p->group_size);
-  scatter_kernel<0><<<grid, 256, 0, stream>>>(sa);
+  const bool fast = sa.dbg_row == nullptr && HW % kChunk == 0;     // candidate-level debug output: legacy full kernel
+  if (fast) {
+    dim3 fgrid(HW / kChunk, p->group_size, p->n_views / p->group_size);
+    scatter_fast_kernel<<<fgrid, 256, 0, stream>>>(sa);
+  } else {
+    scatter_kernel<0><<<grid, 256, 0, stream>>>(sa);
+  }
   SDPC_CUDA(cudaGetLastError());
-  scatter_kernel<1><<<grid, 256, 0, stream>>>(sa);
+  verify_winner_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(sa);
+  SDPC_CUDA(cudaGetLastError());
+  scatter_kernel<1><<<grid, 256, 0, stream>>>(sa);              // exits immediately unless a winner was unconfirmed
   SDPC_CUDA(cudaGetLastError());
   if (b->dbg_cnt || b->dbg_winner || b->dbg_min_d) {
     dump_cells_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(ws, b->dbg_cnt, b->dbg_winner, b->dbg_min_d, first, n);

@@ -82,6 +82,34 @@ SDPC_HD Candidate reproject(double qx, double qy, double qz, float sigma_mod, co
   return c;
 }
 
+// Same result as reproject(), cheaper: the log-range (the z-buffer key) is always the exact float64 expression,
+// but each of the two float64 atan2 calls is replaced by a float32 estimate whenever that estimate is provably
+// far from a rounding boundary.  Error budget of the estimate: inputs rounded to fp32 (6e-8 relative each),
+// atan2f <= 2 ulp at pi (5e-7 rad), i.e. < 2e-4 pixel; the guard band is 1e-2 pixel.  Points inside the guard
+// band (about 2 %), non-finite or huge coordinates take the float64 path, so the integers are identical.
+constexpr double kFastGuard = 1e-2;
+SDPC_HD Candidate reproject_fast(double qx, double qy, double qz, float sigma_mod, const GeoConsts& g) {
+  Candidate c;
+  const double xy = qx * qx + qy * qy;
+  const double r = sqrt(xy + qz * qz);
+  double nd = log2(r + 1.0);
+  nd = sdiv(nd, 6.0, g.recip);
+  c.nd = nd * (double)sigma_mod;
+  const bool tame = r < 1e15;
+  const float fx = (float)qx, fy = (float)qy, fz = (float)qz;
+  double cf = sdiv((double)atan2f(fy, fx) - g.h_min, g.dh, g.recip);
+  double rc = rint(cf);
+  if (!(tame && fabs(cf - rc) < 0.5 - kFastGuard)) rc = rint(sdiv(atan2(qy, qx) - g.h_min, g.dh, g.recip));
+  double rf = sdiv((double)atan2f(fz, sqrtf(fx * fx + fy * fy)) - g.big_row_min, g.dv, g.recip);
+  double rr = rint(rf);
+  if (!(tame && fabs(rf - rr) < 0.5 - kFastGuard)) rr = rint(sdiv(atan2(qz, sqrt(xy)) - g.big_row_min, g.dv, g.recip));
+  int ci = (rc >= -2147483648.0 && rc <= 2147483647.0) ? (int)rc : INT32_MIN;
+  int ri = (rr >= -2147483648.0 && rr <= 2147483647.0) ? (int)rr : INT32_MIN;
+  c.col = (int)((unsigned)ci * (unsigned)-1 + (unsigned)(g.W - 1));
+  c.row = (int)((unsigned)ri * (unsigned)-1 + (unsigned)(g.R - 1));
+  return c;
+}
+
 SDPC_HD bool in_grid(const Candidate& c, const GeoConsts& g) {
   return c.col > -1 && c.col < g.W && c.row > -1 && c.row < g.R;
 }

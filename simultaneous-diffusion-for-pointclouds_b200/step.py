@@ -59,14 +59,18 @@ class StepRunner:
         nbytes = 256 if self.lib is None else self._ws_bytes()
         self.workspace = torch.empty(nbytes, dtype=torch.uint8, device=device)
         self.too_high = torch.zeros(1, dtype=torch.int32, device=device)
+        # debug=True: candidate-level (row/col/valid, selects the legacy full scatter kernel) + cell-level dumps;
+        # debug="cells": only the per-cell dumps, so the production (compacted, fp32-guarded) scatter runs
         self.debug = None
+        self.key_shift_override = 0
         if debug:
             R = self.geo.R
             i32 = dict(device=device, dtype=torch.int32)
-            self.debug = dict(row=torch.zeros(B, group_size * H * W, **i32), col=torch.zeros(B, group_size * H * W, **i32),
-                              valid=torch.zeros(B, group_size * H * W, device=device, dtype=torch.uint8),
-                              cnt=torch.zeros(B, R, W, **i32), winner=torch.zeros(B, R, W, **i32),
+            self.debug = dict(cnt=torch.zeros(B, R, W, **i32), winner=torch.zeros(B, R, W, **i32),
                               min_d=torch.zeros(B, R, W, device=device, dtype=torch.float64))
+            if debug != "cells":
+                self.debug.update(row=torch.zeros(B, group_size * H * W, **i32), col=torch.zeros(B, group_size * H * W, **i32),
+                                  valid=torch.zeros(B, group_size * H * W, device=device, dtype=torch.uint8))
 
     def _ws_bytes(self):
         fn = getattr(self.lib, "sdpc_step_workspace_bytes", None)
@@ -80,6 +84,7 @@ class StepRunner:
         p.variant, p.share, p.nan_to_num, p.sky_filter = self.variant, int(share), int(nan_to_num), int(sky_filter)
         p.tgt_first, p.tgt_count = self.tgt_first, self.tgt_count
         p.scalar_div_recip = int(self.scalar_div_recip)
+        p.key_shift_override = int(self.key_shift_override)
         p.step_size, p.noise_scale = float(step_size), float(noise_scale)
         p.grad_ref, p.corr_coef, p.sigma_mod = float(grad_ref), float(corr_coef), float(sigma_mod)
         p.min_depth_thr = min_depth_threshold(sigma_mod) if min_depth_filter else -1.0
@@ -97,7 +102,8 @@ class StepRunner:
         b.grad_likelihood, b.new_images, b.too_high = _ptr(grad_likelihood), _ptr(new_images), _ptr(self.too_high)
         if self.debug is not None:
             d = self.debug
-            b.dbg_row, b.dbg_col, b.dbg_valid = _ptr(d["row"]), _ptr(d["col"]), _ptr(d["valid"])
+            if "row" in d:
+                b.dbg_row, b.dbg_col, b.dbg_valid = _ptr(d["row"]), _ptr(d["col"]), _ptr(d["valid"])
             b.dbg_cnt, b.dbg_winner, b.dbg_min_d = _ptr(d["cnt"]), _ptr(d["winner"]), _ptr(d["min_d"])
         return b
 

@@ -60,6 +60,7 @@ extern "C" int sdpc_crossview_share(const sdpc_step_params* p, const sdpc_step_b
   std::vector<unsigned long long> zmin(cells, ~0ull);
   std::vector<unsigned> winner(cells, ~0u), cnt(cells, 0u);
   std::vector<long long> sum_d(cells, 0), sum_i(cells, 0);
+  long long fast_mismatch = 0;
   for (int pass = 0; pass < 2; ++pass)
     for (int g = 0; g < B / A; ++g)
       for (int sa = 0; sa < A; ++sa) {
@@ -94,6 +95,10 @@ extern "C" int sdpc_crossview_share(const sdpc_step_params* p, const sdpc_step_b
               qz = wz - (double)b->origins[ta * 3 + 2];
             }
             Candidate cd = reproject(qx, qy, qz, p->sigma_mod, geo);
+            {   // the guarded fp32 fast path of the production kernel must give the identical candidate
+              Candidate cf = reproject_fast(qx, qy, qz, p->sigma_mod, geo);
+              if (cf.row != cd.row || cf.col != cd.col || memcmp(&cf.nd, &cd.nd, 8) != 0) ++fast_mismatch;
+            }
             bool ok = src_ok && in_grid(cd, geo);
             if (p->min_depth_thr >= 0.0f) ok = ok && cd.nd > (double)p->min_depth_thr;
             if (pass == 0 && b->dbg_row) {
@@ -143,6 +148,7 @@ extern "C" int sdpc_crossview_share(const sdpc_step_params* p, const sdpc_step_b
       img[i1] = f.inten;
       sm[(size_t)t * HW + q] = f.filled && b->exist[q] && b->sky[(size_t)t * HW + q];
     }
+  if (fast_mismatch) return 100;
   const bool too_high = too_high_gate(mx, p->sigma_mod, geo.recip);
   if (b->too_high) *b->too_high = too_high;
   for (int t = t0; t < t0 + tn; ++t)

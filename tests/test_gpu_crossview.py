@@ -22,11 +22,11 @@ G = os.path.join(os.path.dirname(__file__), "golden")
 DEV = "cuda:0"
 
 
-def _runner(kind, case, dev=DEV, **extra):
+def _runner(kind, case, dev=DEV, debug=True, **extra):
     kw = dict(to_world=case["toWorld"], from_world=case["fromWorld"]) if kind == "pose" else \
         dict(origins=translation_origins(case["mods"].to(dev)))
     return StepRunner(case["x"].shape, dev, case["refer"], case["mask"], case["sky"], case["exist"], case["A"],
-                      cabi.SDPC_VARIANT_POSE if kind == "pose" else cabi.SDPC_VARIANT_TRANSLATION, debug=True,
+                      cabi.SDPC_VARIANT_POSE if kind == "pose" else cabi.SDPC_VARIANT_TRANSLATION, debug=debug,
                       **kw, **extra)
 
 
@@ -46,8 +46,9 @@ def _oracle(kind, case, sigma, setting, dev):
     return ni, x2, th, d
 
 
-def _cuda_step(kind, case, sigma, setting, recip=None):
-    run = _runner(kind, case, scalar_div_recip=recip)
+def _cuda_step(kind, case, sigma, setting, recip=None, debug=True, key_shift=0):
+    run = _runner(kind, case, scalar_div_recip=recip, debug=debug)
+    run.key_shift_override = key_shift
     sm = sigma if sigma > 1 else 1
     if kind == "pose":
         p = run.params(0.0, 0.0, 0.0, case["coef"], sm, True, setting == 5, 10.0, False)
@@ -209,3 +210,30 @@ def test_samplers_vs_reference_goldens():
             assert np.allclose(t.numpy(), g[f"images{i}"], rtol=1e-5, atol=1e-5), i
     finally:
         torch.randn_like = orig
+
+
+@pytest.mark.parametrize("kind,sigma,setting", CASES)
+def test_production_scatter_equals_full_kernel(kind, sigma, setting):
+    """the compacted / fp32-guarded scatter with the packed winner key (production path) against the full fp64
+    two-pass kernels (selected by candidate-level debug output): every per-cell result must be bit-identical."""
+    case = cases.small_multiview(kind)
+    x_a, ni_a, run_a = _cuda_step(kind, case, sigma, setting, debug=True)
+    x_b, ni_b, run_b = _cuda_step(kind, case, sigma, setting, debug="cells")
+    for k in ("cnt", "winner", "min_d"):
+        assert torch.equal(run_a.debug[k], run_b.debug[k]), k
+    assert torch.equal(ni_a, ni_b) and torch.equal(x_a, x_b)
+    # truncating 44 more bits of the log-range in the packed key makes most packed winners wrong: the verification
+    # must catch them and the exact winner pass must restore the same result
+    x_c, ni_c, run_c = _cuda_step(kind, case, sigma, setting, debug="cells", key_shift=50)
+    for k in ("cnt", "winner", "min_d"):
+        assert torch.equal(run_a.debug[k], run_c.debug[k]), k
+    assert torch.equal(ni_a, ni_c) and torch.equal(x_a, x_c)
+
+
+def test_production_scatter_full_size():
+    case = cases.full_multiview()
+    x_a, ni_a, run_a = _cuda_step("pose", case, 0.3, 5, debug=True)
+    x_b, ni_b, run_b = _cuda_step("pose", case, 0.3, 5, debug="cells")
+    for k in ("cnt", "winner", "min_d"):
+        assert torch.equal(run_a.debug[k], run_b.debug[k]), k
+    assert torch.equal(ni_a, ni_b) and torch.equal(x_a, x_b)

@@ -1,0 +1,19 @@
+"""Per-kernel view of the Langevin + cross-view step only (run under ncu's launch list)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import sdpc_b200  # noqa
+from sdpc_b200 import cabi
+from sdpc_b200.step import StepRunner
+from tests.golden import cases
+B = 8
+case = cases.full_multiview(B=B, A=B)
+run = StepRunner(case["x"].shape, "cuda:0", case["refer"], case["mask"], case["sky"], case["exist"], B,
+                 cabi.SDPC_VARIANT_POSE, to_world=case["toWorld"], from_world=case["fromWorld"])
+xx = case["x"].to("cuda:0")
+g, z = torch.randn_like(xx), torch.randn_like(xx)
+p = run.params(1e-5, 4e-3, 1.0, 0.01, 1.0, True, True, 10.0, False)
+b = run.buffers(xx, g, z)
+for _ in range(3):
+    run.step(p, b)
+torch.cuda.synchronize()
