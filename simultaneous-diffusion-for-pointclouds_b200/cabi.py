@@ -10,8 +10,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsdpc_b200.so")
 
 SDPC_VARIANT_POSE, SDPC_VARIANT_TRANSLATION = 0, 1
-PREC_FP32, PREC_TF32, PREC_BF16 = 0, 1, 2
-PRECISIONS = {"fp32": PREC_FP32, "tf32": PREC_TF32, "bf16": PREC_BF16}
+PREC_FP32, PREC_TF32, PREC_BF16, PREC_BF16X3 = 0, 1, 2, 3
+PRECISIONS = {"fp32": PREC_FP32, "tf32": PREC_TF32, "bf16": PREC_BF16, "bf16x3": PREC_BF16X3}
 
 
 class StepParams(C.Structure):

@@ -52,6 +52,7 @@ struct UmmaCfg {
 template <typename T, int N_TILE, bool SWAP>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const __grid_constant__ CUtensorMap tmap_a_lo, const __grid_constant__ CUtensorMap tmap_b_lo,
                  const ConvGeom g, const EpiParams e) {
   using Cfg = UmmaCfg<N_TILE>;
   constexpr bool kTf32 = sizeof(T) == 4;
@@ -75,6 +76,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
+    if (g.passes > 1) { prefetch_tmap(&tmap_a_lo); prefetch_tmap(&tmap_b_lo); }
     for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, kEpiWarps); }
     fence_barrier_init();
@@ -89,7 +91,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const uint32_t tmem_base = *tmem_slot;
 
   const int k_chunks = g.Cin / kBK;
-  const int k_iters = g.taps * k_chunks;
+  const int k_iters = g.passes * g.taps * k_chunks;
   const int tiles_per_img = g.tiles_w * g.tiles_h;
 
   if (warp == 0) {
@@ -102,18 +104,23 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int rem = tile - n * tiles_per_img;
         const int h0 = (rem / g.tiles_w) * g.BH;
         const int w0 = (rem % g.tiles_w) * g.BW;
-        for (int tap = 0; tap < g.taps; ++tap) {
-          const int dy = (g.taps == 9) ? (tap / 3 - 1) * g.dil : 0;
-          const int dx = (g.taps == 9) ? (tap % 3 - 1) * g.dil : 0;
-          for (int kc = 0; kc < k_chunks; ++kc) {
-            mbar_wait(empty_bar + stage, phase ^ 1);
-            uint8_t* sa = smem + stage * Cfg::kStageBytes;
-            uint8_t* sb = sa + kABytes;
-            mbar_arrive_expect_tx(full_bar + stage, Cfg::kStageBytes);
-            // activations and weights land in the M-side (128 rows) or N-side (N_TILE rows) slot
-            tma_load_4d(SWAP ? sb : sa, &tmap_a, full_bar + stage, kc * kBK, w0 + g.in_pad + dx, h0 + g.in_pad + dy, n);
-            tma_load_3d(SWAP ? sa : sb, &tmap_b, full_bar + stage, kc * kBK, 0, tap);
-            if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        // bf16x3 arm: three passes over K accumulate X_hi.W_hi + X_hi.W_lo + X_lo.W_hi into the same accumulator
+        for (int pass = 0; pass < g.passes; ++pass) {
+          const CUtensorMap* ma = pass == 2 ? &tmap_a_lo : &tmap_a;
+          const CUtensorMap* mb = pass == 1 ? &tmap_b_lo : &tmap_b;
+          for (int tap = 0; tap < g.taps; ++tap) {
+            const int dy = (g.taps == 9) ? (tap / 3 - 1) * g.dil : 0;
+            const int dx = (g.taps == 9) ? (tap % 3 - 1) * g.dil : 0;
+            for (int kc = 0; kc < k_chunks; ++kc) {
+              mbar_wait(empty_bar + stage, phase ^ 1);
+              uint8_t* sa = smem + stage * Cfg::kStageBytes;
+              uint8_t* sb = sa + kABytes;
+              mbar_arrive_expect_tx(full_bar + stage, Cfg::kStageBytes);
+              // activations and weights land in the M-side (128 rows) or N-side (N_TILE rows) slot
+              tma_load_4d(SWAP ? sb : sa, ma, full_bar + stage, kc * kBK, w0 + g.in_pad + dx, h0 + g.in_pad + dy, n);
+              tma_load_3d(SWAP ? sa : sb, mb, full_bar + stage, kc * kBK, 0, tap);
+              if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+            }
           }
         }
       }
@@ -272,11 +279,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               o[0] = elu_sel<T>(o[0], red); o[1] = elu_sel<T>(o[1], red); o[2] = elu_sel<T>(o[2], red); o[3] = elu_sel<T>(o[3], red);
             }
             T* d = op_p + op_off[it];
-            store_op4<T>(d, o, red);
-            if (dup_w[it]) store_op4<T>(d + dup_w[it], o, red);
+            store_op4<T>(d, o, red, e.op_lo_off);
+            if (dup_w[it]) store_op4<T>(d + dup_w[it], o, red, e.op_lo_off);
             if (dup_h[it]) {
-              store_op4<T>(d + dup_h[it], o, red);
-              if (dup_w[it]) store_op4<T>(d + dup_h[it] + dup_w[it], o, red);
+              store_op4<T>(d + dup_h[it], o, red, e.op_lo_off);
+              if (dup_w[it]) store_op4<T>(d + dup_h[it] + dup_w[it], o, red, e.op_lo_off);
             }
           }
         }
@@ -343,7 +350,7 @@ static int launch_t(const UmmaConvLaunch& L, cudaStream_t stream) {
     attr_set = true;
   }
   int grid = L.geom.num_tiles < L.num_sms ? L.geom.num_tiles : L.num_sms;
-  conv_umma_kernel<T, N_TILE, SWAP><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(L.tmap_a, L.tmap_b, L.geom, L.epi);
+  conv_umma_kernel<T, N_TILE, SWAP><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(L.tmap_a, L.tmap_b, L.tmap_a_lo, L.tmap_b_lo, L.geom, L.epi);
   SDPC_CUDA(cudaGetLastError());
   return SDPC_OK;
 }

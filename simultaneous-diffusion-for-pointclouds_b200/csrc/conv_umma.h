@@ -11,6 +11,7 @@ namespace sdpc {
 struct UmmaConvLaunch {
   CUtensorMap tmap_a;   // input operand  {C, W+2p, H+2p, N}, box {BK, BW, BH, 1}, 128B swizzle
   CUtensorMap tmap_b;   // weights        {Cin, Cout, taps}, box {BK, Cout, 1}
+  CUtensorMap tmap_a_lo, tmap_b_lo;   // residual (lo) planes of the bf16x3 arm (copies of a / b otherwise)
   ConvGeom geom;
   EpiParams epi;
   int elem_bytes;       // 2 = bf16 (kind::f16), 4 = tf32 (kind::tf32)

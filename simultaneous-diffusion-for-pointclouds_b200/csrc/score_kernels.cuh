@@ -161,9 +161,9 @@ enum { OP_COPY = 0, OP_ELU = 1, OP_NORM_ELU = 2 };
 enum { HALO_CIRC = 0, HALO_ZERO = 1 };
 
 template <typename T>
-__device__ __forceinline__ void store_op8(T* dst, const float* v, bool tf32) {
-  store_op4<T>(dst, v, tf32);
-  store_op4<T>(dst + 4, v + 4, tf32);
+__device__ __forceinline__ void store_op8(T* dst, const float* v, bool tf32, size_t lo_off = 0) {
+  store_op4<T>(dst, v, tf32, lo_off);
+  store_op4<T>(dst + 4, v + 4, tf32, lo_off);
 }
 
 // One thread: 8 channels x 4 consecutive pixels of a row (all loads issued before use).  With
@@ -171,7 +171,7 @@ __device__ __forceinline__ void store_op8(T* dst, const float* v, bool tf32) {
 template <typename T>
 __global__ void __launch_bounds__(256, 3)
 to_operand_kernel(const float* __restrict__ in, const float* __restrict__ coef, T* __restrict__ out, int N, int H,
-                  int W, int C, int P, int mode, int halo, int tf32) {
+                  int W, int C, int P, int mode, int halo, int tf32, size_t lo_off) {
   const int C8 = C / 8, W4 = W / 4;
   const size_t total = (size_t)N * H * W4 * C8;
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -207,11 +207,11 @@ to_operand_kernel(const float* __restrict__ in, const float* __restrict__ coef, 
     }
     const int w = w0 + j;
     if (halo == HALO_ZERO) {
-      store_op8<T>(out + (((size_t)n * Hp + h + P) * Wp + w + P) * C + c8 * 8, v, tf32 != 0);
+      store_op8<T>(out + (((size_t)n * Hp + h + P) * Wp + w + P) * C + c8 * 8, v, tf32 != 0, lo_off);
     } else {
       const HaloPos d = halo_pos(h, w, H, W, P);
       for_each_halo_pos(d, [&](int hp, int wp) {
-        store_op8<T>(out + (((size_t)n * Hp + hp) * Wp + wp) * C + c8 * 8, v, tf32 != 0);
+        store_op8<T>(out + (((size_t)n * Hp + hp) * Wp + wp) * C + c8 * 8, v, tf32 != 0, lo_off);
       });
     }
   }
@@ -248,7 +248,7 @@ constexpr int kPoolSmemBytes = ((kPoolTH + 4) + kPoolTH) * (kPoolTW + 4) * (kPoo
 template <typename T>
 __global__ void __launch_bounds__(256)
 maxpool5_kernel(const float* __restrict__ in, float* __restrict__ x0_out, T* __restrict__ out, int N, int H, int W,
-                int C, int P, int elu_in, int tf32) {
+                int C, int P, int elu_in, int tf32, size_t lo_off) {
   // Shared-memory tiled, separable 5x5 max (window clipped at the image border = MaxPool2d's -inf padding):
   // load the (8+4) x (16+4) x 32-channel input patch once (128-byte pixel segments, coalesced), take the
   // vertical 5-max, then the horizontal 5-max, and store the operand (with its circular-halo duplicates).
@@ -312,7 +312,7 @@ maxpool5_kernel(const float* __restrict__ in, float* __restrict__ x0_out, T* __r
     const int w = w0 + cc;
     const HaloPos d = halo_pos(h, w, H, W, P);
     for_each_halo_pos(d, [&](int hp, int wp) {
-      store_op4<T>(out + (((size_t)n * Hp + hp) * Wp + wp) * C + c0 + c4 * 4, o, red);
+      store_op4<T>(out + (((size_t)n * Hp + hp) * Wp + wp) * C + c0 + c4 * 4, o, red, lo_off);
     });
     if (x0_out) {
       const float4 a = tin[pr + 2][cc + 2][c4];
@@ -334,7 +334,7 @@ __device__ __forceinline__ float4 pool4(const float* in, size_t i00, size_t i10,
 template <typename T>
 __global__ void __launch_bounds__(256)
 meanpool_kernel(const float* __restrict__ in, const float* __restrict__ add, T* __restrict__ out_op,
-                float* __restrict__ out_raw, int N, int H, int W, int C, int tf32) {
+                float* __restrict__ out_raw, int N, int H, int W, int C, int tf32, size_t lo_off) {
   const int Ho = H / 2, Wo = W / 2, C4 = C / 4;
   const size_t total = (size_t)N * Ho * Wo * C4;
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -353,7 +353,7 @@ meanpool_kernel(const float* __restrict__ in, const float* __restrict__ add, T* 
   if (out_raw) *reinterpret_cast<float4*>(out_raw + i * 4) = v;
   if (out_op) {
     float vv[4] = {v.x, v.y, v.z, v.w};
-    store_op4<T>(out_op + i * 4, vv, tf32 != 0);
+    store_op4<T>(out_op + i * 4, vv, tf32 != 0, lo_off);
   }
 }
 
@@ -470,7 +470,7 @@ __global__ void nhwc_to_nchw_kernel(const float* __restrict__ in, float* __restr
 // ------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void pack_weight_kernel(const float* __restrict__ src, T* __restrict__ dst_tc, float* __restrict__ dst_simt,
-                                   int Cout, int Cin, int taps, int tf32) {
+                                   int Cout, int Cin, int taps, int tf32, T* __restrict__ dst_lo = nullptr) {
   const size_t total = (size_t)Cout * Cin * taps;
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
@@ -479,8 +479,13 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, T* __restrict_
   const int co = (int)(i / ((size_t)taps * Cin));
   const float v = src[i];
   if (dst_tc) {
-    if constexpr (sizeof(T) == 2) dst_tc[((size_t)tap * Cout + co) * Cin + ci] = __float2bfloat16_rn(v);
-    else dst_tc[((size_t)tap * Cout + co) * Cin + ci] = tf32 ? round_tf32(v) : v;
+    if constexpr (sizeof(T) == 2) {
+      const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+      dst_tc[((size_t)tap * Cout + co) * Cin + ci] = hi;
+      if (dst_lo) dst_lo[((size_t)tap * Cout + co) * Cin + ci] = __float2bfloat16_rn(v - __bfloat162float(hi));
+    } else {
+      dst_tc[((size_t)tap * Cout + co) * Cin + ci] = tf32 ? round_tf32(v) : v;
+    }
   }
   if (dst_simt) dst_simt[((size_t)tap * Cin + ci) * Cout + co] = v;
 }

@@ -18,6 +18,7 @@ struct ConvGeom {
   int BW, BH;         // pixel tile: BH rows x BW columns (BW a power of two, BW*BH = pixels per tile)
   int bw_shift;       // log2(BW)
   int tiles_w, tiles_h, num_tiles;
+  int passes;         // 1, or 3 for the bf16x3 arm: (A_hi,B_hi), (A_hi,B_lo), (A_lo,B_hi) accumulated in TMEM
 };
 
 // Fused epilogue of every convolution (SIMT and tcgen05 kernels share it).
@@ -30,6 +31,7 @@ struct EpiParams {
   int op_pad;
   int op_elu;             // 1: ELU before the operand store
   int op_tf32;            // 1: round the fp32 operand to tf32 (rna)
+  size_t op_lo_off;       // bf16x3 arm: element offset of the residual (lo) plane of out_op, else 0
   float* stats;           // per-tile partial sums [tile][parts][Cout][2] (sum, sum of squares) of the out_raw
                           // values for InstanceNorm++ (parts = 4 pixel quadrants, or 2 chunk parities when swapped), or null
 };
@@ -49,22 +51,33 @@ __device__ __forceinline__ float round_tf32(float v) {
   return __uint_as_float(r);
 }
 
+// lo_off != 0 (bf16x3 arm): the operand is stored as two bf16 planes, hi = bf16(v) at dst and the rounding
+// residual lo = bf16(v - hi) at dst + lo_off, so that hi + lo carries ~16 mantissa bits.
 template <typename T>
-__device__ __forceinline__ void store_op4(T* dst, const float* v, bool tf32);
+__device__ __forceinline__ void store_op4(T* dst, const float* v, bool tf32, size_t lo_off = 0);
 template <>
-__device__ __forceinline__ void store_op4<float>(float* dst, const float* v, bool tf32) {
+__device__ __forceinline__ void store_op4<float>(float* dst, const float* v, bool tf32, size_t) {
   float4 o = tf32 ? make_float4(round_tf32(v[0]), round_tf32(v[1]), round_tf32(v[2]), round_tf32(v[3]))
                   : make_float4(v[0], v[1], v[2], v[3]);
   *reinterpret_cast<float4*>(dst) = o;
 }
 template <>
-__device__ __forceinline__ void store_op4<__nv_bfloat16>(__nv_bfloat16* dst, const float* v, bool) {
+__device__ __forceinline__ void store_op4<__nv_bfloat16>(__nv_bfloat16* dst, const float* v, bool, size_t lo_off) {
   __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]);
   __nv_bfloat162 b = __floats2bfloat162_rn(v[2], v[3]);
   uint2 o;
   o.x = *reinterpret_cast<uint32_t*>(&a);
   o.y = *reinterpret_cast<uint32_t*>(&b);
   *reinterpret_cast<uint2*>(dst) = o;
+  if (lo_off) {
+    const float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+    __nv_bfloat162 la = __floats2bfloat162_rn(v[0] - fa.x, v[1] - fa.y);
+    __nv_bfloat162 lb = __floats2bfloat162_rn(v[2] - fb.x, v[3] - fb.y);
+    uint2 l;
+    l.x = *reinterpret_cast<uint32_t*>(&la);
+    l.y = *reinterpret_cast<uint32_t*>(&lb);
+    *reinterpret_cast<uint2*>(dst + lo_off) = l;
+  }
 }
 
 // Positions a pixel (h,w) of an HxW image occupies in a tensor padded by P with circular wrap: its
@@ -130,7 +143,7 @@ __device__ __forceinline__ void epi_store(const EpiParams& e, const ConvGeom& g,
     for_each_halo_pos(d, [&](int hp, int wp) {
       T* dst = reinterpret_cast<T*>(e.out_op) + (((size_t)n * Hp + hp) * Wp + wp) * g.Cout + c0;
 #pragma unroll
-      for (int i = 0; i < NV; i += 4) store_op4<T>(dst + i, v + i, e.op_tf32 != 0);
+      for (int i = 0; i < NV; i += 4) store_op4<T>(dst + i, v + i, e.op_tf32 != 0, e.op_lo_off);
     });
   }
 }

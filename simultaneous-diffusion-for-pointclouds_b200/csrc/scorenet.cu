@@ -32,6 +32,7 @@ struct ParamSlot {
 
 struct ConvW {
   void* w_tc = nullptr;      // [tap][Cout][Cin] in the operand type (bf16 / tf32-rounded fp32)
+  void* w_tc_lo = nullptr;   // bf16x3 arm: residual plane bf16(w - hi)
   float* w_simt = nullptr;   // [tap][Cin][Cout] fp32
   const float* bias = nullptr;
   int Cout = 0, Cin = 0, taps = 0;
@@ -40,6 +41,7 @@ struct ConvW {
 struct Buf {
   char* ptr = nullptr;
   int N = 0, H = 0, W = 0, C = 0, pad = 0, elem = 4;
+  size_t lo_off = 0;         // bf16x3 operands: element offset of the residual plane (0 = single plane)
   size_t bytes = 0;
   size_t off = 0;
   bool valid() const { return bytes != 0; }
@@ -94,7 +96,8 @@ struct sdpc_score {
     if (!ev_pool.empty()) { cudaEvent_t e = ev_pool.back(); ev_pool.pop_back(); return e; }
     cudaEvent_t e; cudaEventCreate(&e); return e;
   }
-  int elem_bytes() const { return cfg.precision == SDPC_PREC_BF16 ? 2 : 4; }
+  int elem_bytes() const { return (cfg.precision == SDPC_PREC_BF16 || cfg.precision == SDPC_PREC_BF16X3) ? 2 : 4; }
+  bool x3() const { return cfg.precision == SDPC_PREC_BF16X3; }
   const float* P(const std::string& n) const { return params[index.at(n)].dev; }
 };
 
@@ -209,7 +212,13 @@ struct Builder {
     return b;
   }
   Buf raw(int H, int W, int C) { return alloc(N, H, W, C, 0, 4); }
-  Buf operand(int H, int W, int C, int pad) { return alloc(N, H, W, C, pad, h->elem_bytes()); }
+  Buf operand(int H, int W, int C, int pad) {
+    if (!h->x3()) return alloc(N, H, W, C, pad, h->elem_bytes());
+    Buf b = alloc(2 * N, H, W, C, pad, 2);                 // hi planes of all views, then lo planes
+    b.N = N;
+    b.lo_off = (size_t)N * (H + 2 * pad) * (W + 2 * pad) * C;
+    return b;
+  }
   void release(Buf& b) {
     if (!b.valid()) return;
     if (!h->keep_all) free_list.insert({b.bytes, b.off});
@@ -286,11 +295,13 @@ struct Builder {
     T* o = (T*)out.ptr;
     const int n = N, H = x.H, W = x.W, C = x.C, P = out.pad;
     const size_t total = (size_t)n * H * (W / 4) * (C / 8);
-    const size_t border = (size_t)n * ((size_t)(H + 2 * P) * (W + 2 * P) - (size_t)H * W) * (C / 8);
+    const size_t lo_off = out.lo_off;
+    const int nz = lo_off ? 2 * n : n;                      // both planes get the zero border
+    const size_t border = (size_t)nz * ((size_t)(H + 2 * P) * (W + 2 * P) - (size_t)H * W) * (C / 8);
     const bool zero = halo == HALO_ZERO && P > 0;
     push([=](cudaStream_t s, const float*, const int64_t*, float*) -> int {
-      if (zero) zero_halo_kernel<T><<<blocks(border), 256, 0, s>>>(o, n, H, W, C, P);
-      to_operand_kernel<T><<<blocks(total), 256, 0, s>>>(in, coef, o, n, H, W, C, P, mode, halo, tf32);
+      if (zero) zero_halo_kernel<T><<<blocks(border), 256, 0, s>>>(o, nz, H, W, C, P);
+      to_operand_kernel<T><<<blocks(total), 256, 0, s>>>(in, coef, o, n, H, W, C, P, mode, halo, tf32, lo_off);
       SDPC_CUDA(cudaGetLastError());
       return SDPC_OK;
     }, zero ? 2 : 1);
@@ -316,9 +327,10 @@ struct Builder {
     const unsigned nblk = (unsigned)((size_t)n * (H / kPoolTH) * (W / kPoolTW) * (C / kPoolCB));
     void* o = out.ptr;
     const int elem = out.elem, ei = elu_in ? 1 : 0;
+    const size_t lo_off = out.lo_off;
     push([=](cudaStream_t s, const float*, const int64_t*, float*) -> int {
-      if (elem == 2) maxpool5_kernel<__nv_bfloat16><<<nblk, 256, kPoolSmemBytes, s>>>(in, x0, (__nv_bfloat16*)o, n, H, W, C, 1, ei, tf32);
-      else maxpool5_kernel<float><<<nblk, 256, kPoolSmemBytes, s>>>(in, x0, (float*)o, n, H, W, C, 1, ei, tf32);
+      if (elem == 2) maxpool5_kernel<__nv_bfloat16><<<nblk, 256, kPoolSmemBytes, s>>>(in, x0, (__nv_bfloat16*)o, n, H, W, C, 1, ei, tf32, lo_off);
+      else maxpool5_kernel<float><<<nblk, 256, kPoolSmemBytes, s>>>(in, x0, (float*)o, n, H, W, C, 1, ei, tf32, lo_off);
       SDPC_CUDA(cudaGetLastError());
       return SDPC_OK;
     });
@@ -360,6 +372,8 @@ struct Builder {
     e.op_pad = out_op ? out_op->pad : 0;
     e.op_elu = op_elu ? 1 : 0;
     e.op_tf32 = h->cfg.precision == SDPC_PREC_TF32;
+    e.op_lo_off = out_op ? out_op->lo_off : 0;
+    g.passes = h->x3() ? 3 : 1;
     e.stats = (stats_out && stats_out->valid()) ? (float*)(base + plan->stats_off + stats_out->off) : nullptr;
     if (cw.taps == 9 && in.pad < dil) { status = set_error(SDPC_ERR_STATE, "plan: halo %d < dilation %d for %s", in.pad, dil, wname.c_str()); return; }
     if (h->cfg.precision == SDPC_PREC_FP32) {
@@ -385,6 +399,13 @@ struct Builder {
     uint32_t bbox[3] = {(uint32_t)bk, (uint32_t)cw.Cout, 1u};
     if (int st = make_tmap(&L.tmap_a, in.ptr, L.elem_bytes, 4, adims, abox)) { status = st; return; }
     if (int st = make_tmap(&L.tmap_b, cw.w_tc, L.elem_bytes, 3, bdims, bbox)) { status = st; return; }
+    L.tmap_a_lo = L.tmap_a;
+    L.tmap_b_lo = L.tmap_b;
+    if (h->x3()) {
+      if (!in.lo_off || !cw.w_tc_lo) { status = set_error(SDPC_ERR_STATE, "bf16x3: operand %s has no residual plane", wname.c_str()); return; }
+      if (int st = make_tmap(&L.tmap_a_lo, in.ptr + in.lo_off * 2, 2, 4, adims, abox)) { status = st; return; }
+      if (int st = make_tmap(&L.tmap_b_lo, cw.w_tc_lo, 2, 3, bdims, bbox)) { status = st; return; }
+    }
     const double fl = 2.0 * (double)N * in.H * in.W * cw.Cout * cw.Cin * cw.taps;
     plan->umma_flops += fl;
     sdpc_score* hh = h;
@@ -463,11 +484,12 @@ struct Builder {
     void* oo = out_op ? out_op->ptr : nullptr;
     float* orr = out_raw ? (float*)out_raw->ptr : nullptr;
     const int elem = out_op ? out_op->elem : 4;
+    const size_t lo_off = out_op ? out_op->lo_off : 0;
     const int n = N, H = x.H, W = x.W, C = x.C, tf32 = h->cfg.precision == SDPC_PREC_TF32;
     const size_t total = (size_t)n * (H / 2) * (W / 2) * (C / 4);
     push([=](cudaStream_t s, const float*, const int64_t*, float*) -> int {
-      if (elem == 2) meanpool_kernel<__nv_bfloat16><<<blocks(total), 256, 0, s>>>(in, ad, (__nv_bfloat16*)oo, orr, n, H, W, C, tf32);
-      else meanpool_kernel<float><<<blocks(total), 256, 0, s>>>(in, ad, (float*)oo, orr, n, H, W, C, tf32);
+      if (elem == 2) meanpool_kernel<__nv_bfloat16><<<blocks(total), 256, 0, s>>>(in, ad, (__nv_bfloat16*)oo, orr, n, H, W, C, tf32, lo_off);
+      else meanpool_kernel<float><<<blocks(total), 256, 0, s>>>(in, ad, (float*)oo, orr, n, H, W, C, tf32, lo_off);
       SDPC_CUDA(cudaGetLastError());
       return SDPC_OK;
     });
@@ -689,7 +711,7 @@ extern "C" int sdpc_score_create(const sdpc_score_config* cfg, sdpc_score_t** ou
   if (!cfg || !out) return set_error(SDPC_ERR_ARG, "score_create: null argument");
   if (cfg->channels != 2) return set_error(SDPC_ERR_UNSUPPORTED, "channels must be 2");
   if (cfg->ngf != 128) return set_error(SDPC_ERR_UNSUPPORTED, "ngf must be 128 (the only LiDAR configuration)");
-  if (cfg->precision < 0 || cfg->precision > 2) return set_error(SDPC_ERR_ARG, "unknown precision %d", cfg->precision);
+  if (cfg->precision < 0 || cfg->precision > 3) return set_error(SDPC_ERR_ARG, "unknown precision %d", cfg->precision);
   if (cfg->height < 16 || cfg->width < 64 || cfg->width % 64 || cfg->height % 16 || (cfg->width & (cfg->width - 1)))
     return set_error(SDPC_ERR_UNSUPPORTED, "need H %% 16 == 0, W a power of two >= 64 (got %dx%d)", cfg->height, cfg->width);
   if (cfg->num_classes <= 0 || cfg->max_views <= 0) return set_error(SDPC_ERR_ARG, "num_classes/max_views must be positive");
@@ -715,7 +737,7 @@ extern "C" int sdpc_score_destroy(sdpc_score_t* h) {
   h->plan.reset_graph();
   if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   for (auto& p : h->params) if (p.dev) cudaFree(p.dev);
-  for (auto& kv : h->convs) { if (kv.second.w_tc) cudaFree(kv.second.w_tc); if (kv.second.w_simt) cudaFree(kv.second.w_simt); }
+  for (auto& kv : h->convs) { if (kv.second.w_tc) cudaFree(kv.second.w_tc); if (kv.second.w_tc_lo) cudaFree(kv.second.w_tc_lo); if (kv.second.w_simt) cudaFree(kv.second.w_simt); }
   delete h;
   return SDPC_OK;
 }
@@ -770,7 +792,9 @@ extern "C" int sdpc_score_finalize(sdpc_score_t* h, void* stream_) {
       pack_weight_kernel<float><<<blocks, 256, 0, stream>>>(p.dev, (float*)cw.w_tc, nullptr, cw.Cout, cw.Cin, cw.taps, 1);
     } else {
       if (!cw.w_tc) SDPC_CUDA(cudaMalloc(&cw.w_tc, n * sizeof(__nv_bfloat16)));
-      pack_weight_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>(p.dev, (__nv_bfloat16*)cw.w_tc, nullptr, cw.Cout, cw.Cin, cw.taps, 0);
+      if (h->x3() && !cw.w_tc_lo) SDPC_CUDA(cudaMalloc(&cw.w_tc_lo, n * sizeof(__nv_bfloat16)));
+      pack_weight_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>(p.dev, (__nv_bfloat16*)cw.w_tc, nullptr, cw.Cout, cw.Cin, cw.taps, 0,
+                                                                    (__nv_bfloat16*)cw.w_tc_lo);
     }
     SDPC_CUDA(cudaGetLastError());
   }

@@ -4,6 +4,7 @@ Oracle: oracle/scorenet_ref.py (torch fp32, pinned bit-for-bit on the reference)
 fixture tests/golden/scorenet_small.npz produced by the unmodified reference module.
 Tolerances (max abs error / max abs value of the reference tensor):
   fp32  (CUDA-core FMA)            1e-4
+  bf16x3 (tcgen05, hi/lo split)    1e-3   the tensor-core arm that meets north_star's fp32 bound
   tf32  (tcgen05 kind::tf32)       2e-2   (measured 6e-3..8e-3; what cuDNN's default TF32 convs give the reference on a GPU)
   bf16  (tcgen05 kind::f16, bf16)  1.5e-1 (measured 5e-2..6e-2), stated separately as north_star asks
 The fp32 arm is the one that meets north_star's 1e-3; per-block intermediates are held to 5x tighter bounds.
@@ -25,8 +26,8 @@ pytestmark = pytest.mark.gpu
 G = os.path.join(os.path.dirname(__file__), "golden")
 DEV = "cuda:0"
 N = argparse.Namespace
-TOL = {"fp32": 1e-4, "tf32": 2e-2, "bf16": 1.5e-1}      # output; per-block taps are 5x tighter (see below)
-TAP_TOL = {"fp32": 2e-5, "tf32": 4e-3, "bf16": 3e-2}
+TOL = {"fp32": 1e-4, "bf16x3": 1e-3, "tf32": 2e-2, "bf16": 1.5e-1}      # output; per-block taps are 5x tighter (see below)
+TAP_TOL = {"fp32": 2e-5, "bf16x3": 2e-4, "tf32": 4e-3, "bf16": 3e-2}
 TAPS = ["begin_conv", "res1.0", "res1.1", "res2.0", "res2.1", "res3.0", "res3.1", "res4.0", "res4.1",
         "refine1", "refine2", "refine3", "refine4"]
 
@@ -52,7 +53,7 @@ def _rel(a, b):
     return float((a - b).abs().max() / b.abs().max())
 
 
-@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3", "tf32", "bf16"])
 def test_small_forward_vs_reference_golden(precision):
     g = np.load(os.path.join(G, "scorenet_small.npz"))
     x, y = torch.from_numpy(g["x"]).to(DEV), torch.from_numpy(g["y"]).to(DEV)
@@ -70,7 +71,7 @@ def test_small_forward_vs_reference_golden(precision):
     assert err <= TOL[precision], err
 
 
-@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3", "tf32", "bf16"])
 def test_batch_and_reuse_consistency(precision):
     """views are independent (InstanceNorm is per sample): a batched forward equals per-view forwards,
     and buffer reuse across the plan does not leak between runs."""
@@ -86,7 +87,7 @@ def test_batch_and_reuse_consistency(precision):
         assert _rel(single, out[i:i + 1]) <= 1e-6
 
 
-@pytest.mark.parametrize("precision,H,W", [("fp32", 32, 128), ("tf32", 64, 1024), ("bf16", 64, 1024)])
+@pytest.mark.parametrize("precision,H,W", [("fp32", 32, 128), ("bf16x3", 64, 1024), ("tf32", 64, 1024), ("bf16", 64, 1024)])
 def test_larger_forward_vs_oracle(precision, H, W):
     """full-size input (the 128-wide TMA box and multi-tile scheduling) against the fp32 oracle on the device."""
     torch.backends.cudnn.allow_tf32 = False
