@@ -2,7 +2,7 @@
 # full ncu captures of the main kernels (one bench invocation per capture, short)
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
-CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
+CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-parity-arm"
 export SDPC_NO_GRAPH=1
 $CMD > gpurun_out/bench_plain.log 2>&1 || { echo "plain run failed"; tail gpurun_out/bench_plain.log; exit 1; }
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:maxpool5 -s 10 -c 2 -o gpurun_out/prof_maxpool $CMD > gpurun_out/ncu_maxpool.log 2>&1; echo "maxpool rc=$?"

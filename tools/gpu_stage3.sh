@@ -5,8 +5,8 @@ mkdir -p gpurun_out
 run() { name=$1; shift; timeout 900 "$@" > gpurun_out/$name.log 2>&1; rc=$?; echo "$name rc=$rc"; tail -n ${TAILN:-12} gpurun_out/$name.log; return $rc; }
 TAILN=30 run t_gpu python -m pytest tests -m gpu -q -s
 run bench_bf16 python bench.py --steps 10 --warmup 3 --no-cpu-baseline
-run bench_tf32 python bench.py --steps 10 --warmup 3 --precision tf32 --no-cpu-baseline
-CMD="python bench.py --steps 3 --warmup 3 --no-cpu-baseline"
+run bench_tf32 python bench.py --steps 10 --warmup 3 --precision tf32 --no-cpu-baseline --no-parity-arm
+CMD="python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-parity-arm"
 if run bench_plain $CMD; then
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 900 -c 360 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
   echo "ncu launches rc=$?"
