@@ -36,6 +36,10 @@ VIEWS_PER_GPU = 8
 STEP_LR = 6.2e-6
 
 
+WORKLOAD = ("Line.yml step (a-4): NCSN_LiDAR_small forward + Langevin update + cross-view (setting 5, minStepToShare "
+            "passed), 8 line poses per GPU (B=A=8), 2x64x1024, random-init 29.7M-param net, noise level 116/232")
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -166,8 +170,9 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "view-steps/sec", "value": v, "unit": "view-steps/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "Line.yml step (a-4): NCSN_LiDAR_small forward + Langevin + cross-view, 2x64x1024, "
-                                   "random-init; CPU sample = 1 view (A=1) per step", "level": LEVEL},
+            "config": {"workload": WORKLOAD, "views_per_gpu": VIEWS_PER_GPU,
+                       "cpu_sample": "each step = 1 view (A=1) of the workload: the reference's CPU path needs ~1 s per "
+                                     "view-forward, a full 8-view step with its O(A^2) cross-view block ~10 s"},
             "cpu_baseline": {"value": v, "unit": "view-steps/s", "cores": threads, "kind": "port",
                              "sample": f"{steps} steps x 1 view (A=1), oracle port (torch CPU ops), {threads} threads"},
             "e2e": {"value": v, "unit": "view-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -313,9 +318,7 @@ def run_b200(args):
         "metric": "view-steps/sec", "value": value, "unit": "view-steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
-        "config": {"workload": "Line.yml step (a-4): NCSN_LiDAR_small forward + Langevin update + cross-view "
-                               "(setting 5, minStepToShare passed), 8 line poses per GPU (B=A=8), 2x64x1024, random-init "
-                               "29.7M-param net, noise level 116/232",
+        "config": {"workload": WORKLOAD,
                    "views_per_gpu": B, "global_views": world * B, "parallelism": f"views x{world} (one group per rank)",
                    "l2": "per-step working set (activations, >2 GB) exceeds the 126 MB L2; no explicit flush",
                    "exchange": "1-float all-reduce(MAX) per step (tooHigh gate)" if world > 1 else "none"},

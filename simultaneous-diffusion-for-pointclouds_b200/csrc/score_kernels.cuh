@@ -166,26 +166,27 @@ __device__ __forceinline__ void store_op8(T* dst, const float* v, bool tf32, siz
   store_op4<T>(dst + 4, v + 4, tf32, lo_off);
 }
 
-// One thread: 8 channels x 4 consecutive pixels of a row (all loads issued before use).  With
+// One thread: 8 channels x kOpPix consecutive pixels of a row (all loads issued before use).  With
 // HALO_ZERO the halo is not written here: the buffer's border is cleared by zero_halo_kernel.
+constexpr int kOpPix = 2;
 template <typename T>
 __global__ void __launch_bounds__(256, 3)
 to_operand_kernel(const float* __restrict__ in, const float* __restrict__ coef, T* __restrict__ out, int N, int H,
                   int W, int C, int P, int mode, int halo, int tf32, size_t lo_off) {
-  const int C8 = C / 8, W4 = W / 4;
-  const size_t total = (size_t)N * H * W4 * C8;
+  const int C8 = C / 8, WS = W / kOpPix;
+  const size_t total = (size_t)N * H * WS * C8;
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int c8 = (int)(i % C8);
   size_t t = i / C8;
-  const int w0 = (int)(t % W4) * 4; t /= W4;
+  const int w0 = (int)(t % WS) * kOpPix; t /= WS;
   const int h = (int)(t % H);
   const int n = (int)(t / H);
   const int Hp = H + 2 * P, Wp = W + 2 * P;
   const float* src = in + (((size_t)n * H + h) * W + w0) * C + c8 * 8;
-  float4 a[4], b[4];
+  float4 a[kOpPix], b[kOpPix];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
+  for (int j = 0; j < kOpPix; ++j) {
     a[j] = *reinterpret_cast<const float4*>(src + (size_t)j * C);
     b[j] = *reinterpret_cast<const float4*>(src + (size_t)j * C + 4);
   }
@@ -196,7 +197,7 @@ to_operand_kernel(const float* __restrict__ in, const float* __restrict__ coef, 
     for (int k = 0; k < 8; ++k) { mu[k] = cf[k * 3]; ga[k] = cf[k * 3 + 1]; be[k] = cf[k * 3 + 2]; }
   }
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
+  for (int j = 0; j < kOpPix; ++j) {
     float v[8] = {a[j].x, a[j].y, a[j].z, a[j].w, b[j].x, b[j].y, b[j].z, b[j].w};
     if (mode == OP_NORM_ELU) {
 #pragma unroll
