@@ -213,6 +213,18 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
         for (int k = 0; k < 4; ++k) ssum[k] = ssq[k] = 0.f;
       };
+      // While the MMAs of this tile are still running, pull the residual rows of the tile into L2 so that the
+      // epilogue's residual loads hit L2 instead of HBM (the 8 warps cover the tile's pixels x Cout floats).
+      if (e.residual && e.prefetch_residual) {
+        const int tile_px = g.BW * g.BH;
+        const int lines_per_px = g.Cout / 32;                       // 128-byte lines per pixel
+        for (int i = (warp - 2) * 32 + lane; i < tile_px * lines_per_px; i += kEpiWarps * 32) {
+          const int m = i / lines_per_px, l = i - m * lines_per_px;
+          const int h = h0 + (m >> g.bw_shift), w = w0 + (m & (g.BW - 1));
+          const float* ptr = e.residual + (((size_t)n * g.H + h) * g.W + w) * g.Cout + l * 32;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+        }
+      }
       mbar_wait(acc_full + ab, acc_phase);
       __syncwarp();
       tc_fence_after();

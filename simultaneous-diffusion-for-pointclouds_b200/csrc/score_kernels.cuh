@@ -168,7 +168,7 @@ __device__ __forceinline__ void store_op8(T* dst, const float* v, bool tf32, siz
 
 // One thread: 8 channels x kOpPix consecutive pixels of a row (all loads issued before use).  With
 // HALO_ZERO the halo is not written here: the buffer's border is cleared by zero_halo_kernel.
-constexpr int kOpPix = 2;
+constexpr int kOpPix = 4;
 template <typename T>
 __global__ void __launch_bounds__(256, 3)
 to_operand_kernel(const float* __restrict__ in, const float* __restrict__ coef, T* __restrict__ out, int N, int H,
@@ -243,20 +243,22 @@ zero_halo_kernel(T* __restrict__ out, int N, int H, int W, int C, int P) {
 // CRP stage (layers.py:76-83): out_op = [ELU](maxpool5(in)) with circular halo for the conv that
 // follows; MaxPool2d(5,1,2) itself pads with -inf, i.e. the window is clipped at the image border.
 // ELU is monotone, so ELU(maxpool(x)) == maxpool(ELU(x)).  Optionally also emits x0 = ELU(in).
-constexpr int kPoolTH = 8, kPoolTW = 16, kPoolCB = 32;     // output tile: 8 rows x 16 columns x 32 channels per block
-constexpr int kPoolSmemBytes = ((kPoolTH + 4) + kPoolTH) * (kPoolTW + 4) * (kPoolCB / 4) * 16;
+constexpr int kPoolTH = 8, kPoolTW = 32, kPoolCB = 32;     // output tile: 8 rows x 32 columns x 32 channels per block
+constexpr int kPoolThreads = (kPoolTW + 4) * (kPoolCB / 4);  // 288: one thread per (input column, float4 of channels)
+constexpr int kPoolSmemBytes = kPoolTH * (kPoolTW + 4) * (kPoolCB / 4) * 16;   // 36 KB
 
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kPoolThreads)
 maxpool5_kernel(const float* __restrict__ in, float* __restrict__ x0_out, T* __restrict__ out, int N, int H, int W,
                 int C, int P, int elu_in, int tf32, size_t lo_off) {
-  // Shared-memory tiled, separable 5x5 max (window clipped at the image border = MaxPool2d's -inf padding):
-  // load the (8+4) x (16+4) x 32-channel input patch once (128-byte pixel segments, coalesced), take the
-  // vertical 5-max, then the horizontal 5-max, and store the operand (with its circular-halo duplicates).
-  extern __shared__ float4 pool_smem[];                                   // kPoolSmemBytes (> 48 KB: opt-in)
-  float4 (*tin)[kPoolTW + 4][kPoolCB / 4] = reinterpret_cast<float4 (*)[kPoolTW + 4][kPoolCB / 4]>(pool_smem);
-  float4 (*tv)[kPoolTW + 4][kPoolCB / 4] =
-      reinterpret_cast<float4 (*)[kPoolTW + 4][kPoolCB / 4]>(pool_smem + (kPoolTH + 4) * (kPoolTW + 4) * (kPoolCB / 4));
+  // Separable 5x5 max (window clipped at the image border = MaxPool2d's -inf padding).
+  //   phase A: a thread owns one input column (of the 32+4) x 4 channels, loads its 8+4 rows straight from global
+  //            memory (independent 128-bit loads, 8 lanes = one pixel's 128 contiguous bytes) and keeps a running
+  //            vertical 5-max in registers; only the 8 results go to shared memory.  The same thread emits
+  //            x0 = ELU(in) for its interior rows.
+  //   phase B: a thread owns 8 consecutive outputs of one row x 4 channels and slides the horizontal 5-max over the
+  //            12 shared-memory columns it needs, then stores the operand with its circular-halo duplicates.
+  __shared__ float4 tv[kPoolTH][kPoolTW + 4][kPoolCB / 4];
   const int CBn = C / kPoolCB, TWn = W / kPoolTW, THn = H / kPoolTH;
   int b = blockIdx.x;
   const int cb = b % CBn; b /= CBn;
@@ -264,61 +266,60 @@ maxpool5_kernel(const float* __restrict__ in, float* __restrict__ x0_out, T* __r
   const int th = b % THn;
   const int n = b / THn;
   const int h0 = th * kPoolTH, w0 = tw * kPoolTW, c0 = cb * kPoolCB;
+  const bool red = tf32 != 0;
   const float4 ninf = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-  // fixed thread roles (no integer divisions): c4 = float4 channel group, (pr, pc) = pixel sub-position;
-  // a thread covers rows pr (+8) and columns pc + 4j.
-  const int c4 = threadIdx.x & 7, pc = (threadIdx.x >> 3) & 3, pr = threadIdx.x >> 5;
+  {
+    const int c4 = threadIdx.x & 7, cc = threadIdx.x >> 3;          // cc in [0, 36)
+    const int ww = w0 - 2 + cc;
+    const bool col_ok = ww >= 0 && ww < W;
+    float4 v[kPoolTH + 4];
 #pragma unroll
-  for (int rr = 0; rr < 2; ++rr) {
-    const int r = pr + 8 * rr;
-    if (r < kPoolTH + 4) {
+    for (int r = 0; r < kPoolTH + 4; ++r) {
       const int hh = h0 - 2 + r;
+      v[r] = ninf;
+      if (col_ok && hh >= 0 && hh < H)
+        v[r] = *reinterpret_cast<const float4*>(in + (((size_t)n * H + hh) * W + ww) * C + c0 + c4 * 4);
+    }
 #pragma unroll
-      for (int j = 0; j < 5; ++j) {
-        const int cc = pc + 4 * j, ww = w0 - 2 + cc;
-        float4 v = ninf;
-        if (hh >= 0 && hh < H && ww >= 0 && ww < W)
-          v = *reinterpret_cast<const float4*>(in + (((size_t)n * H + hh) * W + ww) * C + c0 + c4 * 4);
-        tin[r][cc][c4] = v;
+    for (int r = 0; r < kPoolTH; ++r) {
+      float4 m = v[r];
+#pragma unroll
+      for (int k = 1; k < 5; ++k) {
+        m.x = fmaxf(m.x, v[r + k].x); m.y = fmaxf(m.y, v[r + k].y); m.z = fmaxf(m.z, v[r + k].z); m.w = fmaxf(m.w, v[r + k].w);
+      }
+      tv[r][cc][c4] = m;
+    }
+    if (x0_out && cc >= 2 && cc < kPoolTW + 2) {
+#pragma unroll
+      for (int r = 0; r < kPoolTH; ++r) {
+        const float4 a = v[r + 2];
+        *reinterpret_cast<float4*>(x0_out + (((size_t)n * H + h0 + r) * W + ww) * C + c0 + c4 * 4) =
+            make_float4(elu_sel<T>(a.x, red), elu_sel<T>(a.y, red), elu_sel<T>(a.z, red), elu_sel<T>(a.w, red));
       }
     }
   }
   __syncthreads();
+  if (threadIdx.x < 256) {
+    const int c4 = threadIdx.x & 7, seg = (threadIdx.x >> 3) & 3, r = threadIdx.x >> 5;   // 8 outputs: columns seg*8 ..
+    const int Hp = H + 2 * P, Wp = W + 2 * P;
+    const int h = h0 + r;
+    float4 cfl[12];
 #pragma unroll
-  for (int j = 0; j < 5; ++j) {
-    const int cc = pc + 4 * j;
-    float4 m = tin[pr][cc][c4];
+    for (int j = 0; j < 12; ++j) cfl[j] = tv[r][seg * 8 + j][c4];
 #pragma unroll
-    for (int k = 1; k < 5; ++k) {
-      const float4 v = tin[pr + k][cc][c4];
-      m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
-    }
-    tv[pr][cc][c4] = m;
-  }
-  __syncthreads();
-  const bool red = tf32 != 0;
-  const int Hp = H + 2 * P, Wp = W + 2 * P;
-  const int h = h0 + pr;
+    for (int j = 0; j < 8; ++j) {
+      float4 m = cfl[j];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int cc = pc + 4 * j;
-    float4 m = tv[pr][cc][c4];
-#pragma unroll
-    for (int k = 1; k < 5; ++k) {
-      const float4 v = tv[pr][cc + k][c4];
-      m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
-    }
-    float o[4] = {m.x, m.y, m.z, m.w};
-    if (elu_in) { o[0] = elu_sel<T>(o[0], red); o[1] = elu_sel<T>(o[1], red); o[2] = elu_sel<T>(o[2], red); o[3] = elu_sel<T>(o[3], red); }
-    const int w = w0 + cc;
-    const HaloPos d = halo_pos(h, w, H, W, P);
-    for_each_halo_pos(d, [&](int hp, int wp) {
-      store_op4<T>(out + (((size_t)n * Hp + hp) * Wp + wp) * C + c0 + c4 * 4, o, red, lo_off);
-    });
-    if (x0_out) {
-      const float4 a = tin[pr + 2][cc + 2][c4];
-      *reinterpret_cast<float4*>(x0_out + (((size_t)n * H + h) * W + w) * C + c0 + c4 * 4) =
-          make_float4(elu_sel<T>(a.x, red), elu_sel<T>(a.y, red), elu_sel<T>(a.z, red), elu_sel<T>(a.w, red));
+      for (int k = 1; k < 5; ++k) {
+        m.x = fmaxf(m.x, cfl[j + k].x); m.y = fmaxf(m.y, cfl[j + k].y); m.z = fmaxf(m.z, cfl[j + k].z); m.w = fmaxf(m.w, cfl[j + k].w);
+      }
+      float o[4] = {m.x, m.y, m.z, m.w};
+      if (elu_in) { o[0] = elu_sel<T>(o[0], red); o[1] = elu_sel<T>(o[1], red); o[2] = elu_sel<T>(o[2], red); o[3] = elu_sel<T>(o[3], red); }
+      const int w = w0 + seg * 8 + j;
+      const HaloPos d = halo_pos(h, w, H, W, P);
+      for_each_halo_pos(d, [&](int hp, int wp) {
+        store_op4<T>(out + (((size_t)n * Hp + hp) * Wp + wp) * C + c0 + c4 * 4, o, red, lo_off);
+      });
     }
   }
 }

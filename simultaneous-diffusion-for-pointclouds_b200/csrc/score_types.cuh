@@ -32,6 +32,7 @@ struct EpiParams {
   int op_elu;             // 1: ELU before the operand store
   int op_tf32;            // 1: round the fp32 operand to tf32 (rna)
   size_t op_lo_off;       // bf16x3 arm: element offset of the residual (lo) plane of out_op, else 0
+  int prefetch_residual;  // 1: the epilogue warps prefetch the tile's residual rows into L2 before the accumulator is ready
   float* stats;           // per-tile partial sums [tile][parts][Cout][2] (sum, sum of squares) of the out_raw
                           // values for InstanceNorm++ (parts = 4 pixel quadrants, or 2 chunk parities when swapped), or null
 };

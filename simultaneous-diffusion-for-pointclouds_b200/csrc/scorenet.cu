@@ -318,8 +318,6 @@ struct Builder {
   Buf maxpool(const Buf& x, bool elu_in, Buf* x0_out) {
     Buf out = operand(x.H, x.W, x.C, 1);
     if (dry()) return out;
-    cudaFuncSetAttribute(maxpool5_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPoolSmemBytes);
-    cudaFuncSetAttribute(maxpool5_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPoolSmemBytes);
     const float* in = (const float*)x.ptr;
     float* x0 = x0_out ? (float*)x0_out->ptr : nullptr;
     const int n = N, H = x.H, W = x.W, C = x.C;
@@ -329,8 +327,8 @@ struct Builder {
     const int elem = out.elem, ei = elu_in ? 1 : 0;
     const size_t lo_off = out.lo_off;
     push([=](cudaStream_t s, const float*, const int64_t*, float*) -> int {
-      if (elem == 2) maxpool5_kernel<__nv_bfloat16><<<nblk, 256, kPoolSmemBytes, s>>>(in, x0, (__nv_bfloat16*)o, n, H, W, C, 1, ei, tf32, lo_off);
-      else maxpool5_kernel<float><<<nblk, 256, kPoolSmemBytes, s>>>(in, x0, (float*)o, n, H, W, C, 1, ei, tf32, lo_off);
+      if (elem == 2) maxpool5_kernel<__nv_bfloat16><<<nblk, kPoolThreads, 0, s>>>(in, x0, (__nv_bfloat16*)o, n, H, W, C, 1, ei, tf32, lo_off);
+      else maxpool5_kernel<float><<<nblk, kPoolThreads, 0, s>>>(in, x0, (float*)o, n, H, W, C, 1, ei, tf32, lo_off);
       SDPC_CUDA(cudaGetLastError());
       return SDPC_OK;
     });
@@ -373,6 +371,7 @@ struct Builder {
     e.op_elu = op_elu ? 1 : 0;
     e.op_tf32 = h->cfg.precision == SDPC_PREC_TF32;
     e.op_lo_off = out_op ? out_op->lo_off : 0;
+    e.prefetch_residual = getenv("SDPC_NO_PREFETCH") ? 0 : 1;
     g.passes = h->x3() ? 3 : 1;
     e.stats = (stats_out && stats_out->valid()) ? (float*)(base + plan->stats_off + stats_out->off) : nullptr;
     if (cw.taps == 9 && in.pad < dil) { status = set_error(SDPC_ERR_STATE, "plan: halo %d < dilation %d for %s", in.pad, dil, wname.c_str()); return; }
