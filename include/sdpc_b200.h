@@ -193,6 +193,29 @@ int sdpc_langevin_reproject_step_host(const sdpc_step_params* p, const sdpc_step
                                       float* new_images_host, void* workspace, size_t workspace_bytes,
                                       void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Row N1: point cloud -> range image, the projection that renders the sampler's inputs
+ *   point_cloud_to_range_image        LiDARGen/datasets/lidar_utils.py:54-347
+ * ---------------------------------------------------------------------------------------- */
+typedef struct sdpc_projection_params {
+  int32_t n_points;       /* N */
+  int32_t point_stride;   /* doubles per point (>= 3: x, y, z first) */
+  int32_t intensity_col;  /* column of the remission value, or -1 (return_remission = False) */
+  int32_t height, width;  /* rowMax, colMax (width <= 1024) */
+  int32_t reserved;
+  double origin[3];       /* sensor origin subtracted from every point (lidar_utils.py:146-147) */
+  double h_min, dh;       /* horizontalMin, horizontalAngles (lidar_utils.py:103,109) */
+  double v_min, dv;       /* verticalMin, verticalAngles     (lidar_utils.py:104,118) */
+} sdpc_projection_params;
+
+size_t sdpc_projection_workspace_bytes(int height, int width);
+/* points: float64 [N, point_stride] (device).  Outputs (device), all already flipped by 180 degrees like the reference:
+ * depth [H,W] f64 (2057.701 where empty), intensity [H,W] f64 (nullable when intensity_col < 0), obfuscation [H,W] u8,
+ * sky [H,W] u8 (the reference returns it cleared), index [H,W] f64 (point index of the nearest point, -1 where empty). */
+int sdpc_pointcloud_to_range_image(const sdpc_projection_params* p, const double* points, double* depth,
+                                   double* intensity, uint8_t* obfuscation, uint8_t* sky, double* index,
+                                   void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

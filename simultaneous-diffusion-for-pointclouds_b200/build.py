@@ -18,6 +18,7 @@ UNITS = [
     ("common.cu", []),
     # reference evaluates every op with its own rounding: no FMA contraction (crossview_core.h)
     ("crossview.cu", ["-fmad=false"]),
+    ("lidar_projection.cu", ["-fmad=false"]),
     ("conv_umma.cu", []),
     ("scorenet.cu", []),
 ]

@@ -42,6 +42,12 @@ class ScoreConfig(C.Structure):
                 ("reserved", C.c_int32)]
 
 
+class ProjectionParams(C.Structure):
+    _fields_ = [("n_points", C.c_int32), ("point_stride", C.c_int32), ("intensity_col", C.c_int32), ("height", C.c_int32),
+                ("width", C.c_int32), ("reserved", C.c_int32), ("origin", C.c_double * 3), ("h_min", C.c_double),
+                ("dh", C.c_double), ("v_min", C.c_double), ("dv", C.c_double)]
+
+
 # every symbol include/sdpc_b200.h declares: (name, restype, argtypes)
 _P, _I, _SZ = C.c_void_p, C.c_int, C.c_size_t
 SYMBOLS = [
@@ -67,6 +73,8 @@ SYMBOLS = [
     ("sdpc_step_read_max", _I, [_P, _P, _P]),
     ("sdpc_crossview_share", _I, [C.POINTER(StepParams), C.POINTER(StepBuffers), _P, _SZ, _P]),
     ("sdpc_langevin_reproject_step", _I, [C.POINTER(StepParams), C.POINTER(StepBuffers), _P, _SZ, _P]),
+    ("sdpc_projection_workspace_bytes", _SZ, [_I, _I]),
+    ("sdpc_pointcloud_to_range_image", _I, [C.POINTER(ProjectionParams), _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     ("sdpc_langevin_reproject_step_host", _I, [C.POINTER(StepParams), C.POINTER(StepBuffers), _P, _P, _P, _P, _P, _SZ, _P]),
 ]
 

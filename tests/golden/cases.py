@@ -113,3 +113,23 @@ def scorenet_input(H, W, B=2, seed=99):
 def subsample_tap(t):
     """[B,C,H,W] -> strided sample (every 16th channel, 4th row, 8th column)."""
     return t[:, ::16, ::4, ::8].contiguous()
+
+
+# ---- row N1: point cloud -> range image -------------------------------------------------------------------
+N1_CASES = {"small": (6000, 16, 64, 11), "full": (60000, 64, 1024, 12)}       # tag: (points, H, W, seed)
+
+
+def synthetic_scan(n, seed):
+    """[n,4] float64 points (x, y, z, remission) of a ground plane + walls seen from near the origin, plus clutter
+    (several points per pixel, points outside the vertical field of view, a few exactly repeated points)."""
+    r = _rng(seed, 9)
+    az = r.uniform(-np.pi, np.pi, n)
+    el = np.radians(r.uniform(-27.0, 5.0, n))
+    d_ground = np.where(np.sin(el) < -0.02, 1.73 / np.maximum(-np.sin(el), 1e-3), 80.0)
+    d_wall = 25.0 / np.maximum(np.abs(np.cos(az)) * np.cos(el), 0.05)
+    d = np.minimum(np.minimum(d_ground, d_wall), 70.0) * r.uniform(0.97, 1.03, n)
+    d = np.where(r.uniform(size=n) < 0.05, d * r.uniform(0.2, 0.9, n), d)      # foreground clutter
+    pts = np.stack([d * np.cos(az) * np.cos(el), d * np.sin(az) * np.cos(el), d * np.sin(el), r.uniform(0, 1, n)], 1)
+    pts[-50:] = pts[:50]                                                       # exact duplicates (ties)
+    origin = np.array([0.3, -0.2, 0.1])
+    return pts, origin
