@@ -165,12 +165,29 @@ __device__ __forceinline__ void store_op8(T* dst, const float* v, bool tf32, siz
   store_op4<T>(dst, v, tf32, lo_off);
   store_op4<T>(dst + 4, v + 4, tf32, lo_off);
 }
+// bf16: one 16-byte store per plane instead of two 8-byte ones
+template <>
+__device__ __forceinline__ void store_op8<__nv_bfloat16>(__nv_bfloat16* dst, const float* v, bool, size_t lo_off) {
+  __nv_bfloat162 h[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) h[k] = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
+  *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(h);
+  if (lo_off) {
+    __nv_bfloat162 l[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = __bfloat1622float2(h[k]);
+      l[k] = __floats2bfloat162_rn(v[2 * k] - f.x, v[2 * k + 1] - f.y);
+    }
+    *reinterpret_cast<uint4*>(dst + lo_off) = *reinterpret_cast<const uint4*>(l);
+  }
+}
 
 // One thread: 8 channels x kOpPix consecutive pixels of a row (all loads issued before use).  With
 // HALO_ZERO the halo is not written here: the buffer's border is cleared by zero_halo_kernel.
 constexpr int kOpPix = 4;
-template <typename T>
-__global__ void __launch_bounds__(256, 3)
+template <typename T, int MINB>
+__global__ void __launch_bounds__(256, MINB)
 to_operand_kernel(const float* __restrict__ in, const float* __restrict__ coef, T* __restrict__ out, int N, int H,
                   int W, int C, int P, int mode, int halo, int tf32, size_t lo_off) {
   const int C8 = C / 8, WS = W / kOpPix;
@@ -192,7 +209,14 @@ to_operand_kernel(const float* __restrict__ in, const float* __restrict__ coef, 
   }
   float mu[8], ga[8], be[8];
   if (mode == OP_NORM_ELU) {
-    const float* cf = coef + ((size_t)n * C + c8 * 8) * 3;
+    // 8 channels x {mean, a, b} = 24 contiguous floats: six 16-byte loads
+    const float4* cf4 = reinterpret_cast<const float4*>(coef + ((size_t)n * C + c8 * 8) * 3);
+    float cf[24];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const float4 t4 = cf4[k];
+      cf[4 * k] = t4.x; cf[4 * k + 1] = t4.y; cf[4 * k + 2] = t4.z; cf[4 * k + 3] = t4.w;
+    }
 #pragma unroll
     for (int k = 0; k < 8; ++k) { mu[k] = cf[k * 3]; ga[k] = cf[k * 3 + 1]; be[k] = cf[k * 3 + 2]; }
   }

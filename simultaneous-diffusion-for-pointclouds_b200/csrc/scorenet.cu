@@ -299,9 +299,11 @@ struct Builder {
     const int nz = lo_off ? 2 * n : n;                      // both planes get the zero border
     const size_t border = (size_t)nz * ((size_t)(H + 2 * P) * (W + 2 * P) - (size_t)H * W) * (C / 8);
     const bool zero = halo == HALO_ZERO && P > 0;
+    const bool minb3 = getenv("SDPC_TOOP_MINB3") != nullptr;
     push([=](cudaStream_t s, const float*, const int64_t*, float*) -> int {
       if (zero) zero_halo_kernel<T><<<blocks(border), 256, 0, s>>>(o, nz, H, W, C, P);
-      to_operand_kernel<T><<<blocks(total), 256, 0, s>>>(in, coef, o, n, H, W, C, P, mode, halo, tf32, lo_off);
+      if (minb3) to_operand_kernel<T, 3><<<blocks(total), 256, 0, s>>>(in, coef, o, n, H, W, C, P, mode, halo, tf32, lo_off);
+      else to_operand_kernel<T, 2><<<blocks(total), 256, 0, s>>>(in, coef, o, n, H, W, C, P, mode, halo, tf32, lo_off);
       SDPC_CUDA(cudaGetLastError());
       return SDPC_OK;
     }, zero ? 2 : 1);
