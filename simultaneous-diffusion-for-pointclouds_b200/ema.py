@@ -1,10 +1,18 @@
-"""EMAHelper with the reference's interface and checkpoint layout (LiDARGen/models/ema.py:4-46):
-`shadow` maps un-prefixed parameter names to tensors (states[-1] of a checkpoint)."""
+"""Exponential-moving-average weights for the score network.
+
+Interface and checkpoint layout of the reference's helper (LiDARGen/models/ema.py:4-46): `shadow` maps
+un-prefixed parameter names to tensors and is what a checkpoint stores last (`states[-1]`,
+runners/ncsn_runner_kitti_simultaneous.py:485-489).  Sampling only needs `register` / `load_state_dict` /
+`ema`; `update` and `ema_copy` are kept so that training-side callers keep working.
+"""
+import torch
 import torch.nn as nn
 
 
-def _unwrap(module):
-    return module.module if isinstance(module, nn.DataParallel) else module
+def _trainable(module):
+    """(name, parameter) pairs of the wrapped network, DataParallel unwrapped, frozen parameters skipped."""
+    inner = module.module if isinstance(module, nn.DataParallel) else module
+    return inner, [(n, p) for n, p in inner.named_parameters() if p.requires_grad]
 
 
 class EMAHelper(object):
@@ -13,31 +21,35 @@ class EMAHelper(object):
         self.shadow = {}
 
     def register(self, module):
-        for name, param in _unwrap(module).named_parameters():
-            if param.requires_grad:
-                self.shadow[name] = param.data.clone()
+        _, params = _trainable(module)
+        self.shadow = {name: p.detach().clone() for name, p in params}
 
+    @torch.no_grad()
     def update(self, module):
-        for name, param in _unwrap(module).named_parameters():
-            if param.requires_grad:
-                self.shadow[name].data = (1. - self.mu) * param.data + self.mu * self.shadow[name].data
+        _, params = _trainable(module)
+        keep = self.mu
+        for name, p in params:
+            # (1 - mu) * theta + mu * shadow, one rounding per product like the reference expression
+            self.shadow[name] = torch.add(p.detach() * (1. - keep), self.shadow[name], alpha=keep)
 
+    @torch.no_grad()
     def ema(self, module):
-        inner = _unwrap(module)
-        for name, param in inner.named_parameters():
-            if param.requires_grad:
-                param.data.copy_(self.shadow[name].data)
-        if hasattr(inner, "refresh_weights"):
-            inner.refresh_weights()          # the CUDA handle keeps packed copies of the weights
+        """overwrite the live parameters with the averaged ones (what sampling does after loading a checkpoint)."""
+        inner, params = _trainable(module)
+        for name, p in params:
+            p.copy_(self.shadow[name].to(p.device))
+        refresh = getattr(inner, "refresh_weights", None)
+        if refresh is not None:
+            refresh()                      # the CUDA handle keeps repacked copies of the weights
 
     def ema_copy(self, module):
-        inner = _unwrap(module)
-        module_copy = type(inner)(inner.config).to(inner.config.device)
-        module_copy.load_state_dict(inner.state_dict())
+        inner, _ = _trainable(module)
+        twin = type(inner)(inner.config).to(inner.config.device)
+        twin.load_state_dict(inner.state_dict())
         if isinstance(module, nn.DataParallel):
-            module_copy = nn.DataParallel(module_copy)
-        self.ema(module_copy)
-        return module_copy
+            twin = nn.DataParallel(twin)
+        self.ema(twin)
+        return twin
 
     def state_dict(self):
         return self.shadow
