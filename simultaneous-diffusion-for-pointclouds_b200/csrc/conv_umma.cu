@@ -157,10 +157,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   } else {
     // ------------------------------------------------------------ epilogue (warps 2..9)
     // Eight warps: two per TMEM lane quadrant (a warp may only read lanes 32*(warp%4)..+31), taking the even
-    // and the odd 32-column chunks of the accumulator.  TMEM hands a thread one row x 32 columns; storing that
-    // directly would touch 32 different 128-byte lines per instruction.  Every 32x32 chunk is therefore
-    // transposed through an XOR-swizzled shared-memory tile so that 8 consecutive lanes cover one pixel's
-    // 128 contiguous bytes: all global loads (residual) and stores (raw / operand) are line-coalesced.
+    // and the odd 32-column chunks of the accumulator.  TMEM hands a thread one row x 32 columns.
+    //  SWAP   : row = output channel, columns = 32 consecutive pixels of one image row.  A warp-wide store of
+    //           column j is 32 consecutive channels of one pixel = one full 128-byte line (64 B for bf16), so
+    //           the registers are stored as they are: no transpose, no per-element address arithmetic
+    //           (pixel stride kCout is a compile-time immediate), per-thread bias and statistics.
+    //  !SWAP  : row = pixel, columns = 32 channels; storing that directly would touch 32 different lines per
+    //           instruction, so every 32x32 chunk is transposed through an XOR-swizzled shared-memory tile:
+    //           8 consecutive lanes then cover one pixel's 128 contiguous bytes.
+    constexpr int kCout = SWAP ? kTileM : N_TILE;            // the host only launches this variant for that Cout
     const int quad = warp & 3;                               // TMEM lane quadrant this warp may read
     const int half = (warp - 2) >> 2;                        // 0: even chunks, 1: odd chunks
     float* stg = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes + kBarrierBytes) + (warp - 2) * kStgFloats;
@@ -168,6 +173,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int psub = lane >> 3;                              // pixel within a group of 4
     // staging tile: 32 rows (pixels) x 8 float4 (32 channels); float4 slot of (row, c4) = row*8 + (c4 ^ (row & 7))
     auto stg_slot = [](int row, int c4) { return (row << 3) + (c4 ^ (row & 7)); };
+    const bool red = e.op_tf32 != 0;
+    const int P = e.op_pad, Wp = g.W + 2 * P, Hp = g.H + 2 * P;
     int local = 0;
     for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++local) {
       const int ab = local & 1;
@@ -176,133 +183,201 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const int rem = tile - n * tiles_per_img;
       const int h0 = (rem / g.tiles_w) * g.BH;
       const int w0 = (rem % g.tiles_w) * g.BW;
-      // element offsets of a tile pixel m into the raw tensors / the padded operand tensor, plus the deltas to
-      // the circular-halo duplicates it owns (0 = none).  BW is a power of two (g.bw_shift).
-      const int P = e.op_pad, Wp = g.W + 2 * P, Hp = g.H + 2 * P;
-      auto pixel_offsets = [&](int m, uint32_t& ro, uint32_t& oo, int32_t& dw, int32_t& dh) {
-        const int h = h0 + (m >> g.bw_shift), w = w0 + (m & (g.BW - 1));
-        ro = (uint32_t)((((size_t)n * g.H + h) * g.W + w) * g.Cout);
-        oo = (uint32_t)((((size_t)n * Hp + h + P) * Wp + w + P) * g.Cout);
-        dw = (w < P) ? g.W * g.Cout : ((w >= g.W - P) ? -g.W * g.Cout : 0);
-        dh = (h < P) ? g.H * Wp * g.Cout : ((h >= g.H - P) ? -g.H * Wp * g.Cout : 0);
-      };
-      uint32_t raw_off[8], op_off[8];
-      int32_t dup_w[8], dup_h[8];
-      if constexpr (!SWAP) {                                 // lane's 8 pixels are the same for every channel chunk
-#pragma unroll
-        for (int it = 0; it < 8; ++it) pixel_offsets(quad * 32 + it * 4 + psub, raw_off[it], op_off[it], dup_w[it], dup_h[it]);
-      }
-      // fused InstanceNorm++ statistics of the value written to out_raw: per lane 4 channels, summed over the
-      // lane's pixels, then over the 4 lanes sharing a channel quad; the warp's partial goes to its own slot
-      // [tile][part][Cout][2] (no atomics, every slot written exactly once; norm_finalize sums the slots).
-      float ssum[4] = {0.f, 0.f, 0.f, 0.f}, ssq[4] = {0.f, 0.f, 0.f, 0.f};
-      auto flush_stats = [&](int ch) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          ssum[k] += __shfl_xor_sync(0xffffffffu, ssum[k], 8);
-          ssq[k] += __shfl_xor_sync(0xffffffffu, ssq[k], 8);
-          ssum[k] += __shfl_xor_sync(0xffffffffu, ssum[k], 16);
-          ssq[k] += __shfl_xor_sync(0xffffffffu, ssq[k], 16);
-        }
-        if (psub == 0) {
-          const int part = SWAP ? half : quad;
-          float* sp = e.stats + (((size_t)tile * (SWAP ? 2 : 4) + part) * g.Cout + ch) * 2;
-          *reinterpret_cast<float4*>(sp) = make_float4(ssum[0], ssq[0], ssum[1], ssq[1]);
-          *reinterpret_cast<float4*>(sp + 4) = make_float4(ssum[2], ssq[2], ssum[3], ssq[3]);
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) ssum[k] = ssq[k] = 0.f;
-      };
       // While the MMAs of this tile are still running, pull the residual rows of the tile into L2 so that the
       // epilogue's residual loads hit L2 instead of HBM (the 8 warps cover the tile's pixels x Cout floats).
       if (e.residual && e.prefetch_residual) {
         const int tile_px = g.BW * g.BH;
-        const int lines_per_px = g.Cout / 32;                       // 128-byte lines per pixel
+        constexpr int lines_per_px = kCout / 32;                    // 128-byte lines per pixel
         for (int i = (warp - 2) * 32 + lane; i < tile_px * lines_per_px; i += kEpiWarps * 32) {
           const int m = i / lines_per_px, l = i - m * lines_per_px;
           const int h = h0 + (m >> g.bw_shift), w = w0 + (m & (g.BW - 1));
-          const float* ptr = e.residual + (((size_t)n * g.H + h) * g.W + w) * g.Cout + l * 32;
+          const float* ptr = e.residual + (((size_t)n * g.H + h) * g.W + w) * kCout + l * 32;
           asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
         }
       }
-      mbar_wait(acc_full + ab, acc_phase);
-      __syncwarp();
-      tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + ab * N_TILE;
+
+      if constexpr (SWAP) {
+        const int ch = quad * 32 + lane;                     // this thread's output channel
+        const float bias = e.bias ? e.bias[ch] : 0.0f;
+        float ssum = 0.0f, ssq = 0.0f;                       // InstanceNorm++ partial sums of this channel over the warp's pixels
+        mbar_wait(acc_full + ab, acc_phase);
+        __syncwarp();
+        tc_fence_after();
 #pragma unroll 1
-      for (int c0 = half * 32; c0 < N_TILE; c0 += 64) {
-        int ch;
-        if constexpr (!SWAP) {
-          ch = c0 + cq * 4;
-        } else {
-          ch = quad * 32 + cq * 4;
+        for (int c0 = half * 32; c0 < N_TILE; c0 += 64) {
+          // the chunk's 32 pixels lie on one image row (BW is a multiple of 32): pixel j at (h, w + j)
+          const int h = h0 + (c0 >> g.bw_shift), w = w0 + (c0 & (g.BW - 1));
+          const size_t raw0 = (((size_t)n * g.H + h) * g.W + w) * kCout + ch;
+          float res[32];
+          if (e.residual) {                                  // issued first: the latency overlaps the TMEM read
+            const float* rp = e.residual + raw0;
 #pragma unroll
-          for (int it = 0; it < 8; ++it) pixel_offsets(c0 + it * 4 + psub, raw_off[it], op_off[it], dup_w[it], dup_h[it]);
-        }
-        // issue the residual loads first: their latency overlaps the TMEM read and the staging round trip
-        float4 res[8];
-        if (e.residual) {
-          const float* rp = e.residual + ch;
+            for (int j = 0; j < 32; ++j) res[j] = rp[j * kCout];
+          }
+          uint32_t r[32];
+          tmem_ld_32x32(t_addr + c0, r);
+          tmem_ld_wait();
+          if (c0 + 64 >= N_TILE) {                           // this warp's last chunk: its part of the accumulator is read
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty + ab);
+          }
+          float v[32];
 #pragma unroll
-          for (int it = 0; it < 8; ++it) res[it] = *reinterpret_cast<const float4*>(rp + raw_off[it]);
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + bias;
+          if (e.out_acc) {
+            if (e.acc_bf16) {
+              __nv_bfloat16* ap = reinterpret_cast<__nv_bfloat16*>(e.out_acc) + raw0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) ap[j * kCout] = __float2bfloat16_rn(v[j]);
+            } else {
+              float* ap = reinterpret_cast<float*>(e.out_acc) + raw0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) ap[j * kCout] = v[j];
+            }
+          }
+          if (e.residual) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += res[j];
+          }
+          if (e.out_raw) {
+            float* op = e.out_raw + raw0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) op[j * kCout] = v[j];
+          }
+          if (e.stats) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { ssum += v[j]; ssq = fmaf(v[j], v[j], ssq); }
+          }
+          if (e.out_op) {
+            if (e.op_elu) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = elu_sel<T>(v[j], red);
+            }
+            T* const ob = reinterpret_cast<T*>(e.out_op) + (((size_t)n * Hp + h + P) * Wp + w + P) * kCout + ch;
+            // pixels [jlo, jhi) of the chunk to `ob + delta`: the chunk itself, then its circular-halo duplicates
+            auto emit = [&](ptrdiff_t delta, int jlo, int jhi) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j >= jlo && j < jhi) store_op1<T>(ob + delta + j * kCout, v[j], red, e.op_lo_off);
+            };
+            emit(0, 0, 32);
+            const ptrdiff_t dh = (h < P) ? (ptrdiff_t)g.H * Wp * kCout : ((h >= g.H - P) ? -(ptrdiff_t)g.H * Wp * kCout : 0);
+            if (dh) emit(dh, 0, 32);
+            if (w < P) {                                     // leftmost pixels also live in the right halo
+              emit((ptrdiff_t)g.W * kCout, 0, P - w);
+              if (dh) emit(dh + (ptrdiff_t)g.W * kCout, 0, P - w);
+            }
+            if (w + 32 > g.W - P) {                          // rightmost pixels also live in the left halo
+              emit(-(ptrdiff_t)g.W * kCout, g.W - P - w, 32);
+              if (dh) emit(dh - (ptrdiff_t)g.W * kCout, g.W - P - w, 32);
+            }
+          }
         }
-        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (e.bias) bias4 = *reinterpret_cast<const float4*>(e.bias + ch);
-        uint32_t r[32];
-        tmem_ld_32x32(t_addr + c0, r);
-        tmem_ld_wait();
-        if (c0 + 64 >= N_TILE) {                             // this warp's last chunk: its part of the accumulator is read
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(acc_empty + ab);
+        if (e.stats)                                         // slot [tile][half][Cout][2], written exactly once
+          *reinterpret_cast<float2*>(e.stats + (((size_t)tile * 2 + half) * kCout + ch) * 2) = make_float2(ssum, ssq);
+      } else {
+        // element offsets of the lane's 8 pixels (the same for every channel chunk) into the raw tensors / the
+        // padded operand tensor, plus the deltas to the circular-halo duplicates a pixel owns (0 = none)
+        uint32_t raw_off[8], op_off[8];
+        int32_t dup_w[8], dup_h[8];
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int m = quad * 32 + it * 4 + psub;
+          const int h = h0 + (m >> g.bw_shift), w = w0 + (m & (g.BW - 1));
+          raw_off[it] = (uint32_t)((((size_t)n * g.H + h) * g.W + w) * kCout);
+          op_off[it] = (uint32_t)((((size_t)n * Hp + h + P) * Wp + w + P) * kCout);
+          dup_w[it] = (w < P) ? g.W * kCout : ((w >= g.W - P) ? -g.W * kCout : 0);
+          dup_h[it] = (h < P) ? g.H * Wp * kCout : ((h >= g.H - P) ? -g.H * Wp * kCout : 0);
         }
-        float4* stg4 = reinterpret_cast<float4*>(stg);
-        if constexpr (!SWAP) {
+        // fused InstanceNorm++ statistics of the value written to out_raw: per lane 4 channels, summed over the
+        // lane's pixels, then over the 4 lanes sharing a channel quad; the warp's partial goes to its own slot
+        // [tile][quad][Cout][2] (no atomics, every slot written exactly once; stats_reduce_parts sums the slots).
+        float ssum[4] = {0.f, 0.f, 0.f, 0.f}, ssq[4] = {0.f, 0.f, 0.f, 0.f};
+        mbar_wait(acc_full + ab, acc_phase);
+        __syncwarp();
+        tc_fence_after();
+#pragma unroll 1
+        for (int c0 = half * 32; c0 < N_TILE; c0 += 64) {
+          const int ch = c0 + cq * 4;
+          // issue the residual loads first: their latency overlaps the TMEM read and the staging round trip
+          float4 res[8];
+          if (e.residual) {
+            const float* rp = e.residual + ch;
+#pragma unroll
+            for (int it = 0; it < 8; ++it) res[it] = *reinterpret_cast<const float4*>(rp + raw_off[it]);
+          }
+          float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (e.bias) bias4 = *reinterpret_cast<const float4*>(e.bias + ch);
+          uint32_t r[32];
+          tmem_ld_32x32(t_addr + c0, r);
+          tmem_ld_wait();
+          if (c0 + 64 >= N_TILE) {                           // this warp's last chunk: its part of the accumulator is read
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty + ab);
+          }
+          float4* stg4 = reinterpret_cast<float4*>(stg);
           // thread = pixel (row = lane), registers = 32 channels
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             stg4[stg_slot(lane, j)] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
                                                   __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
-        } else {
-          // thread = output channel (column = lane), registers = 32 pixels: write the transpose
+          __syncwarp();
+          float* const acc_p = (e.out_acc && !e.acc_bf16) ? reinterpret_cast<float*>(e.out_acc) + ch : nullptr;
+          __nv_bfloat16* const acc_h = (e.out_acc && e.acc_bf16) ? reinterpret_cast<__nv_bfloat16*>(e.out_acc) + ch : nullptr;
+          float* const raw_p = e.out_raw ? e.out_raw + ch : nullptr;
+          T* const op_p = e.out_op ? reinterpret_cast<T*>(e.out_op) + ch : nullptr;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) stg[stg_slot(j, lane >> 2) * 4 + (lane & 3)] = __uint_as_float(r[j]);
-        }
-        __syncwarp();
-        float* const acc_p = e.out_acc ? e.out_acc + ch : nullptr;
-        float* const raw_p = e.out_raw ? e.out_raw + ch : nullptr;
-        T* const op_p = e.out_op ? reinterpret_cast<T*>(e.out_op) + ch : nullptr;
-        const bool red = e.op_tf32 != 0;
+          for (int it = 0; it < 8; ++it) {
+            float4 v = stg4[stg_slot(it * 4 + psub, cq)];
+            v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
+            if (acc_p) *reinterpret_cast<float4*>(acc_p + raw_off[it]) = v;
+            if (acc_h) {
+              const float a4[4] = {v.x, v.y, v.z, v.w};
+              store_op4<__nv_bfloat16>(acc_h + raw_off[it], a4, false, 0);
+            }
+            if (e.residual) { v.x += res[it].x; v.y += res[it].y; v.z += res[it].z; v.w += res[it].w; }
+            if (raw_p) *reinterpret_cast<float4*>(raw_p + raw_off[it]) = v;
+            if (e.stats) {
+              ssum[0] += v.x; ssum[1] += v.y; ssum[2] += v.z; ssum[3] += v.w;
+              ssq[0] = fmaf(v.x, v.x, ssq[0]); ssq[1] = fmaf(v.y, v.y, ssq[1]);
+              ssq[2] = fmaf(v.z, v.z, ssq[2]); ssq[3] = fmaf(v.w, v.w, ssq[3]);
+            }
+            if (op_p) {
+              float o[4] = {v.x, v.y, v.z, v.w};
+              if (e.op_elu) {
+                o[0] = elu_sel<T>(o[0], red); o[1] = elu_sel<T>(o[1], red); o[2] = elu_sel<T>(o[2], red); o[3] = elu_sel<T>(o[3], red);
+              }
+              T* d = op_p + op_off[it];
+              store_op4<T>(d, o, red, e.op_lo_off);
+              if (dup_w[it]) store_op4<T>(d + dup_w[it], o, red, e.op_lo_off);
+              if (dup_h[it]) {
+                store_op4<T>(d + dup_h[it], o, red, e.op_lo_off);
+                if (dup_w[it]) store_op4<T>(d + dup_h[it] + dup_w[it], o, red, e.op_lo_off);
+              }
+            }
+          }
+          if (e.stats) {                                     // every chunk covers different channels
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          float4 v = stg4[stg_slot(it * 4 + psub, cq)];
-          v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
-          if (acc_p) *reinterpret_cast<float4*>(acc_p + raw_off[it]) = v;
-          if (e.residual) { v.x += res[it].x; v.y += res[it].y; v.z += res[it].z; v.w += res[it].w; }
-          if (raw_p) *reinterpret_cast<float4*>(raw_p + raw_off[it]) = v;
-          if (e.stats) {
-            ssum[0] += v.x; ssum[1] += v.y; ssum[2] += v.z; ssum[3] += v.w;
-            ssq[0] = fmaf(v.x, v.x, ssq[0]); ssq[1] = fmaf(v.y, v.y, ssq[1]);
-            ssq[2] = fmaf(v.z, v.z, ssq[2]); ssq[3] = fmaf(v.w, v.w, ssq[3]);
-          }
-          if (op_p) {
-            float o[4] = {v.x, v.y, v.z, v.w};
-            if (e.op_elu) {
-              o[0] = elu_sel<T>(o[0], red); o[1] = elu_sel<T>(o[1], red); o[2] = elu_sel<T>(o[2], red); o[3] = elu_sel<T>(o[3], red);
+            for (int k = 0; k < 4; ++k) {
+              ssum[k] += __shfl_xor_sync(0xffffffffu, ssum[k], 8);
+              ssq[k] += __shfl_xor_sync(0xffffffffu, ssq[k], 8);
+              ssum[k] += __shfl_xor_sync(0xffffffffu, ssum[k], 16);
+              ssq[k] += __shfl_xor_sync(0xffffffffu, ssq[k], 16);
             }
-            T* d = op_p + op_off[it];
-            store_op4<T>(d, o, red, e.op_lo_off);
-            if (dup_w[it]) store_op4<T>(d + dup_w[it], o, red, e.op_lo_off);
-            if (dup_h[it]) {
-              store_op4<T>(d + dup_h[it], o, red, e.op_lo_off);
-              if (dup_w[it]) store_op4<T>(d + dup_h[it] + dup_w[it], o, red, e.op_lo_off);
+            if (psub == 0) {
+              float* sp = e.stats + (((size_t)tile * 4 + quad) * kCout + ch) * 2;
+              *reinterpret_cast<float4*>(sp) = make_float4(ssum[0], ssq[0], ssum[1], ssq[1]);
+              *reinterpret_cast<float4*>(sp + 4) = make_float4(ssum[2], ssq[2], ssum[3], ssq[3]);
             }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) ssum[k] = ssq[k] = 0.f;
           }
+          __syncwarp();                                      // staging tile is reused by the next chunk
         }
-        if constexpr (!SWAP) { if (e.stats) flush_stats(ch); }     // every chunk covers different channels
-        __syncwarp();                                        // staging tile is reused by the next chunk
       }
-      if constexpr (SWAP) { if (e.stats) flush_stats(quad * 32 + cq * 4); }   // chunks were pixels of the same channels
     }
   }
 

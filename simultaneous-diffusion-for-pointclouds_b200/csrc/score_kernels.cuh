@@ -2,6 +2,7 @@
 // (begin/end convolutions, InstanceNorm++ statistics, operand materialisation with halo,
 // max / mean pooling, bilinear x2, layout conversion, fp32 SIMT convolution for the strict arm.)
 #pragma once
+#include <type_traits>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -23,9 +24,11 @@ __device__ __forceinline__ float linspace01(int i, int steps) {
 template <int NGF>
 __global__ void __launch_bounds__(NGF)
 begin_conv_kernel(const float* __restrict__ x, const float* __restrict__ wgt, const float* __restrict__ bias,
-                  float* __restrict__ out, int N, int H, int W) {
+                  float* __restrict__ out, float2* __restrict__ stat_parts, int N, int H, int W) {
   // one thread per output channel (its 36 weights live in registers), 64 pixels of one row per block;
   // the 36-value input patches are staged k-major in shared memory and read as broadcast float4s.
+  // stat_parts (or null): [N][H * W/64][NGF] (sum, sum of squares) of the block's 64 outputs per channel, the
+  // partial InstanceNorm++ statistics of the first normalisation (same slot layout as the conv epilogues).
   constexpr int K = 36;
   __shared__ __align__(16) float sin_[K][64];
   const int tiles_w = W / 64;
@@ -52,6 +55,7 @@ begin_conv_kernel(const float* __restrict__ x, const float* __restrict__ wgt, co
   }
   __syncthreads();
   float* orow = out + (((size_t)n * H + h) * W + w0) * NGF + c;
+  float ssum = 0.0f, ssq = 0.0f;
 #pragma unroll 1
   for (int p0 = 0; p0 < 64; p0 += 8) {
     float acc[8];
@@ -67,8 +71,14 @@ begin_conv_kernel(const float* __restrict__ x, const float* __restrict__ wgt, co
       acc[6] = fmaf(b.z, wr[k], acc[6]); acc[7] = fmaf(b.w, wr[k], acc[7]);
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) orow[(size_t)(p0 + i) * NGF] = acc[i] + bc;
+    for (int i = 0; i < 8; ++i) {
+      const float v = acc[i] + bc;
+      orow[(size_t)(p0 + i) * NGF] = v;
+      ssum += v;
+      ssq = fmaf(v, v, ssq);
+    }
   }
+  if (stat_parts) stat_parts[(size_t)blk * NGF + c] = make_float2(ssum, ssq);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -99,18 +109,60 @@ stats_kernel(const float* __restrict__ in, double* __restrict__ stats, int HW, i
   }
 }
 
-// Sum the per-tile partial statistics written by the convolution epilogues
-// (parts: [N][parts_per_view][C][2] floats) into stats [N][C][2] doubles.
-// grid (C/32, N), block 256 = 8 part-groups x 32 channels.
+// coef[n][c] = {mean, a, b}: out = a*(x-mean) + b with a = gamma*rstd, b = gamma*alpha*mean_n + beta
+// (InstanceNorm2dPlus, normalization.py:163-176).  Called by the first C threads of a block (C <= 256); `S`, `Q` are
+// the channel's sum and sum of squares over the image.
+__device__ __forceinline__ void norm_coefficients(double S, double Q, const float* __restrict__ alpha,
+                                                  const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                  float* __restrict__ coef, int HW, int C, int n, int c, bool active) {
+  __shared__ double sm[256];
+  __shared__ double s_m, s_v;
+  const double mean = S / HW;
+  double var = Q / HW - mean * mean;
+  if (var < 0.0) var = 0.0;
+  if (active) sm[c] = mean;
+  __syncthreads();
+  if (c == 0) { double t = 0; for (int i = 0; i < C; ++i) t += sm[i]; s_m = t / C; }
+  __syncthreads();
+  const double dm = mean - s_m;
+  if (active) sm[c] = dm * dm;
+  __syncthreads();
+  if (c == 0) { double t = 0; for (int i = 0; i < C; ++i) t += sm[i]; s_v = t / (C - 1); }
+  __syncthreads();
+  if (!active) return;
+  const float rstd = 1.0f / sqrtf((float)var + 1e-5f);
+  const float mean_n = (float)dm / sqrtf((float)s_v + 1e-5f);
+  float* o = coef + ((size_t)n * C + c) * 3;
+  o[0] = (float)mean;
+  o[1] = gamma[c] * rstd;
+  o[2] = gamma[c] * (mean_n * alpha[c]) + beta[c];
+}
+
+__global__ void norm_finalize_kernel(const double* __restrict__ stats, const float* __restrict__ alpha,
+                                     const float* __restrict__ gamma, const float* __restrict__ beta,
+                                     float* __restrict__ coef, int HW, int C) {
+  const int n = blockIdx.x, c = threadIdx.x;
+  norm_coefficients(stats[((size_t)n * C + c) * 2], stats[((size_t)n * C + c) * 2 + 1], alpha, gamma, beta, coef, HW, C, n, c,
+                    true);
+}
+
+// Fused reducer + finalizer for the statistics the convolution epilogues leave as per-tile partial sums
+// (parts: [N][parts_per_view][C][2] floats): grid (C/8, N), block 256 = 32 part-groups x 8 channels.  Every block
+// sums its 8 channels into stats [N][C][2] (doubles); the block that finishes an image last (per-image ticket
+// counter, reset for the next use) turns the image's C sums into the normalisation coefficients.
 __global__ void __launch_bounds__(256)
-stats_reduce_parts_kernel(const float* __restrict__ parts, double* __restrict__ stats, int parts_per_view, int C) {
-  __shared__ double red[8][32][2];
-  const int cl = threadIdx.x & 31, grp = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + cl, n = blockIdx.y;
+stats_reduce_finalize_kernel(const float* __restrict__ parts, double* __restrict__ stats, int parts_per_view, int C,
+                             const float* __restrict__ alpha, const float* __restrict__ gamma,
+                             const float* __restrict__ beta, float* __restrict__ coef, int HW,
+                             unsigned int* __restrict__ tickets) {
+  __shared__ double red[32][8][2];
+  __shared__ bool s_last;
+  const int cl = threadIdx.x & 7, grp = threadIdx.x >> 3;
+  const int c = blockIdx.x * 8 + cl, n = blockIdx.y;
   const float2* p = reinterpret_cast<const float2*>(parts) + (size_t)n * parts_per_view * C + c;
   double S = 0.0, Q = 0.0;
 #pragma unroll 8
-  for (int j = grp; j < parts_per_view; j += 8) {
+  for (int j = grp; j < parts_per_view; j += 32) {
     const float2 v = p[(size_t)j * C];
     S += (double)v.x;
     Q += (double)v.y;
@@ -120,38 +172,25 @@ stats_reduce_parts_kernel(const float* __restrict__ parts, double* __restrict__ 
   __syncthreads();
   if (grp == 0) {
 #pragma unroll
-    for (int k = 1; k < 8; ++k) { S += red[k][cl][0]; Q += red[k][cl][1]; }
+    for (int k = 1; k < 32; ++k) { S += red[k][cl][0]; Q += red[k][cl][1]; }
     stats[((size_t)n * C + c) * 2] = S;
     stats[((size_t)n * C + c) * 2 + 1] = Q;
+    __threadfence();
   }
-}
-
-// coef[n][c] = {mean, a, b}: out = a*(x-mean) + b with a = gamma*rstd, b = gamma*alpha*mean_n + beta
-__global__ void norm_finalize_kernel(const double* __restrict__ stats, const float* __restrict__ alpha,
-                                     const float* __restrict__ gamma, const float* __restrict__ beta,
-                                     float* __restrict__ coef, int HW, int C) {
-  __shared__ double sm[256];
-  __shared__ double s_m, s_v;
-  const int n = blockIdx.x, c = threadIdx.x;
-  const double S = stats[((size_t)n * C + c) * 2], Q = stats[((size_t)n * C + c) * 2 + 1];
-  const double mean = S / HW;
-  double var = Q / HW - mean * mean;
-  if (var < 0.0) var = 0.0;
-  sm[c] = mean;
   __syncthreads();
-  if (c == 0) { double t = 0; for (int i = 0; i < C; ++i) t += sm[i]; s_m = t / C; }
+  if (threadIdx.x == 0) s_last = atomicAdd(tickets + n, 1u) == gridDim.x - 1;
   __syncthreads();
-  const double dm = mean - s_m;
-  sm[c] = dm * dm;
-  __syncthreads();
-  if (c == 0) { double t = 0; for (int i = 0; i < C; ++i) t += sm[i]; s_v = t / (C - 1); }
-  __syncthreads();
-  const float rstd = 1.0f / sqrtf((float)var + 1e-5f);
-  const float mean_n = (float)dm / sqrtf((float)s_v + 1e-5f);
-  float* o = coef + ((size_t)n * C + c) * 3;
-  o[0] = (float)mean;
-  o[1] = gamma[c] * rstd;
-  o[2] = gamma[c] * (mean_n * alpha[c]) + beta[c];
+  if (!s_last) return;
+  __threadfence();
+  const int t = threadIdx.x;
+  const bool active = t < C;
+  double fS = 0.0, fQ = 0.0;
+  if (active) {
+    fS = __ldcg(stats + ((size_t)n * C + t) * 2);
+    fQ = __ldcg(stats + ((size_t)n * C + t) * 2 + 1);
+  }
+  norm_coefficients(fS, fQ, alpha, gamma, beta, coef, HW, C, n, t, active);
+  if (t == 0) tickets[n] = 0;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -348,6 +387,101 @@ maxpool5_kernel(const float* __restrict__ in, float* __restrict__ x0_out, T* __r
   }
 }
 
+// bf16 arm of the CRP max-pool: rounding to bf16 is monotone, so bf16(max(x)) == max(bf16(x)) and the whole 5x5 max
+// runs on packed bf16 pairs (half the instructions and half the shared-memory bytes of the fp32 kernel above).
+// A thread owns 8 channels (one 16-byte word); the block tile is 8 rows x 32 columns x 64 channels.  The input is
+// either the fp32 trunk tensor (first stage: ELU applied at load, x0 = ELU(in) emitted in fp32 for the residual
+// adds) or the bf16 copy the previous CRP convolution left in its out_acc (second stage).
+constexpr int kPoolHCB = 64;
+constexpr int kPoolHThreads = (kPoolTW + 4) * (kPoolHCB / 8);   // 288
+
+__device__ __forceinline__ uint4 hmax8(const uint4& a, const uint4& b) {
+  uint4 r;
+  const __nv_bfloat162 x = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a.x), *reinterpret_cast<const __nv_bfloat162*>(&b.x));
+  const __nv_bfloat162 y = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a.y), *reinterpret_cast<const __nv_bfloat162*>(&b.y));
+  const __nv_bfloat162 z = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a.z), *reinterpret_cast<const __nv_bfloat162*>(&b.z));
+  const __nv_bfloat162 w = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a.w), *reinterpret_cast<const __nv_bfloat162*>(&b.w));
+  r.x = *reinterpret_cast<const uint32_t*>(&x); r.y = *reinterpret_cast<const uint32_t*>(&y);
+  r.z = *reinterpret_cast<const uint32_t*>(&z); r.w = *reinterpret_cast<const uint32_t*>(&w);
+  return r;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  const __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&t);
+}
+
+template <typename TIn>
+__global__ void __launch_bounds__(kPoolHThreads)
+maxpool5_h2_kernel(const TIn* __restrict__ in, float* __restrict__ x0_out, __nv_bfloat16* __restrict__ out, int N, int H,
+                   int W, int C, int P, int elu_in) {
+  __shared__ uint4 tv[kPoolTH][kPoolTW + 4][kPoolHCB / 8];       // 36 KB
+  const int CBn = C / kPoolHCB, TWn = W / kPoolTW, THn = H / kPoolTH;
+  int b = blockIdx.x;
+  const int cb = b % CBn; b /= CBn;
+  const int tw = b % TWn; b /= TWn;
+  const int th = b % THn;
+  const int n = b / THn;
+  const int h0 = th * kPoolTH, w0 = tw * kPoolTW, c0 = cb * kPoolHCB;
+  const uint4 ninf = make_uint4(0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u);      // bf16 -inf pairs
+  {
+    const int c8 = threadIdx.x & 7, cc = threadIdx.x >> 3;        // cc in [0, 36): input column
+    const int ww = w0 - 2 + cc;
+    const bool col_ok = ww >= 0 && ww < W;
+    const bool interior_col = cc >= 2 && cc < kPoolTW + 2;
+    uint4 v[kPoolTH + 4];
+#pragma unroll
+    for (int r = 0; r < kPoolTH + 4; ++r) {
+      const int hh = h0 - 2 + r;
+      v[r] = ninf;
+      if (col_ok && hh >= 0 && hh < H) {
+        const size_t off = (((size_t)n * H + hh) * W + ww) * C + c0 + c8 * 8;
+        if constexpr (sizeof(TIn) == 2) {
+          v[r] = *reinterpret_cast<const uint4*>(in + off);
+        } else {
+          float4 a = *reinterpret_cast<const float4*>(in + off), c = *reinterpret_cast<const float4*>(in + off + 4);
+          if (elu_in || x0_out) {
+            const float4 ea = make_float4(elu_fast(a.x), elu_fast(a.y), elu_fast(a.z), elu_fast(a.w));
+            const float4 ec = make_float4(elu_fast(c.x), elu_fast(c.y), elu_fast(c.z), elu_fast(c.w));
+            if (x0_out && interior_col && r >= 2 && r < kPoolTH + 2) {
+              *reinterpret_cast<float4*>(x0_out + off) = ea;
+              *reinterpret_cast<float4*>(x0_out + off + 4) = ec;
+            }
+            if (elu_in) { a = ea; c = ec; }
+          }
+          v[r] = make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(c.x, c.y), pack_bf16x2(c.z, c.w));
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < kPoolTH; ++r) {
+      uint4 m = v[r];
+#pragma unroll
+      for (int k = 1; k < 5; ++k) m = hmax8(m, v[r + k]);
+      tv[r][cc][c8] = m;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 256) {
+    const int c8 = threadIdx.x & 7, seg = (threadIdx.x >> 3) & 3, r = threadIdx.x >> 5;   // 8 outputs: columns seg*8 ..
+    const int Hp = H + 2 * P, Wp = W + 2 * P;
+    const int h = h0 + r;
+    uint4 cfl[12];
+#pragma unroll
+    for (int j = 0; j < 12; ++j) cfl[j] = tv[r][seg * 8 + j][c8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      uint4 m = cfl[j];
+#pragma unroll
+      for (int k = 1; k < 5; ++k) m = hmax8(m, cfl[j + k]);
+      const int w = w0 + seg * 8 + j;
+      const HaloPos d = halo_pos(h, w, H, W, P);
+      for_each_halo_pos(d, [&](int hp, int wp) {
+        *reinterpret_cast<uint4*>(out + (((size_t)n * Hp + hp) * Wp + wp) * C + c0 + c8 * 8) = m;
+      });
+    }
+  }
+}
+
 // mean of the four stride-2 phases (layers.py:310-312), in the reference's summation order.
 __device__ __forceinline__ float4 pool4(const float* in, size_t i00, size_t i10, size_t i01, size_t i11) {
   const float4 a = *reinterpret_cast<const float4*>(in + i00), b = *reinterpret_cast<const float4*>(in + i10);
@@ -380,6 +514,46 @@ meanpool_kernel(const float* __restrict__ in, const float* __restrict__ add, T* 
   if (out_op) {
     float vv[4] = {v.x, v.y, v.z, v.w};
     store_op4<T>(out_op + i * 4, vv, tf32 != 0, lo_off);
+  }
+}
+
+// out_raw = meanpool2(in) + add, plus partial InstanceNorm++ statistics of out_raw: a block covers kMpIter * 256 / (C/4)
+// consecutive output pixels of one image and leaves (sum, sum of squares) per channel in its slot
+// stat_parts[block][C] (the [N][parts_per_view][C][2] layout of the convolution epilogues).  Needs 256 % (C/4) == 0.
+constexpr int kMpIter = 16;
+__global__ void __launch_bounds__(256)
+meanpool_add_stats_kernel(const float* __restrict__ in, const float* __restrict__ add, float* __restrict__ out_raw,
+                          float2* __restrict__ stat_parts, int N, int H, int W, int C) {
+  __shared__ float4 ssum[256], ssq[256];
+  const int Ho = H / 2, Wo = W / 2, C4 = C / 4;
+  const int c4 = threadIdx.x % C4;
+  float4 S = make_float4(0.f, 0.f, 0.f, 0.f), Q = S;
+#pragma unroll 4
+  for (int it = 0; it < kMpIter; ++it) {
+    const size_t i = ((size_t)blockIdx.x * kMpIter + it) * 256 + threadIdx.x;
+    size_t t = i / C4;
+    const int wo = (int)(t % Wo); t /= Wo;
+    const int ho = (int)(t % Ho);
+    const int n = (int)(t / Ho);
+    const size_t base = (((size_t)n * H + 2 * ho) * W + 2 * wo) * C + c4 * 4;
+    float4 v = pool4(in, base, base + (size_t)W * C, base + C, base + (size_t)W * C + C);
+    const float4 a = *reinterpret_cast<const float4*>(add + i * 4);
+    v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+    *reinterpret_cast<float4*>(out_raw + i * 4) = v;
+    S.x += v.x; S.y += v.y; S.z += v.z; S.w += v.w;
+    Q.x = fmaf(v.x, v.x, Q.x); Q.y = fmaf(v.y, v.y, Q.y); Q.z = fmaf(v.z, v.z, Q.z); Q.w = fmaf(v.w, v.w, Q.w);
+  }
+  ssum[threadIdx.x] = S;
+  ssq[threadIdx.x] = Q;
+  __syncthreads();
+  if (threadIdx.x < C4) {
+    for (int k = threadIdx.x + C4; k < 256; k += C4) {
+      const float4 s2 = ssum[k], q2 = ssq[k];
+      S.x += s2.x; S.y += s2.y; S.z += s2.z; S.w += s2.w;
+      Q.x += q2.x; Q.y += q2.y; Q.z += q2.z; Q.w += q2.w;
+    }
+    float2* sp = stat_parts + (size_t)blockIdx.x * C + c4 * 4;
+    sp[0] = make_float2(S.x, Q.x); sp[1] = make_float2(S.y, Q.y); sp[2] = make_float2(S.z, Q.z); sp[3] = make_float2(S.w, Q.w);
   }
 }
 
@@ -474,6 +648,115 @@ end_conv_kernel(const float* __restrict__ op, const float* __restrict__ wgt, con
     for (int i = 1; i < 8; ++i) if (lane == i) { v0 = a0[i]; v1 = a1[i]; }
     out[(((size_t)n * 2 + 0) * H + h) * W + w0 + lane] = (v0 + bias[0]) / s;
     out[(((size_t)n * 2 + 1) * H + h) * W + w0 + lane] = (v1 + bias[1]) / s;
+  }
+}
+
+// Fused tail of the network: normalizer (InstanceNorm++) -> ELU -> end_conv -> / sigmas[y] (ncsnv2.py:509-516)
+// reading the raw fp32 trunk once, instead of materialising the activated tensor (a 268 MB write and a 3x re-read).
+// One warp owns an 8-pixel-wide, kEndRows-tall strip and walks DOWN its input rows: every input row (10 columns
+// x 4 channels per lane) is loaded, normalised and activated once, and feeds the three output rows it touches
+// (tap rows 0,1,2 in the same order as end_conv_kernel, so the sums are formed identically).  Out-of-image inputs
+// are the zero padding of the activated tensor.
+constexpr int kEndRows = 16;
+template <int NGF>
+__global__ void __launch_bounds__(256)
+end_conv_norm_kernel(const float* __restrict__ raw, const float* __restrict__ coef, const float* __restrict__ wgt,
+                     const float* __restrict__ bias, const float* __restrict__ sigmas,
+                     const int64_t* __restrict__ labels, float* __restrict__ out, int N, int H, int W, int fast_elu) {
+  static_assert(NGF == 128, "one float4 per lane");
+  __shared__ __align__(16) float sw[2][9][NGF];
+  for (int i = threadIdx.x; i < 2 * 9 * NGF; i += blockDim.x) {
+    const int co = i / (9 * NGF), r = i % (9 * NGF), tap = r / NGF, ci = r % NGF;
+    sw[co][tap][ci] = wgt[((size_t)co * NGF + ci) * 9 + tap];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const size_t strip = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int W8 = W / 8, HB = H / kEndRows;
+  if (strip >= (size_t)N * HB * W8) return;
+  const int w0 = (int)(strip % W8) * 8, hb0 = (int)((strip / W8) % HB) * kEndRows, n = (int)(strip / ((size_t)W8 * HB));
+  // this lane's 4 channels: {mean, a, b} triples are 12 contiguous floats
+  float mu[4], ga[4], be[4];
+  {
+    const float4* cf4 = reinterpret_cast<const float4*>(coef + ((size_t)n * NGF + lane * 4) * 3);
+    const float4 t0 = cf4[0], t1 = cf4[1], t2 = cf4[2];
+    mu[0] = t0.x; ga[0] = t0.y; be[0] = t0.z; mu[1] = t0.w; ga[1] = t1.x; be[1] = t1.y;
+    mu[2] = t1.z; ga[2] = t1.w; be[2] = t2.x; mu[3] = t2.y; ga[3] = t2.z; be[3] = t2.w;
+  }
+  const float sg = sigmas[labels[n]];
+  const float b0 = bias[0], b1 = bias[1];
+  float acc[3][2][8];                                   // [output row slot][co][pixel]; slot of output row ho = (ho - hb0 + 3) % 3
+#pragma unroll
+  for (int s = 0; s < 3; ++s)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[s][0][i] = acc[s][1][i] = 0.0f;
+
+  auto act = [&](float v, int k) {
+    const float t = ga[k] * (v - mu[k]) + be[k];
+    return fast_elu ? elu_fast(t) : elu1(t);
+  };
+  // input row hi = hb0 - 1 + step feeds output rows hi+1 (tap row 0), hi (tap row 1), hi-1 (tap row 2, completing it)
+  auto step = [&](int st, auto slot_c) {
+    constexpr int S = decltype(slot_c)::value;           // st % 3
+    const int hi = hb0 - 1 + st;
+    float4 col[10];
+    if (hi >= 0 && hi < H) {
+      const float* row = raw + (((size_t)n * H + hi) * W + w0 - 1) * NGF + lane * 4;
+#pragma unroll
+      for (int j = 0; j < 10; ++j) {
+        const int ww = w0 - 1 + j;
+        col[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ww >= 0 && ww < W) {
+          const float4 v = *reinterpret_cast<const float4*>(row + (size_t)j * NGF);
+          col[j] = make_float4(act(v.x, 0), act(v.y, 1), act(v.z, 2), act(v.w, 3));
+        }
+      }
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+        // output row hi + 1 - kh lives in slot (st + 1 - kh) % 3 = (S + 4 - kh) % 3
+        const int sl = (S + 4 - kh) % 3;
+        const int ho_k = hi + 1 - kh;
+        if (ho_k < hb0 || ho_k >= hb0 + kEndRows) continue;       // that row belongs to the strip above / below
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const float4 w0v = *reinterpret_cast<const float4*>(&sw[0][kh * 3 + kw][lane * 4]);
+          const float4 w1v = *reinterpret_cast<const float4*>(&sw[1][kh * 3 + kw][lane * 4]);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 v = col[i + kw];
+            acc[sl][0][i] += v.x * w0v.x + v.y * w0v.y + v.z * w0v.z + v.w * w0v.w;
+            acc[sl][1][i] += v.x * w1v.x + v.y * w1v.y + v.z * w1v.z + v.w * w1v.w;
+          }
+        }
+      }
+    }
+    // output row ho = hi - 1 (slot (S + 2) % 3) is complete
+    const int ho = hi - 1;
+    constexpr int so = (S + 2) % 3;
+    if (ho >= hb0 && ho < hb0 + kEndRows) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        for (int o = 16; o > 0; o >>= 1) {
+          acc[so][0][i] += __shfl_xor_sync(0xffffffffu, acc[so][0][i], o);
+          acc[so][1][i] += __shfl_xor_sync(0xffffffffu, acc[so][1][i], o);
+        }
+      if (lane < 8) {
+        float v0 = acc[so][0][0], v1 = acc[so][1][0];
+#pragma unroll
+        for (int i = 1; i < 8; ++i) if (lane == i) { v0 = acc[so][0][i]; v1 = acc[so][1][i]; }
+        out[(((size_t)n * 2 + 0) * H + ho) * W + w0 + lane] = (v0 + b0) / sg;
+        out[(((size_t)n * 2 + 1) * H + ho) * W + w0 + lane] = (v1 + b1) / sg;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[so][0][i] = acc[so][1][i] = 0.0f;   // the slot restarts as output row hi + 2
+  };
+  static_assert((kEndRows + 2) % 3 == 0, "the row walk is unrolled by the three accumulator slots");
+#pragma unroll 1
+  for (int st = 0; st < kEndRows + 2; st += 3) {
+    step(st, std::integral_constant<int, 0>());
+    step(st + 1, std::integral_constant<int, 1>());
+    step(st + 2, std::integral_constant<int, 2>());
   }
 }
 

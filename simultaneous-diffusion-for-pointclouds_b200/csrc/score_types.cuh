@@ -26,7 +26,8 @@ struct EpiParams {
   const float* bias;      // [Cout] or null
   const float* residual;  // fp32 raw [N,H,W,Cout] added after bias, or null
   float* out_raw;         // fp32 raw, value after bias + residual, or null
-  float* out_acc;         // fp32 raw, value after bias only (CRP path), or null
+  void* out_acc;          // raw layout (no halo), value after bias only (CRP path: only a max-pool reads it), or null;
+  int acc_bf16;           // 1: out_acc holds bf16 (max-pooling commutes with the monotone rounding), else fp32
   void* out_op;           // operand (T) with halo `op_pad`, value = act(after bias+residual), or null
   int op_pad;
   int op_elu;             // 1: ELU before the operand store
@@ -38,11 +39,16 @@ struct EpiParams {
 };
 
 __device__ __forceinline__ float elu1(float v) { return v > 0.0f ? v : expm1f(v); }
-// ex2.approx based ELU for the reduced-precision arms (abs error ~1e-7, far below bf16/tf32 rounding);
-// the fp32 arm keeps expm1f.
+// ex2.approx based ELU for the reduced-precision arms (abs error ~1e-7, far below bf16/tf32 rounding): one multiply,
+// one MUFU, one add and a select (__expf would add denormal-range scaling around the MUFU).  The fp32 arm keeps expm1f.
+__device__ __forceinline__ float elu_fast(float v) {
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v * 1.4426950408889634f));
+  return v > 0.0f ? v : e - 1.0f;
+}
 template <typename T>
 __device__ __forceinline__ float elu_sel(float v, bool reduced) {
-  if (sizeof(T) == 2 || reduced) return v > 0.0f ? v : __expf(v) - 1.0f;
+  if (sizeof(T) == 2 || reduced) return elu_fast(v);
   return elu1(v);
 }
 
@@ -81,6 +87,18 @@ __device__ __forceinline__ void store_op4<__nv_bfloat16>(__nv_bfloat16* dst, con
   }
 }
 
+// one element of an operand tensor (the swapped-operand epilogue stores a channel per lane)
+template <typename T>
+__device__ __forceinline__ void store_op1(T* dst, float v, bool tf32, size_t lo_off);
+template <>
+__device__ __forceinline__ void store_op1<float>(float* dst, float v, bool tf32, size_t) { *dst = tf32 ? round_tf32(v) : v; }
+template <>
+__device__ __forceinline__ void store_op1<__nv_bfloat16>(__nv_bfloat16* dst, float v, bool, size_t lo_off) {
+  const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+  *dst = hi;
+  if (lo_off) dst[lo_off] = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+
 // Positions a pixel (h,w) of an HxW image occupies in a tensor padded by P with circular wrap: its
 // interior position (h+P, w+P) plus at most one duplicate row and one duplicate column on the opposite
 // border (H, W >= 2P, so a pixel is never near both borders of an axis).  hb / wb are -1 when absent.
@@ -117,7 +135,7 @@ __device__ __forceinline__ void epi_store(const EpiParams& e, const ConvGeom& g,
     }
   }
   if (e.out_acc) {
-    float* d = e.out_acc + pix * g.Cout + c0;
+    float* d = reinterpret_cast<float*>(e.out_acc) + pix * g.Cout + c0;       // SIMT path: always fp32
 #pragma unroll
     for (int i = 0; i < NV; i += 4) *reinterpret_cast<float4*>(d + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
   }

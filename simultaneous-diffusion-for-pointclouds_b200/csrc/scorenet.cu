@@ -53,7 +53,8 @@ struct Plan {
   size_t bytes = 0;
   std::vector<std::function<int(cudaStream_t, const float*, const int64_t*, float*)>> ops;
   std::map<std::string, Buf> taps;
-  size_t stats_off = 0, stats_bytes = 0;
+  size_t stats_off = 0, stats_bytes = 0;      // zeroed at the start of every forward: stats_kernel sums, tickets
+  size_t parts_off = 0;                       // per-tile partial statistics (every slot written before it is read)
   int n_kernels = 0;          // kernels (and memsets) one forward launches
   double umma_flops = 0.0;    // 2*M*N*K summed over the tensor-core convolution launches
   // fixed staging buffers inside the workspace so that the launch sequence can be replayed as a CUDA graph
@@ -90,7 +91,7 @@ struct sdpc_score {
   // optional CUDA-event bracketing of the tensor-core convolution launches (bench.py roofline)
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;
-  struct ProfRec { cudaEvent_t a, b; double flops; };
+  struct ProfRec { cudaEvent_t a, b; double flops; std::string name; };
   std::vector<ProfRec> prof;
   cudaEvent_t get_event() {
     if (!ev_pool.empty()) { cudaEvent_t e = ev_pool.back(); ev_pool.pop_back(); return e; }
@@ -235,7 +236,7 @@ struct Builder {
   static unsigned blocks(size_t total, int per = 256) { return (unsigned)((total + per - 1) / per); }
 
   // ---- norm: statistics + coefficients -------------------------------------------------
-  size_t stats_cursor = 0;
+  size_t stats_cursor = 0, parts_cursor = 0;
   struct NormRef { size_t stats_off, coef_off; };
   // statistics slot: [N][C][2] doubles filled by stats_kernel (parts_per_view == 0), or per-tile partials
   // [N][parts_per_view][C][2] floats written by a convolution epilogue (fused statistics)
@@ -248,9 +249,9 @@ struct Builder {
   }
   StatsRef new_part_stats(int C, int parts_per_view) {
     StatsRef r;
-    r.off = stats_cursor;
+    r.off = parts_cursor;
     r.parts_per_view = parts_per_view;
-    stats_cursor += al((size_t)N * parts_per_view * C * 2 * sizeof(float));
+    parts_cursor += al((size_t)N * parts_per_view * C * 2 * sizeof(float));
     return r;
   }
   bool can_fuse_stats() const { return h->cfg.precision != SDPC_PREC_FP32; }
@@ -260,6 +261,8 @@ struct Builder {
     r.stats_off = new_stats(x.C).off;                     // [N][C][2] doubles (filled by stats_kernel or the reducer)
     r.coef_off = stats_cursor;
     stats_cursor += al((size_t)N * x.C * 3 * sizeof(float));
+    const size_t ticket_off = stats_cursor;                 // per-image ticket counters of the fused reducer (zeroed with the stats area)
+    if (fused) stats_cursor += al((size_t)N * sizeof(unsigned int));
     if (dry()) return r;
     const float* in = (const float*)x.ptr;
     const int HW = x.H * x.W, C = x.C;
@@ -271,19 +274,23 @@ struct Builder {
     const size_t smem = (size_t)groups * C * 2 * sizeof(double);
     char* sbase = base + plan->stats_off;
     double* stats = (double*)(sbase + r.stats_off);
-    const float* parts = fused ? (const float*)(sbase + have->off) : nullptr;
+    const float* parts = fused ? (const float*)(base + plan->parts_off + have->off) : nullptr;
     const int ppv = fused ? have->parts_per_view : 0;
+    unsigned int* tickets = (unsigned int*)(sbase + ticket_off);
     float* coef = (float*)(sbase + r.coef_off);
     const float *al_ = h->P(pre + ".alpha"), *ga = h->P(pre + ".gamma"), *be = h->P(pre + ".beta");
     const int n = N;
     push([=](cudaStream_t s, const float*, const int64_t*, float*) -> int {
-      if (!fused) stats_kernel<<<dim3(chunks, n), 256, smem, s>>>(in, stats, HW, C, ppb);
-      else stats_reduce_parts_kernel<<<dim3(C / 32, n), 256, 0, s>>>(parts, stats, ppv, C);
-      SDPC_CUDA(cudaGetLastError());
-      norm_finalize_kernel<<<n, C, 0, s>>>(stats, al_, ga, be, coef, HW, C);
+      if (fused) {
+        stats_reduce_finalize_kernel<<<dim3(C / 8, n), 256, 0, s>>>(parts, stats, ppv, C, al_, ga, be, coef, HW, tickets);
+      } else {
+        stats_kernel<<<dim3(chunks, n), 256, smem, s>>>(in, stats, HW, C, ppb);
+        SDPC_CUDA(cudaGetLastError());
+        norm_finalize_kernel<<<n, C, 0, s>>>(stats, al_, ga, be, coef, HW, C);
+      }
       SDPC_CUDA(cudaGetLastError());
       return SDPC_OK;
-    }, 2);
+    }, fused ? 1 : 2);
     return r;
   }
   const float* coef_ptr(const NormRef& r) const { return dry() ? nullptr : (const float*)(base + plan->stats_off + r.coef_off); }
@@ -317,6 +324,8 @@ struct Builder {
     return out;
   }
 
+  // the plain bf16 arm pools on packed bf16 pairs and lets the CRP convolution leave its out_acc in bf16
+  bool pool_h2() const { return h->cfg.precision == SDPC_PREC_BF16; }
   Buf maxpool(const Buf& x, bool elu_in, Buf* x0_out) {
     Buf out = operand(x.H, x.W, x.C, 1);
     if (dry()) return out;
@@ -324,10 +333,21 @@ struct Builder {
     float* x0 = x0_out ? (float*)x0_out->ptr : nullptr;
     const int n = N, H = x.H, W = x.W, C = x.C;
     const int tf32 = h->cfg.precision == SDPC_PREC_TF32;
-    const unsigned nblk = (unsigned)((size_t)n * (H / kPoolTH) * (W / kPoolTW) * (C / kPoolCB));
     void* o = out.ptr;
-    const int elem = out.elem, ei = elu_in ? 1 : 0;
+    const int elem = out.elem, ei = elu_in ? 1 : 0, in_elem = x.elem;
     const size_t lo_off = out.lo_off;
+    if (pool_h2()) {
+      const unsigned nblk = (unsigned)((size_t)n * (H / kPoolTH) * (W / kPoolTW) * (C / kPoolHCB));
+      push([=](cudaStream_t s, const float*, const int64_t*, float*) -> int {
+        if (in_elem == 2) maxpool5_h2_kernel<__nv_bfloat16><<<nblk, kPoolHThreads, 0, s>>>((const __nv_bfloat16*)in, x0, (__nv_bfloat16*)o, n, H, W, C, 1, ei);
+        else maxpool5_h2_kernel<float><<<nblk, kPoolHThreads, 0, s>>>(in, x0, (__nv_bfloat16*)o, n, H, W, C, 1, ei);
+        SDPC_CUDA(cudaGetLastError());
+        return SDPC_OK;
+      });
+      return out;
+    }
+    if (in_elem != 4) { status = set_error(SDPC_ERR_STATE, "maxpool: fp32 input expected"); return out; }
+    const unsigned nblk = (unsigned)((size_t)n * (H / kPoolTH) * (W / kPoolTW) * (C / kPoolCB));
     push([=](cudaStream_t s, const float*, const int64_t*, float*) -> int {
       if (elem == 2) maxpool5_kernel<__nv_bfloat16><<<nblk, kPoolThreads, 0, s>>>(in, x0, (__nv_bfloat16*)o, n, H, W, C, 1, ei, tf32, lo_off);
       else maxpool5_kernel<float><<<nblk, kPoolThreads, 0, s>>>(in, x0, (float*)o, n, H, W, C, 1, ei, tf32, lo_off);
@@ -367,15 +387,25 @@ struct Builder {
     e.bias = use_bias ? cw.bias : nullptr;
     e.residual = residual ? (const float*)residual->ptr : nullptr;
     e.out_raw = out_raw ? (float*)out_raw->ptr : nullptr;
-    e.out_acc = out_acc ? (float*)out_acc->ptr : nullptr;
+    e.out_acc = out_acc ? (void*)out_acc->ptr : nullptr;
+    e.acc_bf16 = (out_acc && out_acc->elem == 2) ? 1 : 0;
     e.out_op = out_op ? out_op->ptr : nullptr;
     e.op_pad = out_op ? out_op->pad : 0;
     e.op_elu = op_elu ? 1 : 0;
     e.op_tf32 = h->cfg.precision == SDPC_PREC_TF32;
     e.op_lo_off = out_op ? out_op->lo_off : 0;
     e.prefetch_residual = getenv("SDPC_NO_PREFETCH") ? 0 : 1;
+    if (const char* dd = getenv("SDPC_DEV_EPI_DROP")) {        // development timing hook: results are garbage
+      const int m = atoi(dd);
+      if (m & 1) e.residual = nullptr;
+      if (m & 2) { e.out_raw = nullptr; e.out_acc = nullptr; }
+      if (m & 4) e.out_op = nullptr;
+      if (m & 16) e.op_elu = 0;
+      if (m & 32) e.bias = nullptr;
+    }
     g.passes = h->x3() ? 3 : 1;
-    e.stats = (stats_out && stats_out->valid()) ? (float*)(base + plan->stats_off + stats_out->off) : nullptr;
+    e.stats = (stats_out && stats_out->valid()) ? (float*)(base + plan->parts_off + stats_out->off) : nullptr;
+    if (const char* dd = getenv("SDPC_DEV_EPI_DROP")) { if (atoi(dd) & 8) e.stats = nullptr; }
     if (cw.taps == 9 && in.pad < dil) { status = set_error(SDPC_ERR_STATE, "plan: halo %d < dilation %d for %s", in.pad, dil, wname.c_str()); return; }
     if (h->cfg.precision == SDPC_PREC_FP32) {
       const float* inp = (const float*)in.ptr;
@@ -410,9 +440,14 @@ struct Builder {
     const double fl = 2.0 * (double)N * in.H * in.W * cw.Cout * cw.Cin * cw.taps;
     plan->umma_flops += fl;
     sdpc_score* hh = h;
+    char pbuf[160];
+    snprintf(pbuf, sizeof pbuf, "%s %dx%d %d->%d t%d d%d%s%s%s%s%s%s", wname.c_str(), in.H, in.W, cw.Cin, cw.Cout, cw.taps, dil,
+             e.bias ? " bias" : "", e.residual ? " res" : "", e.out_raw ? " raw" : "", e.out_acc ? " acc" : "",
+             e.out_op ? (e.op_elu ? " op+elu" : " op") : "", e.stats ? " stats" : "");
+    const std::string pname = pbuf;
     push([=](cudaStream_t s, const float*, const int64_t*, float*) -> int {
       if (!hh->profiling) return conv_umma_launch(L, s);
-      sdpc_score::ProfRec r{hh->get_event(), hh->get_event(), fl};
+      sdpc_score::ProfRec r{hh->get_event(), hh->get_event(), fl, pname};
       cudaEventRecord(r.a, s);
       int st = conv_umma_launch(L, s);
       cudaEventRecord(r.b, s);
@@ -462,7 +497,7 @@ struct Builder {
       conv(xp, pre + ".shortcut.conv.weight", 1, true, nullptr, &s2, nullptr, nullptr, false);
       release(xp);
       out = raw(x.H / 2, x.W / 2, co);
-      pool(t2, &s2, nullptr, &out);
+      pool(t2, &s2, nullptr, &out, out_stats);
       release(t2);
       release(s2);
     } else {
@@ -478,7 +513,13 @@ struct Builder {
     return out;
   }
 
-  void pool(const Buf& x, const Buf* add, Buf* out_op, Buf* out_raw) {
+  //   stats_out : with add + out_raw only; receives the slot of out_raw's partial statistics (fused into the pooling pass)
+  void pool(const Buf& x, const Buf* add, Buf* out_op, Buf* out_raw, StatsRef* stats_out = nullptr) {
+    const int Ho = x.H / 2, Wo = x.W / 2;
+    const size_t px_per_block = (size_t)kMpIter * 256 / (x.C / 4);
+    const bool fuse = stats_out && can_fuse_stats() && add && out_raw && !out_op && 256 % (x.C / 4) == 0 &&
+                      ((size_t)Ho * Wo) % px_per_block == 0;
+    if (stats_out) *stats_out = fuse ? new_part_stats(x.C, (int)((size_t)Ho * Wo / px_per_block)) : StatsRef();
     if (dry()) return;
     const float* in = (const float*)x.ptr;
     const float* ad = add ? (const float*)add->ptr : nullptr;
@@ -488,6 +529,16 @@ struct Builder {
     const size_t lo_off = out_op ? out_op->lo_off : 0;
     const int n = N, H = x.H, W = x.W, C = x.C, tf32 = h->cfg.precision == SDPC_PREC_TF32;
     const size_t total = (size_t)n * (H / 2) * (W / 2) * (C / 4);
+    if (fuse) {
+      float2* sp = (float2*)(base + plan->parts_off + stats_out->off);
+      const unsigned nblk = (unsigned)(total / ((size_t)kMpIter * 256));
+      push([=](cudaStream_t s, const float*, const int64_t*, float*) -> int {
+        meanpool_add_stats_kernel<<<nblk, 256, 0, s>>>(in, ad, orr, sp, n, H, W, C);
+        SDPC_CUDA(cudaGetLastError());
+        return SDPC_OK;
+      });
+      return;
+    }
     push([=](cudaStream_t s, const float*, const int64_t*, float*) -> int {
       if (elem == 2) meanpool_kernel<__nv_bfloat16><<<blocks(total), 256, 0, s>>>(in, ad, (__nv_bfloat16*)oo, orr, n, H, W, C, tf32, lo_off);
       else meanpool_kernel<float><<<blocks(total), 256, 0, s>>>(in, ad, (float*)oo, orr, n, H, W, C, tf32, lo_off);
@@ -537,7 +588,8 @@ struct Builder {
     Buf x0 = raw(hbuf.H, hbuf.W, hbuf.C);
     Buf p0 = maxpool(hbuf, true, &x0);                 // x0 = ELU(h); p0 = maxpool(x0)
     release(hbuf);
-    Buf path1 = raw(x0.H, x0.W, x0.C), x1 = raw(x0.H, x0.W, x0.C);
+    Buf path1 = pool_h2() ? alloc(N, x0.H, x0.W, x0.C, 0, 2) : raw(x0.H, x0.W, x0.C);     // only the next max-pool reads it
+    Buf x1 = raw(x0.H, x0.W, x0.C);
     conv(p0, pre + ".convs.0.weight", 1, false, &x0, &x1, &path1, nullptr, false);
     release(p0);
     release(x0);
@@ -613,12 +665,15 @@ struct Builder {
       plan->io_bytes = (size_t)N * c.channels * H * W * sizeof(float);
     }
     Buf r0 = raw(H, W, g);
+    StatsRef st_r0;                                    // statistics of begin_conv's output, one partial per 64-pixel block
+    if (can_fuse_stats()) st_r0 = new_part_stats(g, H * (W / 64));
     if (!dry()) {
       float* o = (float*)r0.ptr;
+      float2* sp = st_r0.valid() ? (float2*)(base + plan->parts_off + st_r0.off) : nullptr;
       const float *wg = h->P("begin_conv.weight"), *bs = h->P("begin_conv.bias");
       const int n = N;
       push([=](cudaStream_t s, const float* x, const int64_t*, float*) -> int {
-        begin_conv_kernel<128><<<n * H * (W / 64), 128, 0, s>>>(x, wg, bs, o, n, H, W);
+        begin_conv_kernel<128><<<n * H * (W / 64), 128, 0, s>>>(x, wg, bs, o, sp, n, H, W);
         SDPC_CUDA(cudaGetLastError());
         return SDPC_OK;
       });
@@ -628,12 +683,13 @@ struct Builder {
     // l*_op / r*_op: ELU(layer) operands emitted by the producing convolution for the refine blocks' RCUs
     Buf l1_op, l2_op, l3_op, l4_op, r1_op, r2_op, r3_op;
     StatsRef st_a, st_b;                               // statistics of the running trunk tensor, filled by its producer
-    Buf t = residual_block("res1.0", r0, RES_PLAIN, 0, nullptr, nullptr, &st_a);
+    Buf t = residual_block("res1.0", r0, RES_PLAIN, 0, nullptr, st_r0.valid() ? &st_r0 : nullptr, &st_a);
     release(r0);
     Buf l1 = residual_block("res1.1", t, RES_PLAIN, 0, &l1_op, &st_a, &st_b);
     release(t);
-    t = residual_block("res2.0", l1, RES_DOWN_POOL, 0, nullptr, &st_b, nullptr);    // output comes from the pooling kernel
-    Buf l2 = residual_block("res2.1", t, RES_PLAIN, 0, &l2_op, nullptr, &st_a);
+    StatsRef st_p;                                     // res2.0's output comes from the pooling kernel, which also leaves its statistics
+    t = residual_block("res2.0", l1, RES_DOWN_POOL, 0, nullptr, &st_b, &st_p);
+    Buf l2 = residual_block("res2.1", t, RES_PLAIN, 0, &l2_op, st_p.valid() ? &st_p : nullptr, &st_a);
     release(t);
     t = residual_block("res3.0", l2, RES_DILATED, 2, nullptr, &st_a, &st_b);
     Buf l3 = residual_block("res3.1", t, RES_PLAIN, 2, &l3_op, &st_b, &st_a);
@@ -653,21 +709,23 @@ struct Builder {
     Buf r4 = refine("refine4", {&l1, &r3}, {&l1_op, &r3_op}, g, l1.H, l1.W, false, true, nullptr, &st_r4);
     release(l1);
     release(r3);
-    Buf fin = norm_elu_operand(r4, "normalizer", 1, HALO_ZERO, /*force_fp32=*/true, &st_r4);
-    release(r4);
+    // tail: normalizer -> ELU -> end_conv -> / sigma in one kernel reading the raw trunk (fp32 in every arm)
+    NormRef nr = norm(r4, "normalizer", &st_r4);
     flops += 2.0 * H * W * c.channels * g * 9;
+    if (H % kEndRows) { status = set_error(SDPC_ERR_UNSUPPORTED, "end_conv: H=%d not a multiple of %d", H, kEndRows); return; }
     if (!dry()) {
-      const float* op = (const float*)fin.ptr;
+      const float* rw = (const float*)r4.ptr;
+      const float* cf = coef_ptr(nr);
       const float *wg = h->P("end_conv.weight"), *bs = h->P("end_conv.bias"), *sg = h->P("sigmas");
-      const int n = N;
+      const int n = N, fast = h->cfg.precision != SDPC_PREC_FP32;
       push([=](cudaStream_t s, const float*, const int64_t* labels, float* out) -> int {
-        const size_t strips = (size_t)n * H * (W / 8);
-        end_conv_kernel<128><<<(unsigned)((strips + 7) / 8), 256, 0, s>>>(op, wg, bs, sg, labels, out, n, H, W);
+        const size_t strips = (size_t)n * (H / kEndRows) * (W / 8);
+        end_conv_norm_kernel<128><<<(unsigned)((strips + 7) / 8), 256, 0, s>>>(rw, cf, wg, bs, sg, labels, out, n, H, W, fast);
         SDPC_CUDA(cudaGetLastError());
         return SDPC_OK;
       });
     }
-    release(fin);
+    release(r4);
   }
 };
 
@@ -676,9 +734,9 @@ static int build_plan(sdpc_score* h, int n_views, char* ws, size_t ws_bytes, Pla
   Plan scratch;
   Builder dryb{h, &scratch, nullptr, n_views};
   dryb.build();
-  const size_t arena = dryb.high, stats = dryb.stats_cursor;
+  const size_t arena = dryb.high, stats = dryb.stats_cursor, parts = dryb.parts_cursor;
   h->flops_per_view = dryb.flops;
-  *need = arena + stats + 1024;
+  *need = arena + stats + parts + 1024;
   if (!ws) return SDPC_OK;
   if (ws_bytes < *need) return set_error(SDPC_ERR_WORKSPACE, "score workspace too small: %zu < %zu", ws_bytes, *need);
   char* aligned = (char*)(((uintptr_t)ws + 1023) & ~(uintptr_t)1023);
@@ -691,6 +749,7 @@ static int build_plan(sdpc_score* h, int n_views, char* ws, size_t ws_bytes, Pla
   plan->n_views = n_views;
   plan->stats_off = arena;
   plan->stats_bytes = stats;
+  plan->parts_off = arena + stats;
   Builder b{h, plan, aligned, n_views};
   // the statistics area is zeroed at the start of every forward
   char* sbase = aligned + arena;
@@ -892,15 +951,19 @@ extern "C" int sdpc_score_set_profiling(sdpc_score_t* h, int on) {
 extern "C" int sdpc_score_profile_collect(sdpc_score_t* h, double* total_ms, double* total_flops, int* n_launches) {
   if (!h) return set_error(SDPC_ERR_ARG, "profile_collect: null handle");
   double ms = 0.0, fl = 0.0;
+  const char* dump = getenv("SDPC_PROFILE_DUMP");             // per-launch csv (name, flops, ms) for tools/conv_layers.py
+  FILE* df = dump ? fopen(dump, "a") : nullptr;
   for (auto& r : h->prof) {
     SDPC_CUDA(cudaEventSynchronize(r.b));
     float t = 0.0f;
     SDPC_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
+    if (df) fprintf(df, "%s,%.0f,%.6f\n", r.name.c_str(), r.flops, t);
     ms += t;
     fl += r.flops;
     h->ev_pool.push_back(r.a);
     h->ev_pool.push_back(r.b);
   }
+  if (df) fclose(df);
   if (total_ms) *total_ms = ms;
   if (total_flops) *total_flops = fl;
   if (n_launches) *n_launches = (int)h->prof.size();
