@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsdpc_b200.so")
+LIB_PATH = os.environ.get("SDPC_LIB") or os.path.join(_HERE, "libsdpc_b200.so")   # SDPC_LIB: A/B timing of two builds
 
 SDPC_VARIANT_POSE, SDPC_VARIANT_TRANSLATION = 0, 1
 PREC_FP32, PREC_TF32, PREC_BF16, PREC_BF16X3 = 0, 1, 2, 3

@@ -278,22 +278,17 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (e.stats)                                         // slot [tile][half][Cout][2], written exactly once
           *reinterpret_cast<float2*>(e.stats + (((size_t)tile * 2 + half) * kCout + ch) * 2) = make_float2(ssum, ssq);
       } else {
-        // element offsets of the lane's 8 pixels (the same for every channel chunk) into the raw tensors / the
-        // padded operand tensor, plus the deltas to the circular-halo duplicates a pixel owns (0 = none)
-        uint32_t raw_off[8], op_off[8];
-        int32_t dup_w[8], dup_h[8];
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int m = quad * 32 + it * 4 + psub;
-          const int h = h0 + (m >> g.bw_shift), w = w0 + (m & (g.BW - 1));
-          raw_off[it] = (uint32_t)((((size_t)n * g.H + h) * g.W + w) * kCout);
-          op_off[it] = (uint32_t)((((size_t)n * Hp + h + P) * Wp + w + P) * kCout);
-          dup_w[it] = (w < P) ? g.W * kCout : ((w >= g.W - P) ? -g.W * kCout : 0);
-          dup_h[it] = (h < P) ? g.H * Wp * kCout : ((h >= g.H - P) ? -g.H * Wp * kCout : 0);
-        }
+        // The quadrant's 32 pixels lie on one image row (BW >= 32): the lane's pixel `it` is (h, w + 4*it), so every
+        // tensor offset is one per-tile base plus a compile-time multiple of kCout.  Warps whose pixels touch the
+        // image border additionally write the circular-halo duplicates of the operand (slow path, warp-uniform).
+        const int m0 = quad * 32;
+        const int h = h0 + (m0 >> g.bw_shift), wq = w0 + (m0 & (g.BW - 1)), w = wq + psub;
+        const size_t raw0 = (((size_t)n * g.H + h) * g.W + w) * kCout;
+        const size_t op0 = (((size_t)n * Hp + h + P) * Wp + w + P) * kCout;
+        const bool edge = P > 0 && (h < P || h >= g.H - P || wq < P || wq + 32 > g.W - P);
         // fused InstanceNorm++ statistics of the value written to out_raw: per lane 4 channels, summed over the
         // lane's pixels, then over the 4 lanes sharing a channel quad; the warp's partial goes to its own slot
-        // [tile][quad][Cout][2] (no atomics, every slot written exactly once; stats_reduce_parts sums the slots).
+        // [tile][quad][Cout][2] (no atomics, every slot written exactly once; the reducer sums the slots).
         float ssum[4] = {0.f, 0.f, 0.f, 0.f}, ssq[4] = {0.f, 0.f, 0.f, 0.f};
         mbar_wait(acc_full + ab, acc_phase);
         __syncwarp();
@@ -304,12 +299,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           // issue the residual loads first: their latency overlaps the TMEM read and the staging round trip
           float4 res[8];
           if (e.residual) {
-            const float* rp = e.residual + ch;
+            const float* rp = e.residual + raw0 + ch;
 #pragma unroll
-            for (int it = 0; it < 8; ++it) res[it] = *reinterpret_cast<const float4*>(rp + raw_off[it]);
+            for (int it = 0; it < 8; ++it) res[it] = *reinterpret_cast<const float4*>(rp + it * 4 * kCout);
           }
-          float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (e.bias) bias4 = *reinterpret_cast<const float4*>(e.bias + ch);
           uint32_t r[32];
           tmem_ld_32x32(t_addr + c0, r);
           tmem_ld_wait();
@@ -325,37 +318,70 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             stg4[stg_slot(lane, j)] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
                                                   __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
           __syncwarp();
-          float* const acc_p = (e.out_acc && !e.acc_bf16) ? reinterpret_cast<float*>(e.out_acc) + ch : nullptr;
-          __nv_bfloat16* const acc_h = (e.out_acc && e.acc_bf16) ? reinterpret_cast<__nv_bfloat16*>(e.out_acc) + ch : nullptr;
-          float* const raw_p = e.out_raw ? e.out_raw + ch : nullptr;
-          T* const op_p = e.out_op ? reinterpret_cast<T*>(e.out_op) + ch : nullptr;
+          float4 v[8];
 #pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            float4 v = stg4[stg_slot(it * 4 + psub, cq)];
-            v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
-            if (acc_p) *reinterpret_cast<float4*>(acc_p + raw_off[it]) = v;
-            if (acc_h) {
-              const float a4[4] = {v.x, v.y, v.z, v.w};
-              store_op4<__nv_bfloat16>(acc_h + raw_off[it], a4, false, 0);
-            }
-            if (e.residual) { v.x += res[it].x; v.y += res[it].y; v.z += res[it].z; v.w += res[it].w; }
-            if (raw_p) *reinterpret_cast<float4*>(raw_p + raw_off[it]) = v;
-            if (e.stats) {
-              ssum[0] += v.x; ssum[1] += v.y; ssum[2] += v.z; ssum[3] += v.w;
-              ssq[0] = fmaf(v.x, v.x, ssq[0]); ssq[1] = fmaf(v.y, v.y, ssq[1]);
-              ssq[2] = fmaf(v.z, v.z, ssq[2]); ssq[3] = fmaf(v.w, v.w, ssq[3]);
-            }
-            if (op_p) {
-              float o[4] = {v.x, v.y, v.z, v.w};
-              if (e.op_elu) {
-                o[0] = elu_sel<T>(o[0], red); o[1] = elu_sel<T>(o[1], red); o[2] = elu_sel<T>(o[2], red); o[3] = elu_sel<T>(o[3], red);
+          for (int it = 0; it < 8; ++it) v[it] = stg4[stg_slot(it * 4 + psub, cq)];
+          if (e.bias) {
+            const float4 b4 = *reinterpret_cast<const float4*>(e.bias + ch);
+#pragma unroll
+            for (int it = 0; it < 8; ++it) { v[it].x += b4.x; v[it].y += b4.y; v[it].z += b4.z; v[it].w += b4.w; }
+          }
+          if (e.out_acc) {
+            if (e.acc_bf16) {
+              __nv_bfloat16* ap = reinterpret_cast<__nv_bfloat16*>(e.out_acc) + raw0 + ch;
+#pragma unroll
+              for (int it = 0; it < 8; ++it) {
+                const float a4[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
+                store_op4<__nv_bfloat16>(ap + it * 4 * kCout, a4, false, 0);
               }
-              T* d = op_p + op_off[it];
-              store_op4<T>(d, o, red, e.op_lo_off);
-              if (dup_w[it]) store_op4<T>(d + dup_w[it], o, red, e.op_lo_off);
-              if (dup_h[it]) {
-                store_op4<T>(d + dup_h[it], o, red, e.op_lo_off);
-                if (dup_w[it]) store_op4<T>(d + dup_h[it] + dup_w[it], o, red, e.op_lo_off);
+            } else {
+              float* ap = reinterpret_cast<float*>(e.out_acc) + raw0 + ch;
+#pragma unroll
+              for (int it = 0; it < 8; ++it) *reinterpret_cast<float4*>(ap + it * 4 * kCout) = v[it];
+            }
+          }
+          if (e.residual) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) { v[it].x += res[it].x; v[it].y += res[it].y; v[it].z += res[it].z; v[it].w += res[it].w; }
+          }
+          if (e.out_raw) {
+            float* op = e.out_raw + raw0 + ch;
+#pragma unroll
+            for (int it = 0; it < 8; ++it) *reinterpret_cast<float4*>(op + it * 4 * kCout) = v[it];
+          }
+          if (e.stats) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              ssum[0] += v[it].x; ssum[1] += v[it].y; ssum[2] += v[it].z; ssum[3] += v[it].w;
+              ssq[0] = fmaf(v[it].x, v[it].x, ssq[0]); ssq[1] = fmaf(v[it].y, v[it].y, ssq[1]);
+              ssq[2] = fmaf(v[it].z, v[it].z, ssq[2]); ssq[3] = fmaf(v[it].w, v[it].w, ssq[3]);
+            }
+          }
+          if (e.out_op) {
+            if (e.op_elu) {
+#pragma unroll
+              for (int it = 0; it < 8; ++it)
+                v[it] = make_float4(elu_sel<T>(v[it].x, red), elu_sel<T>(v[it].y, red), elu_sel<T>(v[it].z, red), elu_sel<T>(v[it].w, red));
+            }
+            T* const ob = reinterpret_cast<T*>(e.out_op) + op0 + ch;
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const float o[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
+              store_op4<T>(ob + it * 4 * kCout, o, red, e.op_lo_off);
+            }
+            if (edge) {
+              const ptrdiff_t dh = (h < P) ? (ptrdiff_t)g.H * Wp * kCout : ((h >= g.H - P) ? -(ptrdiff_t)g.H * Wp * kCout : 0);
+#pragma unroll
+              for (int it = 0; it < 8; ++it) {
+                const int wi = w + it * 4;
+                const ptrdiff_t dw = (wi < P) ? (ptrdiff_t)g.W * kCout : ((wi >= g.W - P) ? -(ptrdiff_t)g.W * kCout : 0);
+                const float o[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
+                T* const d = ob + it * 4 * kCout;
+                if (dw) store_op4<T>(d + dw, o, red, e.op_lo_off);
+                if (dh) {
+                  store_op4<T>(d + dh, o, red, e.op_lo_off);
+                  if (dw) store_op4<T>(d + dh + dw, o, red, e.op_lo_off);
+                }
               }
             }
           }

@@ -112,23 +112,29 @@ stats_kernel(const float* __restrict__ in, double* __restrict__ stats, int HW, i
 // coef[n][c] = {mean, a, b}: out = a*(x-mean) + b with a = gamma*rstd, b = gamma*alpha*mean_n + beta
 // (InstanceNorm2dPlus, normalization.py:163-176).  Called by the first C threads of a block (C <= 256); `S`, `Q` are
 // the channel's sum and sum of squares over the image.
+// block-wide sum of one double per thread (blockDim.x a multiple of 32, <= 256), fixed reduction tree
+__device__ __forceinline__ double block_sum_256(double v, double* warp_part /*[8]*/) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();                                    // warp_part may still be read from a previous call
+  if ((threadIdx.x & 31) == 0) warp_part[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0.0;
+  const int nw = blockDim.x >> 5;
+  for (int i = 0; i < nw; ++i) t += warp_part[i];
+  return t;
+}
+
 __device__ __forceinline__ void norm_coefficients(double S, double Q, const float* __restrict__ alpha,
                                                   const float* __restrict__ gamma, const float* __restrict__ beta,
                                                   float* __restrict__ coef, int HW, int C, int n, int c, bool active) {
-  __shared__ double sm[256];
-  __shared__ double s_m, s_v;
+  __shared__ double wp[8];
   const double mean = S / HW;
   double var = Q / HW - mean * mean;
   if (var < 0.0) var = 0.0;
-  if (active) sm[c] = mean;
-  __syncthreads();
-  if (c == 0) { double t = 0; for (int i = 0; i < C; ++i) t += sm[i]; s_m = t / C; }
-  __syncthreads();
+  const double s_m = block_sum_256(active ? mean : 0.0, wp) / C;
   const double dm = mean - s_m;
-  if (active) sm[c] = dm * dm;
-  __syncthreads();
-  if (c == 0) { double t = 0; for (int i = 0; i < C; ++i) t += sm[i]; s_v = t / (C - 1); }
-  __syncthreads();
+  const double s_v = block_sum_256(active ? dm * dm : 0.0, wp) / (C - 1);
   if (!active) return;
   const float rstd = 1.0f / sqrtf((float)var + 1e-5f);
   const float mean_n = (float)dm / sqrtf((float)s_v + 1e-5f);
@@ -155,7 +161,7 @@ stats_reduce_finalize_kernel(const float* __restrict__ parts, double* __restrict
                              const float* __restrict__ alpha, const float* __restrict__ gamma,
                              const float* __restrict__ beta, float* __restrict__ coef, int HW,
                              unsigned int* __restrict__ tickets) {
-  __shared__ double red[32][8][2];
+  __shared__ double red[8][8][2];
   __shared__ bool s_last;
   const int cl = threadIdx.x & 7, grp = threadIdx.x >> 3;
   const int c = blockIdx.x * 8 + cl, n = blockIdx.y;
@@ -167,12 +173,15 @@ stats_reduce_finalize_kernel(const float* __restrict__ parts, double* __restrict
     S += (double)v.x;
     Q += (double)v.y;
   }
-  red[grp][cl][0] = S;
-  red[grp][cl][1] = Q;
+  // lanes of a warp hold 4 part-groups x 8 channels: fold the groups with shuffles, then the 8 warps through shared memory
+  S += __shfl_xor_sync(0xffffffffu, S, 8);  Q += __shfl_xor_sync(0xffffffffu, Q, 8);
+  S += __shfl_xor_sync(0xffffffffu, S, 16); Q += __shfl_xor_sync(0xffffffffu, Q, 16);
+  if ((threadIdx.x & 31) < 8) { red[threadIdx.x >> 5][cl][0] = S; red[threadIdx.x >> 5][cl][1] = Q; }
   __syncthreads();
-  if (grp == 0) {
+  if (threadIdx.x < 8) {
+    S = red[0][cl][0]; Q = red[0][cl][1];
 #pragma unroll
-    for (int k = 1; k < 32; ++k) { S += red[k][cl][0]; Q += red[k][cl][1]; }
+    for (int k = 1; k < 8; ++k) { S += red[k][cl][0]; Q += red[k][cl][1]; }
     stats[((size_t)n * C + c) * 2] = S;
     stats[((size_t)n * C + c) * 2 + 1] = Q;
     __threadfence();
@@ -653,25 +662,41 @@ end_conv_kernel(const float* __restrict__ op, const float* __restrict__ wgt, con
 
 // Fused tail of the network: normalizer (InstanceNorm++) -> ELU -> end_conv -> / sigmas[y] (ncsnv2.py:509-516)
 // reading the raw fp32 trunk once, instead of materialising the activated tensor (a 268 MB write and a 3x re-read).
-// One warp owns an 8-pixel-wide, kEndRows-tall strip and walks DOWN its input rows: every input row (10 columns
-// x 4 channels per lane) is loaded, normalised and activated once, and feeds the three output rows it touches
-// (tap rows 0,1,2 in the same order as end_conv_kernel, so the sums are formed identically).  Out-of-image inputs
-// are the zero padding of the activated tensor.
+// One warp owns an 8-pixel-wide, kEndRows-tall strip and walks DOWN its input rows; a lane owns 4 input channels.
+//  * every input row (10 columns x 16 bytes per lane) is prefetched with cp.async into a per-thread shared-memory
+//    slot one row ahead, so the load latency hides behind the previous row's arithmetic;
+//  * the row is normalised and activated once and feeds the three output rows it touches: accumulators r0 / r1 / r2
+//    hold output rows hi+1 / hi / hi-1 and rotate after every input row (tap rows are added in the order 0, 1, 2);
+//  * the 16 per-lane partial sums of a finished output row are reduced across the 32 lanes with a transposing
+//    butterfly (8+4+2+1+1 shuffles instead of 16 x 5): lane l ends up with the total of output (co = l>>4, px = (l>>1)&7).
+// Out-of-image inputs are the zero padding of the activated tensor.
 constexpr int kEndRows = 16;
+constexpr int kEndThreads = 128;
+constexpr int kEndSmemBytes = 2 * 9 * 128 * 4 + 2 * 10 * kEndThreads * 16;    // weights + two row slots per thread
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 template <int NGF>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kEndThreads, 4)
 end_conv_norm_kernel(const float* __restrict__ raw, const float* __restrict__ coef, const float* __restrict__ wgt,
                      const float* __restrict__ bias, const float* __restrict__ sigmas,
                      const int64_t* __restrict__ labels, float* __restrict__ out, int N, int H, int W, int fast_elu) {
   static_assert(NGF == 128, "one float4 per lane");
-  __shared__ __align__(16) float sw[2][9][NGF];
+  extern __shared__ __align__(16) uint8_t end_smem[];
+  float (*sw)[9][NGF] = reinterpret_cast<float (*)[9][NGF]>(end_smem);                       // [2][9][NGF]
+  float4* slots = reinterpret_cast<float4*>(end_smem + 2 * 9 * NGF * 4);                     // [2][10][kEndThreads]
   for (int i = threadIdx.x; i < 2 * 9 * NGF; i += blockDim.x) {
     const int co = i / (9 * NGF), r = i % (9 * NGF), tap = r / NGF, ci = r % NGF;
     sw[co][tap][ci] = wgt[((size_t)co * NGF + ci) * 9 + tap];
   }
   __syncthreads();
   const int lane = threadIdx.x & 31;
-  const size_t strip = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const size_t strip = (size_t)blockIdx.x * (kEndThreads >> 5) + (threadIdx.x >> 5);
   const int W8 = W / 8, HB = H / kEndRows;
   if (strip >= (size_t)N * HB * W8) return;
   const int w0 = (int)(strip % W8) * 8, hb0 = (int)((strip / W8) % HB) * kEndRows, n = (int)(strip / ((size_t)W8 * HB));
@@ -684,39 +709,47 @@ end_conv_norm_kernel(const float* __restrict__ raw, const float* __restrict__ co
     mu[2] = t1.z; ga[2] = t1.w; be[2] = t2.x; mu[3] = t2.y; ga[3] = t2.z; be[3] = t2.w;
   }
   const float sg = sigmas[labels[n]];
-  const float b0 = bias[0], b1 = bias[1];
-  float acc[3][2][8];                                   // [output row slot][co][pixel]; slot of output row ho = (ho - hb0 + 3) % 3
-#pragma unroll
-  for (int s = 0; s < 3; ++s)
-#pragma unroll
-    for (int i = 0; i < 8; ++i) acc[s][0][i] = acc[s][1][i] = 0.0f;
+  const int co_l = lane >> 4, px_l = (lane >> 1) & 7;           // the output this lane holds after the reduction
+  const float bias_l = bias[co_l];
+  const int jlo = (w0 == 0) ? 1 : 0, jhi = (w0 + 8 == W) ? 9 : 10;   // in-image columns of the 10-column window
 
+  auto prefetch = [&](int st) {                                 // input row hb0 - 1 + st into slot st & 1
+    const int hi = hb0 - 1 + st;
+    if (st < kEndRows + 2 && hi >= 0 && hi < H) {
+      const float* row = raw + (((size_t)n * H + hi) * W + w0 - 1) * NGF + lane * 4;
+      float4* dst = slots + (size_t)(st & 1) * 10 * kEndThreads + threadIdx.x;
+#pragma unroll
+      for (int j = 0; j < 10; ++j)
+        if (j >= jlo && j < jhi) cp_async16(dst + j * kEndThreads, row + (size_t)j * NGF);
+    }
+    cp_async_commit();
+  };
   auto act = [&](float v, int k) {
     const float t = ga[k] * (v - mu[k]) + be[k];
     return fast_elu ? elu_fast(t) : elu1(t);
   };
-  // input row hi = hb0 - 1 + step feeds output rows hi+1 (tap row 0), hi (tap row 1), hi-1 (tap row 2, completing it)
-  auto step = [&](int st, auto slot_c) {
-    constexpr int S = decltype(slot_c)::value;           // st % 3
+
+  float r0[2][8], r1[2][8], r2[2][8];                           // partial sums of output rows hi+1, hi, hi-1
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r0[0][i] = r0[1][i] = r1[0][i] = r1[1][i] = r2[0][i] = r2[1][i] = 0.0f;
+  prefetch(0);
+#pragma unroll 1
+  for (int st = 0; st < kEndRows + 2; ++st) {
     const int hi = hb0 - 1 + st;
-    float4 col[10];
+    prefetch(st + 1);
+    cp_async_wait<1>();                                         // row st has landed (a thread reads back only its own bytes)
     if (hi >= 0 && hi < H) {
-      const float* row = raw + (((size_t)n * H + hi) * W + w0 - 1) * NGF + lane * 4;
+      const float4* src = slots + (size_t)(st & 1) * 10 * kEndThreads + threadIdx.x;
+      float4 col[10];
 #pragma unroll
       for (int j = 0; j < 10; ++j) {
-        const int ww = w0 - 1 + j;
         col[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ww >= 0 && ww < W) {
-          const float4 v = *reinterpret_cast<const float4*>(row + (size_t)j * NGF);
+        if (j >= jlo && j < jhi) {
+          const float4 v = src[j * kEndThreads];
           col[j] = make_float4(act(v.x, 0), act(v.y, 1), act(v.z, 2), act(v.w, 3));
         }
       }
-#pragma unroll
-      for (int kh = 0; kh < 3; ++kh) {
-        // output row hi + 1 - kh lives in slot (st + 1 - kh) % 3 = (S + 4 - kh) % 3
-        const int sl = (S + 4 - kh) % 3;
-        const int ho_k = hi + 1 - kh;
-        if (ho_k < hb0 || ho_k >= hb0 + kEndRows) continue;       // that row belongs to the strip above / below
+      auto taps = [&](float (&acc)[2][8], int kh) {
 #pragma unroll
         for (int kw = 0; kw < 3; ++kw) {
           const float4 w0v = *reinterpret_cast<const float4*>(&sw[0][kh * 3 + kw][lane * 4]);
@@ -724,40 +757,51 @@ end_conv_norm_kernel(const float* __restrict__ raw, const float* __restrict__ co
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float4 v = col[i + kw];
-            acc[sl][0][i] += v.x * w0v.x + v.y * w0v.y + v.z * w0v.z + v.w * w0v.w;
-            acc[sl][1][i] += v.x * w1v.x + v.y * w1v.y + v.z * w1v.z + v.w * w1v.w;
+            acc[0][i] = fmaf(v.w, w0v.w, fmaf(v.z, w0v.z, fmaf(v.y, w0v.y, fmaf(v.x, w0v.x, acc[0][i]))));
+            acc[1][i] = fmaf(v.w, w1v.w, fmaf(v.z, w1v.z, fmaf(v.y, w1v.y, fmaf(v.x, w1v.x, acc[1][i]))));
           }
         }
-      }
+      };
+      if (hi + 1 < hb0 + kEndRows) taps(r0, 0);                 // rows outside [hb0, hb0 + kEndRows) belong to other strips
+      if (hi >= hb0 && hi < hb0 + kEndRows) taps(r1, 1);
+      if (hi - 1 >= hb0) taps(r2, 2);
     }
-    // output row ho = hi - 1 (slot (S + 2) % 3) is complete
-    const int ho = hi - 1;
-    constexpr int so = (S + 2) % 3;
+    const int ho = hi - 1;                                      // r2 is complete
     if (ho >= hb0 && ho < hb0 + kEndRows) {
+      // transposing butterfly: at distance o a lane keeps the half of its values selected by its bit o and adds the
+      // partner's copy of that half, so the value count halves per level
+      float b[8], c[4], d[2], e;
+      const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2;
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        for (int o = 16; o > 0; o >>= 1) {
-          acc[so][0][i] += __shfl_xor_sync(0xffffffffu, acc[so][0][i], o);
-          acc[so][1][i] += __shfl_xor_sync(0xffffffffu, acc[so][1][i], o);
-        }
-      if (lane < 8) {
-        float v0 = acc[so][0][0], v1 = acc[so][1][0];
-#pragma unroll
-        for (int i = 1; i < 8; ++i) if (lane == i) { v0 = acc[so][0][i]; v1 = acc[so][1][i]; }
-        out[(((size_t)n * 2 + 0) * H + ho) * W + w0 + lane] = (v0 + b0) / sg;
-        out[(((size_t)n * 2 + 1) * H + ho) * W + w0 + lane] = (v1 + b1) / sg;
+      for (int k = 0; k < 8; ++k) {                             // value index = co * 8 + px: bit 4 of the lane selects co
+        const float keep = h16 ? r2[1][k] : r2[0][k], send = h16 ? r2[0][k] : r2[1][k];
+        b[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
       }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float keep = h8 ? b[k + 4] : b[k], send = h8 ? b[k] : b[k + 4];
+        c[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+      }
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const float keep = h4 ? c[k + 2] : c[k], send = h4 ? c[k] : c[k + 2];
+        d[k] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+      }
+      {
+        const float keep = h2 ? d[1] : d[0], send = h2 ? d[0] : d[1];
+        e = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+      }
+      e += __shfl_xor_sync(0xffffffffu, e, 1);
+      if ((lane & 1) == 0) out[(((size_t)n * 2 + co_l) * H + ho) * W + w0 + px_l] = (e + bias_l) / sg;
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[so][0][i] = acc[so][1][i] = 0.0f;   // the slot restarts as output row hi + 2
-  };
-  static_assert((kEndRows + 2) % 3 == 0, "the row walk is unrolled by the three accumulator slots");
-#pragma unroll 1
-  for (int st = 0; st < kEndRows + 2; st += 3) {
-    step(st, std::integral_constant<int, 0>());
-    step(st + 1, std::integral_constant<int, 1>());
-    step(st + 2, std::integral_constant<int, 2>());
+    for (int i = 0; i < 8; ++i) {
+      r2[0][i] = r1[0][i]; r2[1][i] = r1[1][i];
+      r1[0][i] = r0[0][i]; r1[1][i] = r0[1][i];
+      r0[0][i] = r0[1][i] = 0.0f;
+    }
   }
+  cp_async_wait<0>();
 }
 
 // NHWC fp32 -> NCHW fp32 (debug taps)

@@ -719,8 +719,14 @@ struct Builder {
       const float *wg = h->P("end_conv.weight"), *bs = h->P("end_conv.bias"), *sg = h->P("sigmas");
       const int n = N, fast = h->cfg.precision != SDPC_PREC_FP32;
       push([=](cudaStream_t s, const float*, const int64_t* labels, float* out) -> int {
+        static bool attr_set = false;
+        if (!attr_set) {
+          SDPC_CUDA(cudaFuncSetAttribute(end_conv_norm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kEndSmemBytes));
+          attr_set = true;
+        }
         const size_t strips = (size_t)n * (H / kEndRows) * (W / 8);
-        end_conv_norm_kernel<128><<<(unsigned)((strips + 7) / 8), 256, 0, s>>>(rw, cf, wg, bs, sg, labels, out, n, H, W, fast);
+        const int wpb = kEndThreads / 32;
+        end_conv_norm_kernel<128><<<(unsigned)((strips + wpb - 1) / wpb), kEndThreads, kEndSmemBytes, s>>>(rw, cf, wg, bs, sg, labels, out, n, H, W, fast);
         SDPC_CUDA(cudaGetLastError());
         return SDPC_OK;
       });
