@@ -216,6 +216,28 @@ int sdpc_pointcloud_to_range_image(const sdpc_projection_params* p, const double
                                    double* intensity, uint8_t* obfuscation, uint8_t* sky, double* index,
                                    void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Row N3: the output stage right after the sampler
+ *   range image -> xyz point cloud     LiDARGen/visualization.py:12-43 (visualize_tensor, numeric part)
+ *   L1 depth / intensity error sums    MeasureResults/QuantifyingNotebookSynthesis_Line.ipynb, cell 1
+ * ---------------------------------------------------------------------------------------- */
+size_t sdpc_points_workspace_bytes(int n_views, int height, int width);
+/* image: float32 [V,2,H,W] (device; channel 0 = log-range r, channel 1 = intensity).  depth = 2^(6 r) - 1 in float32;
+ * a pixel yields a point iff 0.5 < depth < 63 (visualization.py:41).  cos_yaw / sin_yaw [W] and cos_pitch / sin_pitch [H]
+ * are float64 device tables of the reference's yaw / pitch grid (visualization.py:30-33).  Outputs (device): xyz float64
+ * [V, H*W, 3], the first n_points[v] rows of view v valid and in row-major pixel order (= pts[mask, :]); intensity
+ * float32 [V, H*W] and pixel int32 [V, H*W] (source pixel of every point) are nullable. */
+int sdpc_range_image_to_points(const float* image, int n_views, int height, int width, const double* cos_yaw,
+                               const double* sin_yaw, const double* cos_pitch, const double* sin_pitch, double* xyz,
+                               float* intensity, int* pixel, int* n_points, void* workspace, size_t workspace_bytes,
+                               void* stream);
+/* pred, gt, input: float32 [V,2,H,W] (device).  out: float64 [V,8] (device) =
+ *   { sum|d_pred - d_gt| over all pixels, sum|i_pred - i_gt| over all pixels, the same two over the input pixels,
+ *     sum d_pred over the input pixels, #pixels, #input pixels, 0 }   with d = 2^(6 r) - 1 and
+ *   input pixel = (input_r > 0.001) & (d_gt < 63)   (notebook: inputMask, distanceError, intensityError, ...Input). */
+int sdpc_depth_intensity_errors(const float* pred, const float* gt, const float* input, int n_views, int height, int width,
+                                double* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

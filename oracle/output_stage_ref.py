@@ -1,0 +1,55 @@
+"""ORACLE (test infrastructure, never imported by the product): CPU restatement of the reference's output stage, row N3.
+
+* `points_ref` follows LiDARGen/visualization.py:14-43 statement by statement (numpy, same dtypes); the open3d / cv2 /
+  matplotlib lines (:18, :36, :44-62) need libraries that are absent here and only render.  Pinned: tests/golden/
+  make_golden_n3.py executes the reference's own statements (read from /root/reference at generation time) and the
+  committed fixture is compared with this restatement in tests/test_n3_output_stage.py.
+* `error_sums_ref` follows cell 1 of MeasureResults/QuantifyingNotebookSynthesis_Line.ipynb (GTdistance / InputDist
+  un-log, `inputMask`, the `distanceError` ... `totalDistanceInput` sums with `mask = np.ones_like(mask)`).  The
+  notebook reads files of a finished run and cannot be executed here: PARITY UNPINNED for this function.
+"""
+import numpy as np
+
+
+def points_ref(image):
+    image = np.asarray(image)
+    lidar_range = image[0]
+    depth_range = np.exp2(lidar_range * 6) - 1                      # visualization.py:15
+    lidar_intensity = image[1]
+    fov_up = 3.0 / 180.0 * np.pi                                    # :21-25
+    fov_down = -25.0 / 180.0 * np.pi
+    fov = abs(fov_down) + abs(fov_up)
+    W, H = 1024.0, 64.0
+    x, y = np.meshgrid(np.arange(0, W), np.arange(0, H))            # :28-30
+    x *= 1 / W
+    y *= 1 / H
+    yaw = (np.pi * (x * 2 - 1)).flatten()                           # :31-34
+    pitch = ((1.0 - y) * fov - abs(fov_down)).flatten()
+    depth = depth_range.flatten()
+    pts = np.zeros((len(yaw), 3))
+    pts[:, 0] = np.cos(yaw) * np.cos(pitch) * depth                 # :37-40
+    pts[:, 1] = -np.sin(yaw) * np.cos(pitch) * depth
+    pts[:, 2] = np.sin(pitch) * depth
+    mask = np.logical_and(depth > 0.5, depth < 63.0)                # :43
+    return pts[mask, :], lidar_intensity.flatten()[mask], mask
+
+
+def error_sums_ref(pred, gt, inp):
+    """per-view dict of the notebook's sums; inputs [V,2,H,W] float32."""
+    pred, gt, inp = (np.asarray(a, dtype=np.float32) for a in (pred, gt, inp))
+    V = pred.shape[0]
+    GTdistance = np.power(2, gt[:, 0] * 6) - 1
+    inputMask = np.logical_and(inp[:, 0] > 0.001, GTdistance < 63)
+    mask = np.ones_like(inputMask)
+    distance = np.power(2, pred[:, 0] * 6) - 1
+    out = {k: np.zeros(V) for k in ("depth_l1", "intensity_l1", "depth_l1_input", "intensity_l1_input", "depth_sum_input",
+                                    "pixels", "input_pixels")}
+    for s in range(V):
+        out["depth_l1"][s] = np.sum(np.absolute(distance[s][mask[s]] - GTdistance[s][mask[s]]))
+        out["intensity_l1"][s] = np.sum(np.absolute(pred[s, 1][mask[s]] - gt[s, 1][mask[s]]))
+        out["depth_l1_input"][s] = np.sum(np.absolute(distance[s][inputMask[s]] - GTdistance[s][inputMask[s]]))
+        out["intensity_l1_input"][s] = np.sum(np.absolute(pred[s, 1][inputMask[s]] - gt[s, 1][inputMask[s]]))
+        out["depth_sum_input"][s] = np.sum(distance[s][inputMask[s]])
+        out["pixels"][s] = np.sum(mask[s])
+        out["input_pixels"][s] = np.sum(inputMask[s])
+    return out

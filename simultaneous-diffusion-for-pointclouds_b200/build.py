@@ -19,6 +19,7 @@ UNITS = [
     # reference evaluates every op with its own rounding: no FMA contraction (crossview_core.h)
     ("crossview.cu", ["-fmad=false"]),
     ("lidar_projection.cu", ["-fmad=false"]),
+    ("output_stage.cu", ["-fmad=false"]),
     ("conv_umma.cu", []),
     ("scorenet.cu", []),
 ]

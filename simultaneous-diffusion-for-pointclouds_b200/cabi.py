@@ -75,6 +75,9 @@ SYMBOLS = [
     ("sdpc_langevin_reproject_step", _I, [C.POINTER(StepParams), C.POINTER(StepBuffers), _P, _SZ, _P]),
     ("sdpc_projection_workspace_bytes", _SZ, [_I, _I]),
     ("sdpc_pointcloud_to_range_image", _I, [C.POINTER(ProjectionParams), _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    ("sdpc_points_workspace_bytes", _SZ, [_I, _I, _I]),
+    ("sdpc_range_image_to_points", _I, [_P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    ("sdpc_depth_intensity_errors", _I, [_P, _P, _P, _I, _I, _I, _P, _P]),
     ("sdpc_langevin_reproject_step_host", _I, [C.POINTER(StepParams), C.POINTER(StepBuffers), _P, _P, _P, _P, _P, _SZ, _P]),
 ]
 
