@@ -242,9 +242,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             for (int j = 0; j < 32; ++j) v[j] += res[j];
           }
           if (e.out_raw) {
-            float* op = e.out_raw + raw0;
+            if (e.raw_bf16) {
+              __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(e.out_raw) + raw0;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) op[j * kCout] = v[j];
+              for (int j = 0; j < 32; ++j) op[j * kCout] = __float2bfloat16_rn(v[j]);
+            } else {
+              float* op = e.out_raw + raw0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) op[j * kCout] = v[j];
+            }
           }
           if (e.stats) {
 #pragma unroll
@@ -345,9 +351,18 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             for (int it = 0; it < 8; ++it) { v[it].x += res[it].x; v[it].y += res[it].y; v[it].z += res[it].z; v[it].w += res[it].w; }
           }
           if (e.out_raw) {
-            float* op = e.out_raw + raw0 + ch;
+            if (e.raw_bf16) {
+              __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(e.out_raw) + raw0 + ch;
 #pragma unroll
-            for (int it = 0; it < 8; ++it) *reinterpret_cast<float4*>(op + it * 4 * kCout) = v[it];
+              for (int it = 0; it < 8; ++it) {
+                const float a4[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
+                store_op4<__nv_bfloat16>(op + it * 4 * kCout, a4, false, 0);
+              }
+            } else {
+              float* op = e.out_raw + raw0 + ch;
+#pragma unroll
+              for (int it = 0; it < 8; ++it) *reinterpret_cast<float4*>(op + it * 4 * kCout) = v[it];
+            }
           }
           if (e.stats) {
 #pragma unroll

@@ -234,9 +234,9 @@ __device__ __forceinline__ void store_op8<__nv_bfloat16>(__nv_bfloat16* dst, con
 // One thread: 8 channels x kOpPix consecutive pixels of a row (all loads issued before use).  With
 // HALO_ZERO the halo is not written here: the buffer's border is cleared by zero_halo_kernel.
 constexpr int kOpPix = 4;
-template <typename T, int MINB>
+template <typename T, int MINB, typename TIn = float>
 __global__ void __launch_bounds__(256, MINB)
-to_operand_kernel(const float* __restrict__ in, const float* __restrict__ coef, T* __restrict__ out, int N, int H,
+to_operand_kernel(const TIn* __restrict__ in, const float* __restrict__ coef, T* __restrict__ out, int N, int H,
                   int W, int C, int P, int mode, int halo, int tf32, size_t lo_off) {
   const int C8 = C / 8, WS = W / kOpPix;
   const size_t total = (size_t)N * H * WS * C8;
@@ -248,12 +248,27 @@ to_operand_kernel(const float* __restrict__ in, const float* __restrict__ coef, 
   const int h = (int)(t % H);
   const int n = (int)(t / H);
   const int Hp = H + 2 * P, Wp = W + 2 * P;
-  const float* src = in + (((size_t)n * H + h) * W + w0) * C + c8 * 8;
+  const TIn* src = in + (((size_t)n * H + h) * W + w0) * C + c8 * 8;
   float4 a[kOpPix], b[kOpPix];
+  if constexpr (sizeof(TIn) == 2) {                            // bf16 input (conv1 outputs of the plain bf16 arm)
+    uint4 q[kOpPix];
 #pragma unroll
-  for (int j = 0; j < kOpPix; ++j) {
-    a[j] = *reinterpret_cast<const float4*>(src + (size_t)j * C);
-    b[j] = *reinterpret_cast<const float4*>(src + (size_t)j * C + 4);
+    for (int j = 0; j < kOpPix; ++j) q[j] = *reinterpret_cast<const uint4*>(src + (size_t)j * C);
+#pragma unroll
+    for (int j = 0; j < kOpPix; ++j) {
+      const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&q[j].x));
+      const float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&q[j].y));
+      const float2 f2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&q[j].z));
+      const float2 f3 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&q[j].w));
+      a[j] = make_float4(f0.x, f0.y, f1.x, f1.y);
+      b[j] = make_float4(f2.x, f2.y, f3.x, f3.y);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < kOpPix; ++j) {
+      a[j] = *reinterpret_cast<const float4*>(src + (size_t)j * C);
+      b[j] = *reinterpret_cast<const float4*>(src + (size_t)j * C + 4);
+    }
   }
   float mu[8], ga[8], be[8];
   if (mode == OP_NORM_ELU) {

@@ -25,7 +25,8 @@ struct ConvGeom {
 struct EpiParams {
   const float* bias;      // [Cout] or null
   const float* residual;  // fp32 raw [N,H,W,Cout] added after bias, or null
-  float* out_raw;         // fp32 raw, value after bias + residual, or null
+  float* out_raw;         // raw layout (no halo), value after bias + residual, or null; fp32 unless raw_bf16
+  int raw_bf16;           // 1: out_raw holds bf16 (tensors only a normalisation pass reads; statistics stay fp32)
   void* out_acc;          // raw layout (no halo), value after bias only (CRP path: only a max-pool reads it), or null;
   int acc_bf16;           // 1: out_acc holds bf16 (max-pooling commutes with the monotone rounding), else fp32
   void* out_op;           // operand (T) with halo `op_pad`, value = act(after bias+residual), or null

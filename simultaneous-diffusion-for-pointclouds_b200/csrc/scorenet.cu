@@ -213,6 +213,9 @@ struct Builder {
     return b;
   }
   Buf raw(int H, int W, int C) { return alloc(N, H, W, C, 0, 4); }
+  // A tensor that only an InstanceNorm++ -> ELU -> operand pass reads (conv1 of a residual block): the plain bf16 arm
+  // stores it in bf16 (its statistics come from the fp32 accumulators in the epilogue), halving that write and re-read.
+  Buf raw_h(int H, int W, int C) { return (h->cfg.precision == SDPC_PREC_BF16 && !getenv("SDPC_RAW_FP32")) ? alloc(N, H, W, C, 0, 2) : raw(H, W, C); }
   Buf operand(int H, int W, int C, int pad) {
     if (!h->x3()) return alloc(N, H, W, C, pad, h->elem_bytes());
     Buf b = alloc(2 * N, H, W, C, pad, 2);                 // hi planes of all views, then lo planes
@@ -264,6 +267,7 @@ struct Builder {
     const size_t ticket_off = stats_cursor;                 // per-image ticket counters of the fused reducer (zeroed with the stats area)
     if (fused) stats_cursor += al((size_t)N * sizeof(unsigned int));
     if (dry()) return r;
+    if (!fused && x.elem != 4) { status = set_error(SDPC_ERR_STATE, "norm %s: a bf16 tensor needs statistics from its producer", pre.c_str()); return r; }
     const float* in = (const float*)x.ptr;
     const int HW = x.H * x.W, C = x.C;
     int chunks = HW / 512;
@@ -306,10 +310,10 @@ struct Builder {
     const int nz = lo_off ? 2 * n : n;                      // both planes get the zero border
     const size_t border = (size_t)nz * ((size_t)(H + 2 * P) * (W + 2 * P) - (size_t)H * W) * (C / 8);
     const bool zero = halo == HALO_ZERO && P > 0;
-    const bool minb3 = getenv("SDPC_TOOP_MINB3") != nullptr;
+    const bool in_h = x.elem == 2;                           // bf16 raw input (see raw_h())
     push([=](cudaStream_t s, const float*, const int64_t*, float*) -> int {
       if (zero) zero_halo_kernel<T><<<blocks(border), 256, 0, s>>>(o, nz, H, W, C, P);
-      if (minb3) to_operand_kernel<T, 3><<<blocks(total), 256, 0, s>>>(in, coef, o, n, H, W, C, P, mode, halo, tf32, lo_off);
+      if (in_h) to_operand_kernel<T, 2, __nv_bfloat16><<<blocks(total), 256, 0, s>>>((const __nv_bfloat16*)in, coef, o, n, H, W, C, P, mode, halo, tf32, lo_off);
       else to_operand_kernel<T, 2><<<blocks(total), 256, 0, s>>>(in, coef, o, n, H, W, C, P, mode, halo, tf32, lo_off);
       SDPC_CUDA(cudaGetLastError());
       return SDPC_OK;
@@ -387,6 +391,7 @@ struct Builder {
     e.bias = use_bias ? cw.bias : nullptr;
     e.residual = residual ? (const float*)residual->ptr : nullptr;
     e.out_raw = out_raw ? (float*)out_raw->ptr : nullptr;
+    e.raw_bf16 = (out_raw && out_raw->elem == 2) ? 1 : 0;
     e.out_acc = out_acc ? (void*)out_acc->ptr : nullptr;
     e.acc_bf16 = (out_acc && out_acc->elem == 2) ? 1 : 0;
     e.out_op = out_op ? out_op->ptr : nullptr;
@@ -478,7 +483,7 @@ struct Builder {
       release(xs);
     }
     Buf a1 = norm_elu_operand(x, pre + ".normalize1", d, HALO_CIRC, false, x_stats);
-    Buf t1 = raw(x.H, x.W, h->convs.at(pre + ".conv1.weight").Cout);
+    Buf t1 = raw_h(x.H, x.W, h->convs.at(pre + ".conv1.weight").Cout);
     StatsRef t1_stats;
     conv(a1, pre + ".conv1.weight", d, true, nullptr, &t1, nullptr, nullptr, false, &t1_stats);
     release(a1);
