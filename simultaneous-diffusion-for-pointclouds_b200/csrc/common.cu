@@ -1,4 +1,5 @@
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.h"
@@ -12,6 +13,10 @@ int set_error(int code, const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
   return code;
+}
+bool pdl_enabled() {
+  static const bool on = getenv("SDPC_PDL") != nullptr;   // opt-in: measured neutral to 2 % slower
+  return on;
 }
 }  // namespace sdpc
 

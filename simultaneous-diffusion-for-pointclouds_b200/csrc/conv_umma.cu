@@ -89,6 +89,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Everything above (barriers, descriptor prefetch, TMEM allocation) may overlap the previous kernel's tail; its
+  // results (this layer's input, residual, the buffers this layer overwrites) are only touched after this point.
+  pdl_sync();
 
   const int k_chunks = g.Cin / kBK;
   const int k_iters = g.passes * g.taps * k_chunks;
@@ -478,7 +481,7 @@ static int launch_t(const UmmaConvLaunch& L, cudaStream_t stream) {
     attr_set = true;
   }
   int grid = L.geom.num_tiles < L.num_sms ? L.geom.num_tiles : L.num_sms;
-  conv_umma_kernel<T, N_TILE, SWAP><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(L.tmap_a, L.tmap_b, L.tmap_a_lo, L.tmap_b_lo, L.geom, L.epi);
+  SDPC_CUDA(launch_k(conv_umma_kernel<T, N_TILE, SWAP>, dim3(grid), dim3(kThreads), Cfg::kSmemBytes, stream, L.tmap_a, L.tmap_b, L.tmap_a_lo, L.tmap_b_lo, L.geom, L.epi));
   SDPC_CUDA(cudaGetLastError());
   return SDPC_OK;
 }

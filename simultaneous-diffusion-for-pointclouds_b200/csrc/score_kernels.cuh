@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "common.h"
 #include "score_types.cuh"
 
 namespace sdpc {
@@ -25,6 +26,7 @@ template <int NGF>
 __global__ void __launch_bounds__(NGF)
 begin_conv_kernel(const float* __restrict__ x, const float* __restrict__ wgt, const float* __restrict__ bias,
                   float* __restrict__ out, float2* __restrict__ stat_parts, int N, int H, int W) {
+  pdl_sync();
   // one thread per output channel (its 36 weights live in registers), 64 pixels of one row per block;
   // the 36-value input patches are staged k-major in shared memory and read as broadcast float4s.
   // stat_parts (or null): [N][H * W/64][NGF] (sum, sum of squares) of the block's 64 outputs per channel, the
@@ -87,6 +89,7 @@ begin_conv_kernel(const float* __restrict__ x, const float* __restrict__ wgt, co
 // per-(n,c) sum and sum of squares over H*W; fp32 partials per thread, fp64 across threads.
 __global__ void __launch_bounds__(256)
 stats_kernel(const float* __restrict__ in, double* __restrict__ stats, int HW, int C, int pix_per_block) {
+  pdl_sync();
   extern __shared__ double sred[];                  // [groups][C][2]
   const int lanes_c = C / 4;
   const int groups = blockDim.x / lanes_c;
@@ -147,6 +150,7 @@ __device__ __forceinline__ void norm_coefficients(double S, double Q, const floa
 __global__ void norm_finalize_kernel(const double* __restrict__ stats, const float* __restrict__ alpha,
                                      const float* __restrict__ gamma, const float* __restrict__ beta,
                                      float* __restrict__ coef, int HW, int C) {
+  pdl_sync();
   const int n = blockIdx.x, c = threadIdx.x;
   norm_coefficients(stats[((size_t)n * C + c) * 2], stats[((size_t)n * C + c) * 2 + 1], alpha, gamma, beta, coef, HW, C, n, c,
                     true);
@@ -161,6 +165,7 @@ stats_reduce_finalize_kernel(const float* __restrict__ parts, double* __restrict
                              const float* __restrict__ alpha, const float* __restrict__ gamma,
                              const float* __restrict__ beta, float* __restrict__ coef, int HW,
                              unsigned int* __restrict__ tickets) {
+  pdl_sync();
   __shared__ double red[8][8][2];
   __shared__ bool s_last;
   const int cl = threadIdx.x & 7, grp = threadIdx.x >> 3;
@@ -238,6 +243,7 @@ template <typename T, int MINB, typename TIn = float>
 __global__ void __launch_bounds__(256, MINB)
 to_operand_kernel(const TIn* __restrict__ in, const float* __restrict__ coef, T* __restrict__ out, int N, int H,
                   int W, int C, int P, int mode, int halo, int tf32, size_t lo_off) {
+  pdl_sync();
   const int C8 = C / 8, WS = W / kOpPix;
   const size_t total = (size_t)N * H * WS * C8;
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -309,6 +315,7 @@ to_operand_kernel(const TIn* __restrict__ in, const float* __restrict__ coef, T*
 template <typename T>
 __global__ void __launch_bounds__(256)
 zero_halo_kernel(T* __restrict__ out, int N, int H, int W, int C, int P) {
+  pdl_sync();
   const int Hp = H + 2 * P, Wp = W + 2 * P, C8 = C / 8;
   const int border = Hp * Wp - H * W;                 // border pixels per image
   const size_t total = (size_t)N * border * C8;
@@ -338,6 +345,7 @@ template <typename T>
 __global__ void __launch_bounds__(kPoolThreads)
 maxpool5_kernel(const float* __restrict__ in, float* __restrict__ x0_out, T* __restrict__ out, int N, int H, int W,
                 int C, int P, int elu_in, int tf32, size_t lo_off) {
+  pdl_sync();
   // Separable 5x5 max (window clipped at the image border = MaxPool2d's -inf padding).
   //   phase A: a thread owns one input column (of the 32+4) x 4 channels, loads its 8+4 rows straight from global
   //            memory (independent 128-bit loads, 8 lanes = one pixel's 128 contiguous bytes) and keeps a running
@@ -438,6 +446,7 @@ template <typename TIn>
 __global__ void __launch_bounds__(kPoolHThreads)
 maxpool5_h2_kernel(const TIn* __restrict__ in, float* __restrict__ x0_out, __nv_bfloat16* __restrict__ out, int N, int H,
                    int W, int C, int P, int elu_in) {
+  pdl_sync();
   __shared__ uint4 tv[kPoolTH][kPoolTW + 4][kPoolHCB / 8];       // 36 KB
   const int CBn = C / kPoolHCB, TWn = W / kPoolTW, THn = H / kPoolTH;
   int b = blockIdx.x;
@@ -519,6 +528,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 meanpool_kernel(const float* __restrict__ in, const float* __restrict__ add, T* __restrict__ out_op,
                 float* __restrict__ out_raw, int N, int H, int W, int C, int tf32, size_t lo_off) {
+  pdl_sync();
   const int Ho = H / 2, Wo = W / 2, C4 = C / 4;
   const size_t total = (size_t)N * Ho * Wo * C4;
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -548,6 +558,7 @@ constexpr int kMpIter = 16;
 __global__ void __launch_bounds__(256)
 meanpool_add_stats_kernel(const float* __restrict__ in, const float* __restrict__ add, float* __restrict__ out_raw,
                           float2* __restrict__ stat_parts, int N, int H, int W, int C) {
+  pdl_sync();
   __shared__ float4 ssum[256], ssq[256];
   const int Ho = H / 2, Wo = W / 2, C4 = C / 4;
   const int c4 = threadIdx.x % C4;
@@ -585,6 +596,7 @@ meanpool_add_stats_kernel(const float* __restrict__ in, const float* __restrict_
 __global__ void __launch_bounds__(256)
 upsample_add_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int N, int H,
                     int W, int C, int h, int w) {
+  pdl_sync();
   const int C4 = C / 4;
   const size_t total = (size_t)N * H * W * C4;
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -615,66 +627,9 @@ upsample_add_kernel(const float* __restrict__ a, const float* __restrict__ b, fl
 }
 
 // ------------------------------------------------------------------------------------------
-// end_conv: ngf->2, 3x3 zero-padded, then / sigmas[y] (ncsnv2.py:512-516).  fp32 throughout.
-// One warp per output pixel; the operand has a zero halo of 1.
+// end_conv: ngf->2, 3x3 zero-padded, then / sigmas[y] (ncsnv2.py:512-516), fp32 throughout, fused with the final
+// normalisation
 // ------------------------------------------------------------------------------------------
-template <int NGF>
-__global__ void __launch_bounds__(256)
-end_conv_kernel(const float* __restrict__ op, const float* __restrict__ wgt, const float* __restrict__ bias,
-                const float* __restrict__ sigmas, const int64_t* __restrict__ labels, float* __restrict__ out, int N,
-                int H, int W) {
-  // one warp: 8 consecutive pixels of a row; a lane owns 4 input channels.  The 3 x 10 input columns
-  // are loaded once and reused by the 9 taps of the 8 outputs.
-  static_assert(NGF == 128, "one float4 per lane");
-  __shared__ __align__(16) float sw[2][9][NGF];
-  for (int i = threadIdx.x; i < 2 * 9 * NGF; i += blockDim.x) {
-    const int co = i / (9 * NGF), r = i % (9 * NGF), tap = r / NGF, ci = r % NGF;
-    sw[co][tap][ci] = wgt[((size_t)co * NGF + ci) * 9 + tap];
-  }
-  __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const size_t strip = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int W8 = W / 8;
-  if (strip >= (size_t)N * H * W8) return;
-  const int w0 = (int)(strip % W8) * 8, h = (int)((strip / W8) % H), n = (int)(strip / ((size_t)W8 * H));
-  const int Hp = H + 2, Wp = W + 2;
-  float a0[8], a1[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) a0[i] = a1[i] = 0.0f;
-#pragma unroll
-  for (int kh = 0; kh < 3; ++kh) {
-    float4 col[10];
-    const float* row = op + (((size_t)n * Hp + h + kh) * Wp + w0) * NGF + lane * 4;
-#pragma unroll
-    for (int j = 0; j < 10; ++j) col[j] = *reinterpret_cast<const float4*>(row + (size_t)j * NGF);
-#pragma unroll
-    for (int kw = 0; kw < 3; ++kw) {
-      const float4 w0v = *reinterpret_cast<const float4*>(&sw[0][kh * 3 + kw][lane * 4]);
-      const float4 w1v = *reinterpret_cast<const float4*>(&sw[1][kh * 3 + kw][lane * 4]);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float4 v = col[i + kw];
-        a0[i] += v.x * w0v.x + v.y * w0v.y + v.z * w0v.z + v.w * w0v.w;
-        a1[i] += v.x * w1v.x + v.y * w1v.y + v.z * w1v.z + v.w * w1v.w;
-      }
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-    for (int o = 16; o > 0; o >>= 1) {
-      a0[i] += __shfl_xor_sync(0xffffffffu, a0[i], o);
-      a1[i] += __shfl_xor_sync(0xffffffffu, a1[i], o);
-    }
-  if (lane < 8) {
-    const float s = sigmas[labels[n]];
-    float v0 = a0[0], v1 = a1[0];
-#pragma unroll
-    for (int i = 1; i < 8; ++i) if (lane == i) { v0 = a0[i]; v1 = a1[i]; }
-    out[(((size_t)n * 2 + 0) * H + h) * W + w0 + lane] = (v0 + bias[0]) / s;
-    out[(((size_t)n * 2 + 1) * H + h) * W + w0 + lane] = (v1 + bias[1]) / s;
-  }
-}
-
 // Fused tail of the network: normalizer (InstanceNorm++) -> ELU -> end_conv -> / sigmas[y] (ncsnv2.py:509-516)
 // reading the raw fp32 trunk once, instead of materialising the activated tensor (a 268 MB write and a 3x re-read).
 // One warp owns an 8-pixel-wide, kEndRows-tall strip and walks DOWN its input rows; a lane owns 4 input channels.
@@ -701,6 +656,7 @@ __global__ void __launch_bounds__(kEndThreads, 4)
 end_conv_norm_kernel(const float* __restrict__ raw, const float* __restrict__ coef, const float* __restrict__ wgt,
                      const float* __restrict__ bias, const float* __restrict__ sigmas,
                      const int64_t* __restrict__ labels, float* __restrict__ out, int N, int H, int W, int fast_elu) {
+  pdl_sync();
   static_assert(NGF == 128, "one float4 per lane");
   extern __shared__ __align__(16) uint8_t end_smem[];
   float (*sw)[9][NGF] = reinterpret_cast<float (*)[9][NGF]>(end_smem);                       // [2][9][NGF]
@@ -865,6 +821,7 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, T* __restrict_
 __global__ void __launch_bounds__(256)
 conv_simt_kernel(const float* __restrict__ in, const float* __restrict__ wgt /*[tap][Cin][Cout]*/, const ConvGeom g,
                  const EpiParams e) {
+  pdl_sync();
   __shared__ float As[16][64 + 4];
   __shared__ float Bs[16][64];
   const int bw = g.W < 64 ? g.W : 64, bh = 64 / bw;

@@ -286,11 +286,11 @@ struct Builder {
     const int n = N;
     push([=](cudaStream_t s, const float*, const int64_t*, float*) -> int {
       if (fused) {
-        stats_reduce_finalize_kernel<<<dim3(C / 8, n), 256, 0, s>>>(parts, stats, ppv, C, al_, ga, be, coef, HW, tickets);
+        SDPC_CUDA(launch_k(stats_reduce_finalize_kernel, dim3(dim3(C / 8, n)), dim3(256), 0, s, parts, stats, ppv, C, al_, ga, be, coef, HW, tickets));
       } else {
-        stats_kernel<<<dim3(chunks, n), 256, smem, s>>>(in, stats, HW, C, ppb);
+        SDPC_CUDA(launch_k(stats_kernel, dim3(dim3(chunks, n)), dim3(256), smem, s, in, stats, HW, C, ppb));
         SDPC_CUDA(cudaGetLastError());
-        norm_finalize_kernel<<<n, C, 0, s>>>(stats, al_, ga, be, coef, HW, C);
+        SDPC_CUDA(launch_k(norm_finalize_kernel, dim3(n), dim3(C), 0, s, stats, al_, ga, be, coef, HW, C));
       }
       SDPC_CUDA(cudaGetLastError());
       return SDPC_OK;
@@ -312,9 +312,9 @@ struct Builder {
     const bool zero = halo == HALO_ZERO && P > 0;
     const bool in_h = x.elem == 2;                           // bf16 raw input (see raw_h())
     push([=](cudaStream_t s, const float*, const int64_t*, float*) -> int {
-      if (zero) zero_halo_kernel<T><<<blocks(border), 256, 0, s>>>(o, nz, H, W, C, P);
-      if (in_h) to_operand_kernel<T, 2, __nv_bfloat16><<<blocks(total), 256, 0, s>>>((const __nv_bfloat16*)in, coef, o, n, H, W, C, P, mode, halo, tf32, lo_off);
-      else to_operand_kernel<T, 2><<<blocks(total), 256, 0, s>>>(in, coef, o, n, H, W, C, P, mode, halo, tf32, lo_off);
+      if (zero) SDPC_CUDA(launch_k(zero_halo_kernel<T>, dim3(blocks(border)), dim3(256), 0, s, o, nz, H, W, C, P));
+      if (in_h) SDPC_CUDA(launch_k(to_operand_kernel<T, 2, __nv_bfloat16>, dim3(blocks(total)), dim3(256), 0, s, (const __nv_bfloat16*)in, coef, o, n, H, W, C, P, mode, halo, tf32, lo_off));
+      else SDPC_CUDA(launch_k(to_operand_kernel<T, 2>, dim3(blocks(total)), dim3(256), 0, s, in, coef, o, n, H, W, C, P, mode, halo, tf32, lo_off));
       SDPC_CUDA(cudaGetLastError());
       return SDPC_OK;
     }, zero ? 2 : 1);
@@ -343,8 +343,8 @@ struct Builder {
     if (pool_h2()) {
       const unsigned nblk = (unsigned)((size_t)n * (H / kPoolTH) * (W / kPoolTW) * (C / kPoolHCB));
       push([=](cudaStream_t s, const float*, const int64_t*, float*) -> int {
-        if (in_elem == 2) maxpool5_h2_kernel<__nv_bfloat16><<<nblk, kPoolHThreads, 0, s>>>((const __nv_bfloat16*)in, x0, (__nv_bfloat16*)o, n, H, W, C, 1, ei);
-        else maxpool5_h2_kernel<float><<<nblk, kPoolHThreads, 0, s>>>(in, x0, (__nv_bfloat16*)o, n, H, W, C, 1, ei);
+        if (in_elem == 2) SDPC_CUDA(launch_k(maxpool5_h2_kernel<__nv_bfloat16>, dim3(nblk), dim3(kPoolHThreads), 0, s, (const __nv_bfloat16*)in, x0, (__nv_bfloat16*)o, n, H, W, C, 1, ei));
+        else SDPC_CUDA(launch_k(maxpool5_h2_kernel<float>, dim3(nblk), dim3(kPoolHThreads), 0, s, in, x0, (__nv_bfloat16*)o, n, H, W, C, 1, ei));
         SDPC_CUDA(cudaGetLastError());
         return SDPC_OK;
       });
@@ -353,8 +353,8 @@ struct Builder {
     if (in_elem != 4) { status = set_error(SDPC_ERR_STATE, "maxpool: fp32 input expected"); return out; }
     const unsigned nblk = (unsigned)((size_t)n * (H / kPoolTH) * (W / kPoolTW) * (C / kPoolCB));
     push([=](cudaStream_t s, const float*, const int64_t*, float*) -> int {
-      if (elem == 2) maxpool5_kernel<__nv_bfloat16><<<nblk, kPoolThreads, 0, s>>>(in, x0, (__nv_bfloat16*)o, n, H, W, C, 1, ei, tf32, lo_off);
-      else maxpool5_kernel<float><<<nblk, kPoolThreads, 0, s>>>(in, x0, (float*)o, n, H, W, C, 1, ei, tf32, lo_off);
+      if (elem == 2) SDPC_CUDA(launch_k(maxpool5_kernel<__nv_bfloat16>, dim3(nblk), dim3(kPoolThreads), 0, s, in, x0, (__nv_bfloat16*)o, n, H, W, C, 1, ei, tf32, lo_off));
+      else SDPC_CUDA(launch_k(maxpool5_kernel<float>, dim3(nblk), dim3(kPoolThreads), 0, s, in, x0, (float*)o, n, H, W, C, 1, ei, tf32, lo_off));
       SDPC_CUDA(cudaGetLastError());
       return SDPC_OK;
     });
@@ -419,7 +419,7 @@ struct Builder {
       if (g.W % bw || g.H % bh || g.Cout % 64 || g.Cin % 16) { status = set_error(SDPC_ERR_UNSUPPORTED, "conv_simt: shape"); return; }
       dim3 grid(N * (g.W / bw) * (g.H / bh), g.Cout / 64);
       push([=](cudaStream_t s, const float*, const int64_t*, float*) -> int {
-        conv_simt_kernel<<<grid, 256, 0, s>>>(inp, w, g, e);
+        SDPC_CUDA(launch_k(conv_simt_kernel, dim3(grid), dim3(256), 0, s, inp, w, g, e));
         SDPC_CUDA(cudaGetLastError());
         return SDPC_OK;
       });
@@ -538,15 +538,15 @@ struct Builder {
       float2* sp = (float2*)(base + plan->parts_off + stats_out->off);
       const unsigned nblk = (unsigned)(total / ((size_t)kMpIter * 256));
       push([=](cudaStream_t s, const float*, const int64_t*, float*) -> int {
-        meanpool_add_stats_kernel<<<nblk, 256, 0, s>>>(in, ad, orr, sp, n, H, W, C);
+        SDPC_CUDA(launch_k(meanpool_add_stats_kernel, dim3(nblk), dim3(256), 0, s, in, ad, orr, sp, n, H, W, C));
         SDPC_CUDA(cudaGetLastError());
         return SDPC_OK;
       });
       return;
     }
     push([=](cudaStream_t s, const float*, const int64_t*, float*) -> int {
-      if (elem == 2) meanpool_kernel<__nv_bfloat16><<<blocks(total), 256, 0, s>>>(in, ad, (__nv_bfloat16*)oo, orr, n, H, W, C, tf32, lo_off);
-      else meanpool_kernel<float><<<blocks(total), 256, 0, s>>>(in, ad, (float*)oo, orr, n, H, W, C, tf32, lo_off);
+      if (elem == 2) SDPC_CUDA(launch_k(meanpool_kernel<__nv_bfloat16>, dim3(blocks(total)), dim3(256), 0, s, in, ad, (__nv_bfloat16*)oo, orr, n, H, W, C, tf32, lo_off));
+      else SDPC_CUDA(launch_k(meanpool_kernel<float>, dim3(blocks(total)), dim3(256), 0, s, in, ad, (float*)oo, orr, n, H, W, C, tf32, lo_off));
       SDPC_CUDA(cudaGetLastError());
       return SDPC_OK;
     });
@@ -639,7 +639,7 @@ struct Builder {
           const int n = N, C = features, hh = ms[1].H, ww = ms[1].W;
           const size_t total = (size_t)n * outH * outW * (C / 4);
           push([=](cudaStream_t s, const float*, const int64_t*, float*) -> int {
-            upsample_add_kernel<<<blocks(total), 256, 0, s>>>(a, b, o, n, outH, outW, C, hh, ww);
+            SDPC_CUDA(launch_k(upsample_add_kernel, dim3(blocks(total)), dim3(256), 0, s, a, b, o, n, outH, outW, C, hh, ww));
             SDPC_CUDA(cudaGetLastError());
             return SDPC_OK;
           });
@@ -678,7 +678,7 @@ struct Builder {
       const float *wg = h->P("begin_conv.weight"), *bs = h->P("begin_conv.bias");
       const int n = N;
       push([=](cudaStream_t s, const float* x, const int64_t*, float*) -> int {
-        begin_conv_kernel<128><<<n * H * (W / 64), 128, 0, s>>>(x, wg, bs, o, sp, n, H, W);
+        SDPC_CUDA(launch_k(begin_conv_kernel<128>, dim3(n * H * (W / 64)), dim3(128), 0, s, x, wg, bs, o, sp, n, H, W));
         SDPC_CUDA(cudaGetLastError());
         return SDPC_OK;
       });
@@ -731,7 +731,7 @@ struct Builder {
         }
         const size_t strips = (size_t)n * (H / kEndRows) * (W / 8);
         const int wpb = kEndThreads / 32;
-        end_conv_norm_kernel<128><<<(unsigned)((strips + wpb - 1) / wpb), kEndThreads, kEndSmemBytes, s>>>(rw, cf, wg, bs, sg, labels, out, n, H, W, fast);
+        SDPC_CUDA(launch_k(end_conv_norm_kernel<128>, dim3((unsigned)((strips + wpb - 1) / wpb)), dim3(kEndThreads), kEndSmemBytes, s, rw, cf, wg, bs, sg, labels, out, n, H, W, fast));
         SDPC_CUDA(cudaGetLastError());
         return SDPC_OK;
       });
