@@ -45,11 +45,13 @@ struct UmmaCfg {
 };
 
 // SWAP = false: D[pixel (M=128), cout (N=Cout)]      = X_tile . W^T      (Cout = 256 layers)
-// SWAP = true : D[cout  (M=128), pixel (N=256)]      = W . X_tile^T      (Cout = 128 layers)
+// SWAP = true : D[cout  (M=128), pixel (N=256)]      = W . X_tile^T      (Cout = 128 layers; Cout = 256 layers as two
+//                                                                          128-channel halves, COUT = 256: same bytes
+//                                                                          through L2 per FLOP, cheaper epilogue)
 //   A 128x128 MMA reads (128+128) rows of operands per 128x128 MACs and is bound by shared-memory
 //   bandwidth; putting the weights on the M side lets a 128-output-channel layer run the same
 //   128x256 instruction shape as the 256-channel layers (256 pixels per tile on the N side).
-template <typename T, int N_TILE, bool SWAP>
+template <typename T, int N_TILE, bool SWAP, int COUT>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_a_lo, const __grid_constant__ CUtensorMap tmap_b_lo,
@@ -96,6 +98,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const int k_chunks = g.Cin / kBK;
   const int k_iters = g.passes * g.taps * k_chunks;
   const int tiles_per_img = g.tiles_w * g.tiles_h;
+  constexpr int kMH = SWAP ? COUT / kTileM : 1;          // swapped: tiles = pixel tiles x 128-channel halves
+  static_assert(SWAP ? (COUT == 128 || COUT == 256) : COUT == N_TILE, "unsupported channel count");
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -103,8 +107,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
-        const int n = tile / tiles_per_img;
-        const int rem = tile - n * tiles_per_img;
+        const int ptile = tile / kMH, mh = tile - ptile * kMH;   // pixel tile, 128-channel half of the weights (swapped)
+        const int n = ptile / tiles_per_img;
+        const int rem = ptile - n * tiles_per_img;
         const int h0 = (rem / g.tiles_w) * g.BH;
         const int w0 = (rem % g.tiles_w) * g.BW;
         // bf16x3 arm: three passes over K accumulate X_hi.W_hi + X_hi.W_lo + X_lo.W_hi into the same accumulator
@@ -121,7 +126,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               mbar_arrive_expect_tx(full_bar + stage, Cfg::kStageBytes);
               // activations and weights land in the M-side (128 rows) or N-side (N_TILE rows) slot
               tma_load_4d(SWAP ? sb : sa, ma, full_bar + stage, kc * kBK, w0 + g.in_pad + dx, h0 + g.in_pad + dy, n);
-              tma_load_3d(SWAP ? sa : sb, mb, full_bar + stage, kc * kBK, 0, tap);
+              tma_load_3d(SWAP ? sa : sb, mb, full_bar + stage, kc * kBK, mh * kTileM, tap);
               if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
             }
           }
@@ -168,7 +173,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     //  !SWAP  : row = pixel, columns = 32 channels; storing that directly would touch 32 different lines per
     //           instruction, so every 32x32 chunk is transposed through an XOR-swizzled shared-memory tile:
     //           8 consecutive lanes then cover one pixel's 128 contiguous bytes.
-    constexpr int kCout = SWAP ? kTileM : N_TILE;            // the host only launches this variant for that Cout
+    constexpr int kCout = COUT;                              // the host only launches this variant for that Cout
     const int quad = warp & 3;                               // TMEM lane quadrant this warp may read
     const int half = (warp - 2) >> 2;                        // 0: even chunks, 1: odd chunks
     float* stg = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes + kBarrierBytes) + (warp - 2) * kStgFloats;
@@ -182,26 +187,27 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++local) {
       const int ab = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
-      const int n = tile / tiles_per_img;
-      const int rem = tile - n * tiles_per_img;
+      const int ptile = tile / kMH, mh = tile - ptile * kMH;
+      const int n = ptile / tiles_per_img;
+      const int rem = ptile - n * tiles_per_img;
       const int h0 = (rem / g.tiles_w) * g.BH;
       const int w0 = (rem % g.tiles_w) * g.BW;
       // While the MMAs of this tile are still running, pull the residual rows of the tile into L2 so that the
       // epilogue's residual loads hit L2 instead of HBM (the 8 warps cover the tile's pixels x Cout floats).
       if (e.residual && e.prefetch_residual) {
         const int tile_px = g.BW * g.BH;
-        constexpr int lines_per_px = kCout / 32;                    // 128-byte lines per pixel
+        constexpr int lines_per_px = (SWAP ? kTileM : kCout) / 32;  // 128-byte lines per pixel (of this tile's channels)
         for (int i = (warp - 2) * 32 + lane; i < tile_px * lines_per_px; i += kEpiWarps * 32) {
           const int m = i / lines_per_px, l = i - m * lines_per_px;
           const int h = h0 + (m >> g.bw_shift), w = w0 + (m & (g.BW - 1));
-          const float* ptr = e.residual + (((size_t)n * g.H + h) * g.W + w) * kCout + l * 32;
+          const float* ptr = e.residual + (((size_t)n * g.H + h) * g.W + w) * kCout + mh * kTileM + l * 32;
           asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
         }
       }
       const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + ab * N_TILE;
 
       if constexpr (SWAP) {
-        const int ch = quad * 32 + lane;                     // this thread's output channel
+        const int ch = mh * kTileM + quad * 32 + lane;       // this thread's output channel
         const float bias = e.bias ? e.bias[ch] : 0.0f;
         float ssum = 0.0f, ssq = 0.0f;                       // InstanceNorm++ partial sums of this channel over the warp's pixels
         mbar_wait(acc_full + ab, acc_phase);
@@ -285,7 +291,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           }
         }
         if (e.stats)                                         // slot [tile][half][Cout][2], written exactly once
-          *reinterpret_cast<float2*>(e.stats + (((size_t)tile * 2 + half) * kCout + ch) * 2) = make_float2(ssum, ssq);
+          *reinterpret_cast<float2*>(e.stats + (((size_t)ptile * 2 + half) * kCout + ch) * 2) = make_float2(ssum, ssq);
       } else {
         // The quadrant's 32 pixels lie on one image row (BW >= 32): the lane's pixel `it` is (h, w + 4*it), so every
         // tensor offset is one per-tile base plus a compile-time multiple of kCout.  Warps whose pixels touch the
@@ -471,34 +477,48 @@ int make_tmap(CUtensorMap* out, void* base, int elem_bytes, int rank, const uint
   return SDPC_OK;
 }
 
-template <typename T, int N_TILE, bool SWAP>
+template <typename T, int N_TILE, bool SWAP, int COUT>
 static int launch_t(const UmmaConvLaunch& L, cudaStream_t stream) {
   using Cfg = UmmaCfg<N_TILE>;
   static bool attr_set = false;
   if (!attr_set) {
-    SDPC_CUDA(cudaFuncSetAttribute(conv_umma_kernel<T, N_TILE, SWAP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    SDPC_CUDA(cudaFuncSetAttribute(conv_umma_kernel<T, N_TILE, SWAP, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    Cfg::kSmemBytes));
     attr_set = true;
   }
   int grid = L.geom.num_tiles < L.num_sms ? L.geom.num_tiles : L.num_sms;
-  SDPC_CUDA(launch_k(conv_umma_kernel<T, N_TILE, SWAP>, dim3(grid), dim3(kThreads), Cfg::kSmemBytes, stream, L.tmap_a, L.tmap_b, L.tmap_a_lo, L.tmap_b_lo, L.geom, L.epi));
+  SDPC_CUDA(launch_k(conv_umma_kernel<T, N_TILE, SWAP, COUT>, dim3(grid), dim3(kThreads), Cfg::kSmemBytes, stream, L.tmap_a, L.tmap_b, L.tmap_a_lo, L.tmap_b_lo, L.geom, L.epi));
   SDPC_CUDA(cudaGetLastError());
   return SDPC_OK;
 }
 
+// Cout = 256 layers run swapped as two 128-channel halves unless SDPC_SWAP256=0 (A/B switch, read once)
+bool conv_umma_swap256() {
+  static const bool on = [] { const char* v = getenv("SDPC_SWAP256"); return !(v && v[0] == '0'); }();
+  return on;
+}
 // tile_pixels(Cout): pixels per tile the kernel variant for this Cout uses (the host builds the TMA box from it)
-int conv_umma_tile_pixels(int Cout) { return Cout == 128 ? 256 : 128; }
+int conv_umma_tile_pixels(int Cout) { return (Cout == 128 || conv_umma_swap256()) ? 256 : 128; }
+// partial-statistics slots a tile leaves per pixel tile (score_types.cuh, EpiParams::stats)
+int conv_umma_stats_parts(int Cout) { return (Cout == 128 || conv_umma_swap256()) ? 2 : 4; }
+// rows of the weight TMA box
+int conv_umma_weight_rows(int Cout) { return (Cout == 128 || conv_umma_swap256()) ? 128 : Cout; }
 
 int conv_umma_launch(const UmmaConvLaunch& L, cudaStream_t stream) {
   const ConvGeom& g = L.geom;
   const int bk = 128 / L.elem_bytes;
-  if (g.BW * g.BH != conv_umma_tile_pixels(g.Cout) || (1 << g.bw_shift) != g.BW || g.Cin % bk != 0 ||
-      (g.Cout != 128 && g.Cout != 256))
-    return set_error(SDPC_ERR_UNSUPPORTED, "conv_umma: unsupported shape Cin=%d Cout=%d tile=%dx%d", g.Cin, g.Cout,
-                     g.BH, g.BW);
-  if (L.elem_bytes == 2)
-    return g.Cout == 256 ? launch_t<__nv_bfloat16, 256, false>(L, stream) : launch_t<__nv_bfloat16, 256, true>(L, stream);
-  return g.Cout == 256 ? launch_t<float, 256, false>(L, stream) : launch_t<float, 256, true>(L, stream);
+  const bool swapped = g.Cout == 128 || conv_umma_swap256();
+  const int tiles = g.N * g.tiles_w * g.tiles_h * (swapped ? g.Cout / 128 : 1);
+  if (g.BW * g.BH != conv_umma_tile_pixels(g.Cout) || (1 << g.bw_shift) != g.BW || g.Cin % bk != 0 || g.BW % 32 != 0 ||
+      (g.Cout != 128 && g.Cout != 256) || g.num_tiles != tiles)
+    return set_error(SDPC_ERR_UNSUPPORTED, "conv_umma: unsupported shape Cin=%d Cout=%d tile=%dx%d tiles=%d", g.Cin, g.Cout,
+                     g.BH, g.BW, g.num_tiles);
+  if (L.elem_bytes == 2) {
+    if (g.Cout == 128) return launch_t<__nv_bfloat16, 256, true, 128>(L, stream);
+    return swapped ? launch_t<__nv_bfloat16, 256, true, 256>(L, stream) : launch_t<__nv_bfloat16, 256, false, 256>(L, stream);
+  }
+  if (g.Cout == 128) return launch_t<float, 256, true, 128>(L, stream);
+  return swapped ? launch_t<float, 256, true, 256>(L, stream) : launch_t<float, 256, false, 256>(L, stream);
 }
 
 }  // namespace sdpc

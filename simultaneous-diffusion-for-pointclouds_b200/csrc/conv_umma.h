@@ -10,7 +10,7 @@ namespace sdpc {
 
 struct UmmaConvLaunch {
   CUtensorMap tmap_a;   // input operand  {C, W+2p, H+2p, N}, box {BK, BW, BH, 1}, 128B swizzle
-  CUtensorMap tmap_b;   // weights        {Cin, Cout, taps}, box {BK, Cout, 1}
+  CUtensorMap tmap_b;   // weights        {Cin, Cout, taps}, box {BK, conv_umma_weight_rows(Cout), 1}
   CUtensorMap tmap_a_lo, tmap_b_lo;   // residual (lo) planes of the bf16x3 arm (copies of a / b otherwise)
   ConvGeom geom;
   EpiParams epi;
@@ -21,6 +21,9 @@ struct UmmaConvLaunch {
 // rank-`rank` tiled tensor map with 128-byte swizzle; dims/box innermost first.
 int make_tmap(CUtensorMap* out, void* base, int elem_bytes, int rank, const uint64_t* dims, const uint32_t* box);
 int conv_umma_launch(const UmmaConvLaunch& L, cudaStream_t stream);
-int conv_umma_tile_pixels(int Cout);   // 128 (Cout = 256) or 256 (Cout = 128, swapped operands)
+int conv_umma_tile_pixels(int Cout);   // 256 with swapped operands (Cout = 128, and Cout = 256 as two halves), else 128
+int conv_umma_stats_parts(int Cout);   // partial-statistics slots per pixel tile
+int conv_umma_weight_rows(int Cout);   // rows of the weight TMA box
+bool conv_umma_swap256();
 
 }  // namespace sdpc

@@ -370,7 +370,7 @@ struct Builder {
       if (can_fuse_stats() && out_raw) {
         const int co = h->convs.at(wname).Cout;
         const int tile_px = conv_umma_tile_pixels(co);
-        const int parts = co == 128 ? 2 : 4;
+        const int parts = conv_umma_stats_parts(co);
         *stats_out = new_part_stats(co, (in.H * in.W / tile_px) * parts);
       }
     }
@@ -387,6 +387,7 @@ struct Builder {
     g.tiles_w = in.W / g.BW;
     g.tiles_h = in.H / g.BH;
     g.num_tiles = N * g.tiles_w * g.tiles_h;
+    if (h->cfg.precision != SDPC_PREC_FP32 && tile_px == 256) g.num_tiles *= cw.Cout / 128;   // swapped: one tile per 128-channel half
     EpiParams e;
     e.bias = use_bias ? cw.bias : nullptr;
     e.residual = residual ? (const float*)residual->ptr : nullptr;
@@ -432,7 +433,7 @@ struct Builder {
     uint64_t adims[4] = {(uint64_t)cw.Cin, (uint64_t)(in.W + 2 * in.pad), (uint64_t)(in.H + 2 * in.pad), (uint64_t)N};
     uint32_t abox[4] = {(uint32_t)bk, (uint32_t)g.BW, (uint32_t)g.BH, 1u};
     uint64_t bdims[3] = {(uint64_t)cw.Cin, (uint64_t)cw.Cout, (uint64_t)cw.taps};
-    uint32_t bbox[3] = {(uint32_t)bk, (uint32_t)cw.Cout, 1u};
+    uint32_t bbox[3] = {(uint32_t)bk, (uint32_t)conv_umma_weight_rows(cw.Cout), 1u};
     if (int st = make_tmap(&L.tmap_a, in.ptr, L.elem_bytes, 4, adims, abox)) { status = st; return; }
     if (int st = make_tmap(&L.tmap_b, cw.w_tc, L.elem_bytes, 3, bdims, bbox)) { status = st; return; }
     L.tmap_a_lo = L.tmap_a;
