@@ -331,7 +331,7 @@ def run_b200(args):
                      # dram__bytes_read.sum + dram__bytes_write.sum per launch, mean of the 6 conv launches captured with
                      # ncu --set full in profiles/r01_ncu_full_conv2.txt (256->256 @32x512x8 views; algorithmic bytes of such
                      # a launch: 67 MB operand + 134 MB fp32 output [+ 134 MB residual])
-                     "traffic": 2.15e8 if args.precision == "bf16" else None, "traffic_unit": "bytes/launch (ncu, profiles/)",
+                     "traffic": 2.18e8 if args.precision == "bf16" else None, "traffic_unit": "bytes/launch (ncu, profiles/)",
                      "peak_source": peak_src, "launches_timed": conv_launches,
                      "conv_share_of_step": conv_ms / ms_prof if ms_prof else None,
                      "timing": "CUDA events around each conv launch, separate eager pass of the same K steps "
