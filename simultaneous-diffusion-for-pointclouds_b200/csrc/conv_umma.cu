@@ -51,11 +51,17 @@ struct UmmaCfg {
 //   A 128x128 MMA reads (128+128) rows of operands per 128x128 MACs and is bound by shared-memory
 //   bandwidth; putting the weights on the M side lets a 128-output-channel layer run the same
 //   128x256 instruction shape as the 256-channel layers (256 pixels per tile on the N side).
-template <typename T, int N_TILE, bool SWAP, int COUT>
+// CL (swapped layers only): the kernel runs as 2-CTA clusters on paired tiles that share one operand - the activation
+// tile for the two 128-channel halves of a Cout = 256 layer, the weights for two neighbouring pixel tiles of a
+// Cout = 128 layer.  Each CTA fetches half of the shared operand and TMA-multicasts it into both CTAs (tmap_half has the
+// half-sized box), so the L2 -> SM operand traffic drops by a third (a sixth); a stage is released to both producers by
+// a multicast tcgen05.commit (empty barriers count two arrivals).
+template <typename T, int N_TILE, bool SWAP, int COUT, bool CL>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_a_lo, const __grid_constant__ CUtensorMap tmap_b_lo,
-                 const ConvGeom g, const EpiParams e) {
+                 const __grid_constant__ CUtensorMap tmap_half, const ConvGeom g, const EpiParams e) {
+  static_assert(!CL || SWAP, "clusters are implemented for the swapped-operand variant");
   using Cfg = UmmaCfg<N_TILE>;
   constexpr bool kTf32 = sizeof(T) == 4;
   constexpr int kBK = kRowBytes / (int)sizeof(T);     // channels per k-block: 64 bf16 / 32 tf32
@@ -79,7 +85,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
     if (g.passes > 1) { prefetch_tmap(&tmap_a_lo); prefetch_tmap(&tmap_b_lo); }
-    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
+    if (CL) prefetch_tmap(&tmap_half);
+    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, CL ? 2 : 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, kEpiWarps); }
     fence_barrier_init();
   }
@@ -91,6 +98,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t crank = CL ? cluster_ctarank() : 0;
+  if (CL) cluster_sync_all();                          // the peer's barriers are initialised before anything is multicast
   // Everything above (barriers, descriptor prefetch, TMEM allocation) may overlap the previous kernel's tail; its
   // results (this layer's input, residual, the buffers this layer overwrites) are only touched after this point.
   pdl_sync();
@@ -125,8 +134,21 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               uint8_t* sb = sa + kABytes;
               mbar_arrive_expect_tx(full_bar + stage, Cfg::kStageBytes);
               // activations and weights land in the M-side (128 rows) or N-side (N_TILE rows) slot
-              tma_load_4d(SWAP ? sb : sa, ma, full_bar + stage, kc * kBK, w0 + g.in_pad + dx, h0 + g.in_pad + dy, n);
-              tma_load_3d(SWAP ? sa : sb, mb, full_bar + stage, kc * kBK, mh * kTileM, tap);
+              if constexpr (!CL) {
+                tma_load_4d(SWAP ? sb : sa, ma, full_bar + stage, kc * kBK, w0 + g.in_pad + dx, h0 + g.in_pad + dy, n);
+                tma_load_3d(SWAP ? sa : sb, mb, full_bar + stage, kc * kBK, mh * kTileM, tap);
+              } else if constexpr (kMH == 2) {
+                // own weight half; rows [128 r, 128 r + 128) of the shared activation tile, multicast to both CTAs
+                tma_load_3d(sa, mb, full_bar + stage, kc * kBK, mh * kTileM, tap);
+                const int hw = g.BH >= 2 ? 0 : (int)crank * (g.BW / 2), hh = g.BH >= 2 ? (int)crank * (g.BH / 2) : 0;
+                tma_load_4d_mc(sb + crank * (N_TILE / 2) * kRowBytes, &tmap_half, full_bar + stage, kc * kBK,
+                               w0 + hw + g.in_pad + dx, h0 + hh + g.in_pad + dy, n, (uint16_t)3);
+              } else {
+                // own activation tile; rows [64 r, 64 r + 64) of the shared weights, multicast to both CTAs
+                tma_load_4d(sb, ma, full_bar + stage, kc * kBK, w0 + g.in_pad + dx, h0 + g.in_pad + dy, n);
+                tma_load_3d_mc(sa + crank * (kTileM / 2) * kRowBytes, &tmap_half, full_bar + stage, kc * kBK,
+                               (int)crank * (kTileM / 2), tap, (uint16_t)3);
+              }
               if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
             }
           }
@@ -156,7 +178,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             // advance 32 bytes along K inside the swizzle span: +2 in the (addr >> 4) field
             umma_ss<kTf32>(d_tmem, da + (uint64_t)(2 * j), db + (uint64_t)(2 * j), kIdesc, (k | j) != 0);
           }
-          umma_commit(empty_bar + stage);                    // frees the smem slot when the MMAs retire
+          if constexpr (CL) umma_commit_mc(empty_bar + stage, (uint16_t)3);   // both producers write this slot
+          else umma_commit(empty_bar + stage);               // frees the smem slot when the MMAs retire
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
         umma_commit(acc_full + ab);                          // accumulator complete
@@ -438,6 +461,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
+  if (CL) cluster_sync_all();                          // no CTA leaves while its peer may still signal its barriers
 }
 
 // ------------------------------------------------------------------------------------------ host
@@ -477,21 +501,56 @@ int make_tmap(CUtensorMap* out, void* base, int elem_bytes, int rank, const uint
   return SDPC_OK;
 }
 
-template <typename T, int N_TILE, bool SWAP, int COUT>
+template <typename T, int N_TILE, bool SWAP, int COUT, bool CL>
 static int launch_t(const UmmaConvLaunch& L, cudaStream_t stream) {
   using Cfg = UmmaCfg<N_TILE>;
+  auto kernel = conv_umma_kernel<T, N_TILE, SWAP, COUT, CL>;
   static bool attr_set = false;
+  static int max_clusters = 0;
   if (!attr_set) {
-    SDPC_CUDA(cudaFuncSetAttribute(conv_umma_kernel<T, N_TILE, SWAP, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   Cfg::kSmemBytes));
+    SDPC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    if (CL) {
+      cudaLaunchConfig_t q = {};
+      q.gridDim = dim3(L.num_sms & ~1);
+      q.blockDim = dim3(kThreads);
+      q.dynamicSmemBytes = Cfg::kSmemBytes;
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = 2; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+      q.attrs = qa;
+      q.numAttrs = 1;
+      SDPC_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, kernel, &q));
+      if (max_clusters < 1) return set_error(SDPC_ERR_CUDA, "conv_umma: no 2-CTA cluster fits on this device");
+    }
     attr_set = true;
   }
-  int grid = L.geom.num_tiles < L.num_sms ? L.geom.num_tiles : L.num_sms;
-  SDPC_CUDA(launch_k(conv_umma_kernel<T, N_TILE, SWAP, COUT>, dim3(grid), dim3(kThreads), Cfg::kSmemBytes, stream, L.tmap_a, L.tmap_b, L.tmap_a_lo, L.tmap_b_lo, L.geom, L.epi));
+  if (!CL) {
+    int grid = L.geom.num_tiles < L.num_sms ? L.geom.num_tiles : L.num_sms;
+    SDPC_CUDA(launch_k(kernel, dim3(grid), dim3(kThreads), Cfg::kSmemBytes, stream, L.tmap_a, L.tmap_b, L.tmap_a_lo, L.tmap_b_lo, L.tmap_half, L.geom, L.epi));
+  } else {
+    int clusters = L.geom.num_tiles / 2 < max_clusters ? L.geom.num_tiles / 2 : max_clusters;
+    if (clusters > L.num_sms / 2) clusters = L.num_sms / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    SDPC_CUDA(cudaLaunchKernelEx(&cfg, kernel, L.tmap_a, L.tmap_b, L.tmap_a_lo, L.tmap_b_lo, L.tmap_half, L.geom, L.epi));
+  }
   SDPC_CUDA(cudaGetLastError());
   return SDPC_OK;
 }
 
+// swapped layers run as 2-CTA clusters with operand multicast unless SDPC_CLUSTER=0 (A/B switch, read once)
+bool conv_umma_cluster() {
+  static const bool on = [] { const char* v = getenv("SDPC_CLUSTER"); return !(v && v[0] == '0'); }();
+  return on;
+}
 // Cout = 256 layers run swapped as two 128-channel halves unless SDPC_SWAP256=0 (A/B switch, read once)
 bool conv_umma_swap256() {
   static const bool on = [] { const char* v = getenv("SDPC_SWAP256"); return !(v && v[0] == '0'); }();
@@ -513,12 +572,15 @@ int conv_umma_launch(const UmmaConvLaunch& L, cudaStream_t stream) {
       (g.Cout != 128 && g.Cout != 256) || g.num_tiles != tiles)
     return set_error(SDPC_ERR_UNSUPPORTED, "conv_umma: unsupported shape Cin=%d Cout=%d tile=%dx%d tiles=%d", g.Cin, g.Cout,
                      g.BH, g.BW, g.num_tiles);
+  const bool cl = L.use_cluster && swapped && g.passes == 1 && (g.num_tiles % 2) == 0;
   if (L.elem_bytes == 2) {
-    if (g.Cout == 128) return launch_t<__nv_bfloat16, 256, true, 128>(L, stream);
-    return swapped ? launch_t<__nv_bfloat16, 256, true, 256>(L, stream) : launch_t<__nv_bfloat16, 256, false, 256>(L, stream);
+    if (g.Cout == 128) return cl ? launch_t<__nv_bfloat16, 256, true, 128, true>(L, stream) : launch_t<__nv_bfloat16, 256, true, 128, false>(L, stream);
+    if (!swapped) return launch_t<__nv_bfloat16, 256, false, 256, false>(L, stream);
+    return cl ? launch_t<__nv_bfloat16, 256, true, 256, true>(L, stream) : launch_t<__nv_bfloat16, 256, true, 256, false>(L, stream);
   }
-  if (g.Cout == 128) return launch_t<float, 256, true, 128>(L, stream);
-  return swapped ? launch_t<float, 256, true, 256>(L, stream) : launch_t<float, 256, false, 256>(L, stream);
+  if (g.Cout == 128) return cl ? launch_t<float, 256, true, 128, true>(L, stream) : launch_t<float, 256, true, 128, false>(L, stream);
+  if (!swapped) return launch_t<float, 256, false, 256, false>(L, stream);
+  return cl ? launch_t<float, 256, true, 256, true>(L, stream) : launch_t<float, 256, true, 256, false>(L, stream);
 }
 
 }  // namespace sdpc

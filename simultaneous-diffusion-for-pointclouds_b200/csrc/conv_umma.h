@@ -12,6 +12,8 @@ struct UmmaConvLaunch {
   CUtensorMap tmap_a;   // input operand  {C, W+2p, H+2p, N}, box {BK, BW, BH, 1}, 128B swizzle
   CUtensorMap tmap_b;   // weights        {Cin, Cout, taps}, box {BK, conv_umma_weight_rows(Cout), 1}
   CUtensorMap tmap_a_lo, tmap_b_lo;   // residual (lo) planes of the bf16x3 arm (copies of a / b otherwise)
+  CUtensorMap tmap_half;   // cluster variant: half-sized box of the operand the two CTAs of a cluster share (see conv_umma.cu)
+  int use_cluster;         // 1: tmap_half is valid and the layer may run as 2-CTA clusters
   ConvGeom geom;
   EpiParams epi;
   int elem_bytes;       // 2 = bf16 (kind::f16), 4 = tf32 (kind::tf32)
@@ -25,5 +27,6 @@ int conv_umma_tile_pixels(int Cout);   // 256 with swapped operands (Cout = 128,
 int conv_umma_stats_parts(int Cout);   // partial-statistics slots per pixel tile
 int conv_umma_weight_rows(int Cout);   // rows of the weight TMA box
 bool conv_umma_swap256();
+bool conv_umma_cluster();
 
 }  // namespace sdpc
