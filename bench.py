@@ -188,8 +188,7 @@ def run_b200(args):
     from sdpc_b200 import cabi
     from sdpc_b200.scorenet import NCSN_LiDAR_small
     from sdpc_b200.step import StepRunner
-    from oracle.sigmas import sigma_schedule
-    from oracle.weights import make_state_dict
+    from sdpc_b200.sigmas import get_sigmas
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -202,9 +201,10 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
     B = args.views_per_gpu
     g = synthetic_group(B, 1234 + rank)
-    sig = sigma_schedule(50, 0.01, LEVELS).numpy()
-    net = NCSN_LiDAR_small(config_ns(dev), precision=args.precision).to(dev)
-    net.load_state_dict(make_state_dict(num_classes=LEVELS))          # deterministic random-init weights
+    cfg = config_ns(dev)
+    sig = get_sigmas(cfg).cpu().numpy()
+    torch.manual_seed(1234)                                           # random-init weights (nn.Conv2d-style init of the module)
+    net = NCSN_LiDAR_small(cfg, precision=args.precision).to(dev)
     run = StepRunner((B, 2, H, W), dev, g["refer"], g["mask"], g["sky"], g["exist"], B, cabi.SDPC_VARIANT_POSE,
                      to_world=g["toWorld"], from_world=g["fromWorld"])
     x = g["x"].to(dev)
@@ -292,7 +292,7 @@ def run_b200(args):
     parity = None
     if args.precision == "bf16" and not args.no_parity_arm:
         net3 = NCSN_LiDAR_small(config_ns(dev), precision="bf16x3").to(dev)
-        net3.load_state_dict(make_state_dict(num_classes=LEVELS))
+        net3.load_state_dict(net.state_dict())
         fast_net, net = net, net3
         for _ in range(3):
             step(x)
