@@ -13,6 +13,8 @@ OUT = os.path.join(HERE, "libsdpc_b200.so")
 OBJ = os.path.join(HERE, "build")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+if os.environ.get("SDPC_DEV_HOOKS"):            # timing probes that corrupt results (tools/gpu_epi_probe.sh); never in a shipped build
+    COMMON.append("-DSDPC_DEV_HOOKS")
 # (source, extra flags)
 UNITS = [
     ("common.cu", []),

@@ -401,7 +401,10 @@ struct Builder {
     e.op_tf32 = h->cfg.precision == SDPC_PREC_TF32;
     e.op_lo_off = out_op ? out_op->lo_off : 0;
     e.prefetch_residual = getenv("SDPC_NO_PREFETCH") ? 0 : 1;
-    if (const char* dd = getenv("SDPC_DEV_EPI_DROP")) {        // development timing hook: results are garbage
+#ifdef SDPC_DEV_HOOKS
+    // development timing probe (tools/gpu_epi_probe.sh; build with SDPC_DEV_HOOKS=1): drops parts of the epilogue,
+    // results are garbage.  Not compiled into the shipped library.
+    if (const char* dd = getenv("SDPC_DEV_EPI_DROP")) {
       const int m = atoi(dd);
       if (m & 1) e.residual = nullptr;
       if (m & 2) { e.out_raw = nullptr; e.out_acc = nullptr; }
@@ -409,9 +412,12 @@ struct Builder {
       if (m & 16) e.op_elu = 0;
       if (m & 32) e.bias = nullptr;
     }
+#endif
     g.passes = h->x3() ? 3 : 1;
     e.stats = (stats_out && stats_out->valid()) ? (float*)(base + plan->parts_off + stats_out->off) : nullptr;
+#ifdef SDPC_DEV_HOOKS
     if (const char* dd = getenv("SDPC_DEV_EPI_DROP")) { if (atoi(dd) & 8) e.stats = nullptr; }
+#endif
     if (cw.taps == 9 && in.pad < dil) { status = set_error(SDPC_ERR_STATE, "plan: halo %d < dilation %d for %s", in.pad, dil, wname.c_str()); return; }
     if (h->cfg.precision == SDPC_PREC_FP32) {
       const float* inp = (const float*)in.ptr;

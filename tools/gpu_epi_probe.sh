@@ -1,5 +1,6 @@
 #!/bin/bash
-# per-layer conv times with parts of the epilogue dropped (development timing probe; dropped runs give garbage results)
+# per-layer conv times with parts of the epilogue dropped (development timing probe; needs a build with SDPC_DEV_HOOKS=1;
+# dropped runs give garbage results)
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
 for m in 0 63 62 4 20 1 2 8; do
