@@ -147,3 +147,39 @@ def sampler_single_view(x_mod, refer_image, refer_mask, scorenet, sigmas, n_step
     images.append(x_mod.to("cpu"))
     targets.append(refer_image.to("cpu"))
     return images, targets
+
+
+@torch.no_grad()
+def sampler_unconditional(x_mod, scorenet, sigmas, n_steps_each=200, step_lr=0.000008, final_only=False,
+                          denoise=True, noise_fn=torch.randn_like):
+    """row N4, anneal_Langevin_dynamics (LiDARGen/models/__init__.py:20-58): x += eps*s + sqrt(2 eps)*z, no likelihood
+    term, no nan_to_num; a CPU snapshot per step unless final_only."""
+    images = []
+    dev = x_mod.device
+    L = len(sigmas)
+    for c, sigma in enumerate(sigmas):
+        labels = (torch.ones(x_mod.shape[0], device=dev) * c).long()
+        step_size, noise_scale = _step_constants(step_lr, sigma, sigmas[-1])
+        for s in range(n_steps_each):
+            grad = scorenet(x_mod, labels)
+            noise = noise_fn(x_mod)
+            x_mod = x_mod + step_size * grad + noise * noise_scale          # :35
+            if not final_only:
+                images.append(x_mod.to("cpu"))
+    if denoise:
+        last = ((L - 1) * torch.ones(x_mod.shape[0], device=dev)).long()
+        x_mod = x_mod + sigmas[-1] ** 2 * scorenet(x_mod, last)             # :51
+        images.append(x_mod.to("cpu"))
+    return [x_mod.to("cpu")] if final_only else images
+
+
+@torch.no_grad()
+def sampler_densification(x_mod, refer_image, scorenet, sigmas, n_steps_each=100, step_lr=0.000008, denoise=True,
+                          grad_ref=0.1, sampling_step=16, noise_fn=torch.randn_like):
+    """row N4, anneal_Langevin_dynamics_densification (LiDARGen/models/__init__.py:60-109): the known pixels are the
+    beams 0, sampling_step, 2*sampling_step, ... (mask built inside, float); otherwise the a-6 loop including the stale
+    likelihood gradient in the denoise step (:96)."""
+    mask = torch.zeros_like(x_mod)
+    mask[:, :, 0:64:sampling_step, :] = 1                                   # :67 (the bilinear `raw_interp` of :66 is unused)
+    return sampler_single_view(x_mod, refer_image, mask, scorenet, sigmas, n_steps_each, step_lr, denoise, False,
+                               grad_ref, noise_fn)

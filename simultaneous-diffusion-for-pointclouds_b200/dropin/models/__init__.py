@@ -17,6 +17,7 @@ _root = os.path.dirname(os.path.dirname(os.path.dirname(os.path.dirname(os.path.
 if _root not in sys.path:
     sys.path.insert(0, _root)
 import sdpc_b200  # noqa: E402,F401
-from sdpc_b200.samplers import (anneal_Langevin_dynamics_inpainting,  # noqa: E402,F401
+from sdpc_b200.samplers import (anneal_Langevin_dynamics, anneal_Langevin_dynamics_densification,  # noqa: E402,F401
+                                anneal_Langevin_dynamics_inpainting,
                                 anneal_Langevin_dynamics_inpainting_simultaneous_basic)
 from sdpc_b200.sigmas import get_sigmas  # noqa: E402,F401

@@ -206,3 +206,53 @@ def anneal_Langevin_dynamics_inpainting(x_mod, refer_image, refer_mask, scorenet
                                                       torch.median(torch.abs(x - refer))))
     targets.append(_snap(refer))
     return images, targets
+
+
+# ---- row N4: the unconditional and the beam-densification samplers, on the same update kernel ----------
+@torch.no_grad()
+def anneal_Langevin_dynamics(x_mod, scorenet, sigmas, n_steps_each=200, step_lr=0.000008,
+                             final_only=False, verbose=False, denoise=True):
+    """Unconditional annealed Langevin sampling (LiDARGen/models/__init__.py:20-58): x += eps*s + sqrt(2 eps)*z.
+    Runs `sdpc_langevin_update` with an all-zero mask and grad_ref = 0 (the likelihood term is then exactly +-0)."""
+    _require_cuda(x_mod)
+    dev = x_mod.device
+    images = []
+    B = x_mod.shape[0]
+    x = x_mod.detach().to(torch.float32).clone().contiguous()
+    run = StepRunner(x.shape, dev, torch.zeros_like(x), torch.zeros(x.shape, dtype=torch.int32, device=dev), None, None, 1,
+                     cabi.SDPC_VARIANT_POSE)
+    L = len(sigmas)
+    for c, sigma in enumerate(sigmas):
+        labels = (torch.ones(B, device=dev) * c).long()
+        step_size = step_lr * (sigma / sigmas[-1]) ** 2
+        p = run.params(step_size, np.sqrt(step_size * 2), 0.0, 0.0, 1.0, False, False, None, False, nan_to_num=False)
+        for s in range(n_steps_each):
+            grad = scorenet(x, labels)
+            noise = torch.randn_like(x)
+            run.update_only(p, run.buffers(x, grad, noise))
+            if not final_only:
+                images.append(_snap(x))
+            if verbose:
+                flat = lambda t: t.view(t.shape[0], -1)
+                grad_norm, noise_norm = torch.norm(flat(grad), dim=-1).mean(), torch.norm(flat(noise), dim=-1).mean()
+                print("level: {}, step_size: {}, grad_norm: {}, image_norm: {}, snr: {}, grad_mean_norm: {}".format(
+                    c, step_size, grad_norm.item(), torch.norm(flat(x), dim=-1).mean().item(),
+                    (np.sqrt(step_size / 2.) * grad_norm / noise_norm).item(),
+                    (torch.norm(grad.mean(dim=0).view(-1)) ** 2 * sigma ** 2).item()))
+    if denoise:
+        last_noise = ((L - 1) * torch.ones(B, device=dev)).long()
+        x = x + sigmas[-1] ** 2 * scorenet(x, last_noise)
+        images.append(_snap(x))
+    return [_snap(x)] if final_only else images
+
+
+@torch.no_grad()
+def anneal_Langevin_dynamics_densification(x_mod, refer_image, scorenet, sigmas, n_steps_each=100, step_lr=0.000008,
+                                           denoise=True, verbose=True, grad_ref=0.1, sampling_step=16):
+    """Beam densification of one view (LiDARGen/models/__init__.py:60-109): beams 0, sampling_step, ... are known, the
+    rest is sampled.  Same loop as a-6 with the mask built here (the reference's unused bilinear `raw_interp`, :66, is
+    not evaluated)."""
+    mask = torch.zeros(x_mod.shape, dtype=torch.int32, device=x_mod.device)
+    mask[:, :, 0:64:sampling_step, :] = 1
+    return anneal_Langevin_dynamics_inpainting(x_mod, refer_image, mask, scorenet, sigmas, n_steps_each, step_lr, denoise,
+                                               verbose, grad_ref)

@@ -241,6 +241,27 @@ def gen_samplers():
          **{f"images{i}": t.numpy() for i, t in enumerate(images)})
 
 
+def gen_n4():
+    """row N4: the unconditional and the beam-densification samplers (models/__init__.py:20-109)."""
+    sig = cases.short_sigmas()
+    case = cases.small_multiview(kind="trans")
+    score = cases.fake_score(sig)
+    noise = cases.noise_list(case["x"].shape, len(sig) * 2, seed=80)
+    with Recorder(noise_list=noise):
+        images = ref_models.anneal_Langevin_dynamics(case["x"].clone(), score, sig, n_steps_each=2, step_lr=6.2e-6,
+                                                     final_only=False, verbose=False, denoise=True)
+    arrs = {"u_n": np.int32(len(images))}
+    arrs.update({f"u{i}": t.numpy() for i, t in enumerate(images)})
+    noise = cases.noise_list(case["x"].shape, len(sig) * 2, seed=81)
+    with Recorder(noise_list=noise):
+        images, targets = ref_models.anneal_Langevin_dynamics_densification(
+            case["x"].clone(), case["refer"], score, sig, n_steps_each=2, step_lr=6.2e-6, denoise=True, verbose=False,
+            grad_ref=0.1, sampling_step=4)
+    arrs["d_n"] = np.int32(len(images))
+    arrs.update({f"d{i}": t.numpy() for i, t in enumerate(images)})
+    save("sampler_n4.npz", **arrs)
+
+
 def gen_full():
     case = cases.full_multiview()
     r = run_one_step("pose", case, 0.3, 5)
@@ -260,7 +281,7 @@ def gen_full():
 
 if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count())
-    which = sys.argv[1:] or ["sigmas", "scorenet", "crossview", "samplers", "full"]
+    which = sys.argv[1:] or ["sigmas", "scorenet", "crossview", "samplers", "n4", "full"]
     for w in which:
         {"sigmas": gen_sigmas, "scorenet": gen_scorenet, "crossview": gen_crossview,
-         "samplers": gen_samplers, "full": gen_full}[w]()
+         "samplers": gen_samplers, "n4": gen_n4, "full": gen_full}[w]()

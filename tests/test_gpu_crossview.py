@@ -208,6 +208,25 @@ def test_samplers_vs_reference_goldens():
         assert len(im) == int(g["n_images"]) and len(tg) == 1
         for i, t in enumerate(im):
             assert np.allclose(t.numpy(), g[f"images{i}"], rtol=1e-5, atol=1e-5), i
+        # row N4: unconditional and beam-densification samplers (models/__init__.py:20-109) on the same update kernel
+        g = np.load(os.path.join(G, "sampler_n4.npz"))
+        inject(80, case["x"].shape)
+        im = samplers.anneal_Langevin_dynamics(to(case["x"]), score, sig, n_steps_each=2, step_lr=6.2e-6,
+                                               final_only=False, verbose=False, denoise=True)
+        assert len(im) == int(g["u_n"])
+        for i, t in enumerate(im):
+            assert np.allclose(t.numpy(), g[f"u{i}"], rtol=1e-5, atol=1e-5), i
+        inject(80, case["x"].shape)
+        fin = samplers.anneal_Langevin_dynamics(to(case["x"]), score, sig, n_steps_each=2, step_lr=6.2e-6,
+                                                final_only=True, verbose=False, denoise=True)
+        assert len(fin) == 1 and np.array_equal(fin[0].numpy(), im[-1].numpy())
+        inject(81, case["x"].shape)
+        im, tg = samplers.anneal_Langevin_dynamics_densification(
+            to(case["x"]), to(case["refer"]), score, sig, n_steps_each=2, step_lr=6.2e-6, denoise=True, verbose=False,
+            grad_ref=0.1, sampling_step=4)
+        assert len(im) == int(g["d_n"]) and len(tg) == 1
+        for i, t in enumerate(im):
+            assert np.allclose(t.numpy(), g[f"d{i}"], rtol=1e-5, atol=1e-5), i
     finally:
         torch.randn_like = orig
 

@@ -170,6 +170,25 @@ def test_sampler_single_view_trajectory():
         assert np.array_equal(t.numpy(), g[f"images{i}"])
 
 
+def test_n4_unconditional_and_densification_trajectories():
+    """row N4: the oracle restatements against trajectories of the unmodified reference samplers (models/__init__.py:20-109)."""
+    g = _load("sampler_n4.npz")
+    sig = cases.short_sigmas()
+    case = cases.small_multiview("trans")
+    im = sr.sampler_unconditional(case["x"].clone(), cases.fake_score(sig), sig, n_steps_each=2, step_lr=6.2e-6,
+                                  final_only=False, denoise=True,
+                                  noise_fn=_noise_iter(cases.noise_list(case["x"].shape, 8, 80)))
+    assert len(im) == int(g["u_n"]) == 9
+    for i, t in enumerate(im):
+        assert np.array_equal(t.numpy(), g[f"u{i}"])
+    im, tg = sr.sampler_densification(case["x"].clone(), case["refer"], cases.fake_score(sig), sig, n_steps_each=2,
+                                      step_lr=6.2e-6, denoise=True, grad_ref=0.1, sampling_step=4,
+                                      noise_fn=_noise_iter(cases.noise_list(case["x"].shape, 8, 81)))
+    assert len(im) == int(g["d_n"]) == 10 and len(tg) == 1
+    for i, t in enumerate(im):
+        assert np.array_equal(t.numpy(), g[f"d{i}"])
+
+
 def test_crossview_full_size_checksums():
     g = _load("crossview_full.npz")
     case = cases.full_multiview()
