@@ -238,6 +238,25 @@ int sdpc_range_image_to_points(const float* image, int n_views, int height, int 
 int sdpc_depth_intensity_errors(const float* pred, const float* gt, const float* input, int n_views, int height, int width,
                                 double* out, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Row N2: multi-view dataset assembly around the projection of row N1
+ *   KITTI360_im_8batch.__getitem__      LiDARGen/datasets/kitti360_im_8Batch.py:94-304
+ *   (kitti360_im_AllForOne.py:94-355 and kitti360_im_simultenous_densification.py differ in the pose they pick and in
+ *    the origin handed to the projection, not in these two steps)
+ * ---------------------------------------------------------------------------------------- */
+/* scan: float32 [N,4] (device; x, y, z, remission as read from a KITTI .bin).  to_world / from_world: float64 4x4 row
+ * major (HOST pointers).  out: float64 [N,4] (device) = (from_world . (to_world . (x, y, z, 1)))[:3], remission. */
+int sdpc_transform_scan(const float* scan, int n_points, const double* to_world, const double* from_world, double* out,
+                        void* stream);
+/* depth, intensity (nullable), obfuscation (nullable), sky: the images sdpc_pointcloud_to_range_image returns (device).
+ * real: float64 [C,H,W] (C = 2 with intensity, else 1): log2(depth + 1) / 6 and remission, offset by 1e-4 and clipped
+ * to [0,1], holes (depth >= max_range, remission >= 1) zeroed first.  known (nullable): uint8 [C,H,W] =
+ * logical_not(mask) with mask = obfuscation | holes.  notsky (nullable): uint8 [H,W] = logical_not(sky shifted down by
+ * three rows). */
+int sdpc_range_image_postprocess(const double* depth, const double* intensity, const uint8_t* obfuscation,
+                                 const uint8_t* sky, int height, int width, double max_range, double* real,
+                                 uint8_t* known, uint8_t* notsky, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

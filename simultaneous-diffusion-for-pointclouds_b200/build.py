@@ -22,6 +22,7 @@ UNITS = [
     ("crossview.cu", ["-fmad=false"]),
     ("lidar_projection.cu", ["-fmad=false"]),
     ("output_stage.cu", ["-fmad=false"]),
+    ("dataset_assembly.cu", ["-fmad=false"]),
     ("conv_umma.cu", []),
     ("scorenet.cu", []),
 ]

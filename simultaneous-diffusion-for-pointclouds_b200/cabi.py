@@ -78,6 +78,8 @@ SYMBOLS = [
     ("sdpc_points_workspace_bytes", _SZ, [_I, _I, _I]),
     ("sdpc_range_image_to_points", _I, [_P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     ("sdpc_depth_intensity_errors", _I, [_P, _P, _P, _I, _I, _I, _P, _P]),
+    ("sdpc_transform_scan", _I, [_P, _I, C.POINTER(C.c_double), C.POINTER(C.c_double), _P, _P]),
+    ("sdpc_range_image_postprocess", _I, [_P, _P, _P, _P, _I, _I, C.c_double, _P, _P, _P, _P]),
     ("sdpc_langevin_reproject_step_host", _I, [C.POINTER(StepParams), C.POINTER(StepBuffers), _P, _P, _P, _P, _P, _SZ, _P]),
 ]
 

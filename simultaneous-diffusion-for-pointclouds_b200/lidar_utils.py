@@ -10,14 +10,11 @@ import torch
 from . import cabi
 
 
-def point_cloud_to_range_image(point_cloud, origin, return_remission=False, return_points=False,
-                               provided_origin=False, rowMax=64, colMax=1024, saveNum=0, device="cuda"):
+def project_device(pc, origin, return_remission, H, W):
+    """pc: float64 [N, >=3(+1)] CUDA tensor.  Returns device tensors (depth f64, intensity f64 or None, obfuscation u8,
+    sky u8, index f64), all [H, W] and flipped like the reference's outputs."""
     lib = cabi.load()
-    if not torch.cuda.is_available():
-        raise cabi.SdpcError("point_cloud_to_range_image needs a CUDA device: there is no CPU fallback")
-    dev = torch.device(device)
-    pc = torch.as_tensor(np.ascontiguousarray(point_cloud, dtype=np.float64)).to(dev)
-    H, W = int(rowMax), int(colMax)
+    dev = pc.device
     p = cabi.ProjectionParams()
     p.n_points, p.point_stride = pc.shape[0], pc.shape[1]
     p.intensity_col = 3 if return_remission else -1
@@ -41,6 +38,16 @@ def point_cloud_to_range_image(point_cloud, origin, return_remission=False, retu
                                                 C.c_void_p(obf.data_ptr()), C.c_void_p(sky.data_ptr()),
                                                 C.c_void_p(index.data_ptr()), C.c_void_p(ws.data_ptr()), ws.numel(), stream)
         cabi.check(lib, st, "sdpc_pointcloud_to_range_image")
+    return depth, (inten if return_remission else None), obf, sky, index
+
+
+def point_cloud_to_range_image(point_cloud, origin, return_remission=False, return_points=False,
+                               provided_origin=False, rowMax=64, colMax=1024, saveNum=0, device="cuda"):
+    if not torch.cuda.is_available():
+        raise cabi.SdpcError("point_cloud_to_range_image needs a CUDA device: there is no CPU fallback")
+    dev = torch.device(device)
+    pc = torch.as_tensor(np.ascontiguousarray(point_cloud, dtype=np.float64)).to(dev)
+    depth, inten, obf, sky, index = project_device(pc, origin, return_remission, int(rowMax), int(colMax))
     d, ob, sk, ix = depth.cpu().numpy(), obf.cpu().numpy().astype(bool), sky.cpu().numpy().astype(bool), index.cpu().numpy()
     if return_remission:
         return d, inten.cpu().numpy(), ob, saveNum, sk, ix

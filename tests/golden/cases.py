@@ -133,3 +133,32 @@ def synthetic_scan(n, seed):
     pts[-50:] = pts[:50]                                                       # exact duplicates (ties)
     origin = np.array([0.3, -0.2, 0.1])
     return pts, origin
+
+
+# ---- row N2: synthetic KITTI-360-like drive (calibration, poses, scans) ------------------------------------------------
+N2_SHAPE = (32, 256)           # rowMax, colMax of the fixture
+N2_FRAMES = 24
+N2_BATCH = 3                   # actualBatchSize: views per item group
+
+
+def n2_calibration():
+    """(cam_to_velo 12, cam_to_pose rows [k,12], poses [F,13]) with the layouts of calib_cam_to_velo.txt,
+    calib_cam_to_pose.txt (after stripping the labels) and poses.txt."""
+    def rigid(yaw, pitch, t):
+        cy, sy, cp, sp = np.cos(yaw), np.sin(yaw), np.cos(pitch), np.sin(pitch)
+        R = np.array([[cy, -sy, 0], [sy, cy, 0], [0, 0, 1.0]]) @ np.array([[cp, 0, sp], [0, 1, 0], [-sp, 0, cp]])
+        return np.concatenate((R, np.asarray(t, dtype=np.float64).reshape(3, 1)), 1).reshape(-1)
+
+    cam_to_velo = rigid(0.02, -0.01, [0.8, 0.3, -0.6])
+    cam_to_pose = np.stack([rigid(0.05, 0.02, [1.6, 0.06, 1.3]), rigid(0.0, 0.0, [0, 0, 0])])
+    poses = []
+    for f in range(N2_FRAMES):                       # a gentle left curve, ~1 m per frame; frame ids skip some numbers
+        yaw = 0.01 * f
+        poses.append(np.concatenate(([1 + f + (f // 7)], rigid(yaw, 0.002 * f, [1.0 * f, 0.02 * f * f, 0.01 * f]))))
+    return cam_to_velo, cam_to_pose, np.asarray(poses)
+
+
+def n2_scan(frame, n=20000):
+    """float32 [n,4] raw scan of a frame, like np.fromfile(<frame>.bin, float32).reshape(-1, 4)"""
+    pts, _ = synthetic_scan(n, 1000 + int(frame))
+    return pts.astype(np.float32)
