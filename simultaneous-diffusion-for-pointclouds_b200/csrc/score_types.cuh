@@ -35,6 +35,9 @@ struct EpiParams {
   int op_tf32;            // 1: round the fp32 operand to tf32 (rna)
   size_t op_lo_off;       // bf16x3 arm: element offset of the residual (lo) plane of out_op, else 0
   int prefetch_residual;  // 1: the epilogue warps prefetch the tile's residual rows into L2 before the accumulator is ready
+#ifdef SDPC_DEV_HOOKS
+  int dev_wrap;           // timing probe: bit 0 wraps store offsets, bit 1 wraps residual-load offsets into a 1 MB window
+#endif
   float* stats;           // per-tile partial sums [tile][parts][Cout][2] (sum, sum of squares) of the out_raw
                           // values for InstanceNorm++ (parts = 4 pixel quadrants, or 2 chunk parities when swapped), or null
 };

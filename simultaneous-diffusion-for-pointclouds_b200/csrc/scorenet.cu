@@ -402,6 +402,7 @@ struct Builder {
     e.op_lo_off = out_op ? out_op->lo_off : 0;
     e.prefetch_residual = getenv("SDPC_NO_PREFETCH") ? 0 : 1;
 #ifdef SDPC_DEV_HOOKS
+    e.dev_wrap = getenv("SDPC_DEV_WRAP") ? atoi(getenv("SDPC_DEV_WRAP")) : 0;
     // development timing probe (tools/gpu_epi_probe.sh; build with SDPC_DEV_HOOKS=1): drops parts of the epilogue,
     // results are garbage.  Not compiled into the shipped library.
     if (const char* dd = getenv("SDPC_DEV_EPI_DROP")) {
