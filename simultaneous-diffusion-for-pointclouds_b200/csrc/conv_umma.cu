@@ -2,18 +2,21 @@
 // operands staged by TMA.  This is the kernel that carries ~99% of the score network's FLOPs
 // (NCSN_LiDAR_small: LiDARGen/models/ncsnv2.py:484-518, conv definitions layers.py:37-60).
 //
-// GEMM view:  D[m, co] = sum_{tap, ci} X[pixel(m) + offset(tap), ci] * Wt[tap, co, ci]
-//   M tile : 128 output pixels = a BH x BW box of one image (BW = min(W,128))
-//   N tile : all Cout (128 or 256) -> the activation tile is fetched once per pixel tile
+// GEMM view:  D[co, m] = sum_{tap, ci} Wt[tap, co, ci] * X[pixel(m) + offset(tap), ci]   (one tcgen05.mma shape: 128 x 256 x 16)
+//   M side : 128 output channels (all of a Cout = 128 layer, one half of a Cout = 256 layer)
+//   N side : 256 output pixels = a BH x BW box of one image (BW = min(W, 256))
 //   K loop : taps x (Cin / BK), BK = 128 bytes of channels (64 bf16 / 32 tf32)
-// A operand: the input activation is an NHWC tensor with a materialised halo (circular wrap or
-//   zeros), so every shifted tap is an in-bounds 4-D TMA box {BK, BW, BH, 1}; the box lands in
-//   shared memory as 128 rows x 128 B, 128B-swizzled = the canonical K-major UMMA layout.
-// B operand: weights repacked to [tap][Cout][Cin] (K-major), 3-D TMA box {BK, Cout, 1}.
-// Accumulator: fp32 in TMEM, double buffered (2 x Cout columns) so the epilogue of tile i
-//   overlaps the MMAs of tile i+1.  Persistent CTAs, one per SM, static round-robin tiles.
+//   (the unswapped tiling - 128 pixels on M, 256 channels on N - is kept behind SDPC_SWAP256=0 for Cout = 256)
+// Activations: the input is an NHWC tensor with a materialised halo (circular wrap or zeros), so every shifted
+//   tap is an in-bounds 4-D TMA box {BK, BW, BH, 1}; the box lands in shared memory as 256 rows x 128 B,
+//   128B-swizzled = the canonical K-major UMMA layout.
+// Weights: repacked to [tap][Cout][Cin] (K-major), 3-D TMA box {BK, 128, 1}.
+// Clusters: CTAs run in pairs on tiles that share one operand (the activation tile for the two channel halves, the
+//   weights for two neighbouring pixel tiles); each CTA fetches half of it and TMA-multicasts it into both.
+// Accumulator: fp32 in TMEM, double buffered (2 x 256 columns) so the epilogue of tile i overlaps the MMAs of
+//   tile i+1.  Persistent CTAs, one per SM, static round-robin tiles.
 // Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane) + TMEM allocator,
-//   warps 2-5 = epilogue (tcgen05.ld -> bias / residual / ELU / stores, see score_types.cuh).
+//   warps 2-9 = epilogue (tcgen05.ld -> bias / residual / ELU / statistics / stores, see score_types.cuh).
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>

@@ -39,7 +39,8 @@ struct EpiParams {
   int dev_wrap;           // timing probe: bit 0 wraps store offsets, bit 1 wraps residual-load offsets into a 1 MB window
 #endif
   float* stats;           // per-tile partial sums [tile][parts][Cout][2] (sum, sum of squares) of the out_raw
-                          // values for InstanceNorm++ (parts = 4 pixel quadrants, or 2 chunk parities when swapped), or null
+                          // values for InstanceNorm++ (parts = conv_umma_stats_parts(): 2 chunk parities per 256-pixel tile with swapped
+                          // operands, 4 pixel quadrants per 128-pixel tile otherwise), or null
 };
 
 __device__ __forceinline__ float elu1(float v) { return v > 0.0f ? v : expm1f(v); }

@@ -41,6 +41,15 @@ def test_oracle_pose_chain_and_items_match_reference_golden():
         assert 0.2 < r["known"][0].mean() < 0.98                       # holes and obfuscated pixels exist
 
 
+def test_host_pose_chain_matches_reference_golden():
+    """the calibration chain is host code (float64 numpy): it must reproduce the reference's matrices bit for bit, no GPU needed"""
+    import sdpc_b200  # noqa: F401
+    from sdpc_b200 import datasets
+    cam_to_velo, cam_to_pose, poses = cases.n2_calibration()
+    frames, table = datasets.velo_to_world_poses(cam_to_velo, cam_to_pose[0], poses)
+    assert np.array_equal(frames, G["frames"]) and np.array_equal(np.stack([table[f] for f in frames]), G["poses"])
+
+
 @pytest.mark.gpu
 def test_cuda_assembly_matches_oracle_and_golden(tmp_path):
     import sdpc_b200  # noqa: F401

@@ -33,6 +33,21 @@ def test_error_sums_oracle_properties():
     assert (e["depth_l1"] > e["depth_l1_input"]).all() and (e["depth_l1_input"] > 0).all()
 
 
+def test_host_yaw_pitch_grid_matches_reference_expressions():
+    """the sin / cos tables handed to the kernel come from the reference's own yaw / pitch expressions (host, float64)"""
+    import sdpc_b200  # noqa: F401
+    from sdpc_b200.visualization import yaw_pitch_grid
+    yaw, pitch = yaw_pitch_grid(64, 1024)
+    W, H = 1024.0, 64.0
+    x, y = np.meshgrid(np.arange(0, W), np.arange(0, H))
+    x *= 1 / W
+    y *= 1 / H
+    assert np.array_equal(np.pi * (x * 2 - 1), np.broadcast_to(yaw[None, :], (64, 1024)))
+    fov_up, fov_down = 3.0 / 180.0 * np.pi, -25.0 / 180.0 * np.pi
+    fov = abs(fov_down) + abs(fov_up)
+    assert np.array_equal((1.0 - y) * fov - abs(fov_down), np.broadcast_to(pitch[:, None], (64, 1024)))
+
+
 @pytest.mark.gpu
 def test_cuda_points_match_oracle_and_golden():
     import torch
