@@ -85,9 +85,11 @@ SDPC_HD Candidate reproject(double qx, double qy, double qz, float sigma_mod, co
 // Same result as reproject(), cheaper: the log-range (the z-buffer key) is always the exact float64 expression,
 // but each of the two float64 atan2 calls is replaced by a float32 estimate whenever that estimate is provably
 // far from a rounding boundary.  Error budget of the estimate: inputs rounded to fp32 (6e-8 relative each),
-// atan2f <= 2 ulp at pi (5e-7 rad), i.e. < 2e-4 pixel; the guard band is 1e-2 pixel.  Points inside the guard
-// band (about 2 %), non-finite or huge coordinates take the float64 path, so the integers are identical.
-constexpr double kFastGuard = 1e-2;
+// atan2f <= 2 ulp at pi (5e-7 rad), i.e. < 2e-4 pixel; the guard band is 1e-3 pixel (5x the budget).  Points inside
+// the guard band (about 0.2 % per axis), non-finite or huge coordinates take the float64 path, so the integers are
+// identical.  The band is kept narrow because the float64 path is paid per WARP: with a 1e-2 band about half of the
+// warps had at least one lane in it (ncu: the two fallback lines were 28 % of the kernel's instructions).
+constexpr double kFastGuard = 1e-3;
 SDPC_HD Candidate reproject_fast(double qx, double qy, double qz, float sigma_mod, const GeoConsts& g) {
   Candidate c;
   const double xy = qx * qx + qy * qy;
