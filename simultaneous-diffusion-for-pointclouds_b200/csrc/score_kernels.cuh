@@ -236,45 +236,32 @@ __device__ __forceinline__ void store_op8<__nv_bfloat16>(__nv_bfloat16* dst, con
   }
 }
 
-// One thread: 8 channels x kOpPix consecutive pixels of a row (all loads issued before use).  With
-// HALO_ZERO the halo is not written here: the buffer's border is cleared by zero_halo_kernel.
-constexpr int kOpPix = 4;
+// One thread: 8 channels x PIX consecutive pixels of a row (all loads issued before use: 128 bytes in flight per
+// thread, i.e. 4 pixels of fp32 input or 8 pixels of bf16 input).  With HALO_ZERO the halo is not written here: the
+// buffer's border is cleared by zero_halo_kernel.
+template <typename TIn> __host__ __device__ constexpr int op_pix() { return sizeof(TIn) == 2 ? 8 : 4; }
 template <typename T, int MINB, typename TIn = float>
 __global__ void __launch_bounds__(256, MINB)
 to_operand_kernel(const TIn* __restrict__ in, const float* __restrict__ coef, T* __restrict__ out, int N, int H,
                   int W, int C, int P, int mode, int halo, int tf32, size_t lo_off) {
   pdl_sync();
-  const int C8 = C / 8, WS = W / kOpPix;
+  constexpr int PIX = op_pix<TIn>();
+  const int C8 = C / 8, WS = W / PIX;
   const size_t total = (size_t)N * H * WS * C8;
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int c8 = (int)(i % C8);
   size_t t = i / C8;
-  const int w0 = (int)(t % WS) * kOpPix; t /= WS;
+  const int w0 = (int)(t % WS) * PIX; t /= WS;
   const int h = (int)(t % H);
   const int n = (int)(t / H);
   const int Hp = H + 2 * P, Wp = W + 2 * P;
   const TIn* src = in + (((size_t)n * H + h) * W + w0) * C + c8 * 8;
-  float4 a[kOpPix], b[kOpPix];
-  if constexpr (sizeof(TIn) == 2) {                            // bf16 input (conv1 outputs of the plain bf16 arm)
-    uint4 q[kOpPix];
+  uint4 q[PIX], q2[PIX];                                       // raw input words: q (+ q2 for the second half of fp32 input)
 #pragma unroll
-    for (int j = 0; j < kOpPix; ++j) q[j] = *reinterpret_cast<const uint4*>(src + (size_t)j * C);
-#pragma unroll
-    for (int j = 0; j < kOpPix; ++j) {
-      const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&q[j].x));
-      const float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&q[j].y));
-      const float2 f2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&q[j].z));
-      const float2 f3 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&q[j].w));
-      a[j] = make_float4(f0.x, f0.y, f1.x, f1.y);
-      b[j] = make_float4(f2.x, f2.y, f3.x, f3.y);
-    }
-  } else {
-#pragma unroll
-    for (int j = 0; j < kOpPix; ++j) {
-      a[j] = *reinterpret_cast<const float4*>(src + (size_t)j * C);
-      b[j] = *reinterpret_cast<const float4*>(src + (size_t)j * C + 4);
-    }
+  for (int j = 0; j < PIX; ++j) {
+    q[j] = *reinterpret_cast<const uint4*>(src + (size_t)j * C);
+    if constexpr (sizeof(TIn) == 4) q2[j] = *reinterpret_cast<const uint4*>(src + (size_t)j * C + 4);
   }
   float mu[8], ga[8], be[8];
   if (mode == OP_NORM_ELU) {
@@ -290,8 +277,18 @@ to_operand_kernel(const TIn* __restrict__ in, const float* __restrict__ coef, T*
     for (int k = 0; k < 8; ++k) { mu[k] = cf[k * 3]; ga[k] = cf[k * 3 + 1]; be[k] = cf[k * 3 + 2]; }
   }
 #pragma unroll
-  for (int j = 0; j < kOpPix; ++j) {
-    float v[8] = {a[j].x, a[j].y, a[j].z, a[j].w, b[j].x, b[j].y, b[j].z, b[j].w};
+  for (int j = 0; j < PIX; ++j) {
+    float v[8];
+    if constexpr (sizeof(TIn) == 2) {                          // bf16 input (conv1 outputs of the plain bf16 arm)
+      const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&q[j].x));
+      const float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&q[j].y));
+      const float2 f2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&q[j].z));
+      const float2 f3 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&q[j].w));
+      v[0] = f0.x; v[1] = f0.y; v[2] = f1.x; v[3] = f1.y; v[4] = f2.x; v[5] = f2.y; v[6] = f3.x; v[7] = f3.y;
+    } else {
+      v[0] = __uint_as_float(q[j].x); v[1] = __uint_as_float(q[j].y); v[2] = __uint_as_float(q[j].z); v[3] = __uint_as_float(q[j].w);
+      v[4] = __uint_as_float(q2[j].x); v[5] = __uint_as_float(q2[j].y); v[6] = __uint_as_float(q2[j].z); v[7] = __uint_as_float(q2[j].w);
+    }
     if (mode == OP_NORM_ELU) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) v[k] = elu_sel<T>(ga[k] * (v[k] - mu[k]) + be[k], tf32 != 0);

@@ -305,7 +305,7 @@ struct Builder {
     const float* in = (const float*)x.ptr;
     T* o = (T*)out.ptr;
     const int n = N, H = x.H, W = x.W, C = x.C, P = out.pad;
-    const size_t total = (size_t)n * H * (W / kOpPix) * (C / 8);
+    const size_t total = (size_t)n * H * (W / (x.elem == 2 ? op_pix<__nv_bfloat16>() : op_pix<float>())) * (C / 8);
     const size_t lo_off = out.lo_off;
     const int nz = lo_off ? 2 * n : n;                      // both planes get the zero border
     const size_t border = (size_t)nz * ((size_t)(H + 2 * P) * (W + 2 * P) - (size_t)H * W) * (C / 8);
