@@ -38,11 +38,12 @@ constexpr int kBarrierBytes = 256;
 constexpr int kStgFloats = 32 * 32;             // per epilogue warp: 32 pixels x 32 channels, XOR-swizzled float4 slots
 constexpr int kEpiWarps = 8;
 
-template <int N_TILE>
+// CG = 2 (CTA pair driven by one cta_group::2 MMA): each CTA stages only its half of the N-side operand
+template <int N_TILE, int CG = 1>
 struct UmmaCfg {
-  static constexpr int kBBytes = N_TILE * kRowBytes;
+  static constexpr int kBBytes = N_TILE / CG * kRowBytes;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = kSmemBudget / kStageBytes;          // 4 (N=256) / 6 (N=128)
+  static constexpr int kStages = kSmemBudget / kStageBytes;          // 4 (N=256) / 6 (N=128, or N=256 split over a CTA pair)
   static constexpr int kTmemCols = 2 * N_TILE;                       // 512 / 256
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + kBarrierBytes + kEpiWarps * kStgFloats * 4;
 };
@@ -59,18 +60,26 @@ struct UmmaCfg {
 // Cout = 128 layer.  Each CTA fetches half of the shared operand and TMA-multicasts it into both CTAs (tmap_half has the
 // half-sized box), so the L2 -> SM operand traffic drops by a third (a sixth); a stage is released to both producers by
 // a multicast tcgen05.commit (empty barriers count two arrivals).
-template <typename T, int N_TILE, bool SWAP, int COUT, bool CL>
+// CG = 2 (Cout = 256 clusters only, SDPC_CTA2=1): the pair runs ONE tcgen05.mma.cta_group::2 of shape 256 x 256 per k-step
+// instead of two 128 x 256 ones.  M = 256 is the two 128-channel halves (one per CTA, each accumulating in its own
+// TMEM), the 256-pixel activation tile is split in two halves of 128 rows, one in each CTA's shared memory: nothing is
+// multicast, every SM reads 128 + 128 operand rows from its shared memory per k-step instead of 128 + 256, and a stage
+// is 32 KB instead of 48 KB (6 stages instead of 4).  Only the leader (cluster rank 0) issues MMAs; both producers
+// report their bytes to the leader's full barrier, the leader's commits are multicast to the empty / accumulator-full
+// barriers of both CTAs, and the epilogue warps of both CTAs release an accumulator on the leader's barrier.
+template <typename T, int N_TILE, bool SWAP, int COUT, bool CL, int CG = 1>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_a_lo, const __grid_constant__ CUtensorMap tmap_b_lo,
                  const __grid_constant__ CUtensorMap tmap_half, const ConvGeom g, const EpiParams e) {
   static_assert(!CL || SWAP, "clusters are implemented for the swapped-operand variant");
-  using Cfg = UmmaCfg<N_TILE>;
+  static_assert(CG == 1 || (CG == 2 && CL && COUT == 2 * kTileM), "CTA pairs: the two 128-channel halves of a Cout = 256 layer");
+  using Cfg = UmmaCfg<N_TILE, CG>;
   constexpr bool kTf32 = sizeof(T) == 4;
   constexpr int kBK = kRowBytes / (int)sizeof(T);     // channels per k-block: 64 bf16 / 32 tf32
   constexpr int kUmmaK = 32 / (int)sizeof(T);         // 16 / 8 -> 32 bytes per MMA along K
   constexpr int kMmasPerStage = kBK / kUmmaK;         // 4
-  constexpr uint32_t kIdesc = umma_idesc(kTf32 ? 2u : 1u, kTileM, N_TILE);
+  constexpr uint32_t kIdesc = umma_idesc(kTf32 ? 2u : 1u, CG * kTileM, N_TILE);
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -89,13 +98,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     prefetch_tmap(&tmap_b);
     if (g.passes > 1) { prefetch_tmap(&tmap_a_lo); prefetch_tmap(&tmap_b_lo); }
     if (CL) prefetch_tmap(&tmap_half);
-    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, CL ? 2 : 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, kEpiWarps); }
+    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, (CL && CG == 1) ? 2 : 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, CG * kEpiWarps); }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, Cfg::kTmemCols);
-    tmem_relinquish();
+    if constexpr (CG == 2) { tmem_alloc_cg2(tmem_slot, Cfg::kTmemCols); tmem_relinquish_cg2(); }
+    else { tmem_alloc(tmem_slot, Cfg::kTmemCols); tmem_relinquish(); }
   }
   tc_fence_before();
   __syncthreads();
@@ -135,19 +144,28 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               mbar_wait(empty_bar + stage, phase ^ 1);
               uint8_t* sa = smem + stage * Cfg::kStageBytes;
               uint8_t* sb = sa + kABytes;
-              mbar_arrive_expect_tx(full_bar + stage, Cfg::kStageBytes);
-              // activations and weights land in the M-side (128 rows) or N-side (N_TILE rows) slot
-              if constexpr (!CL) {
+              if constexpr (CG == 2) {
+                // own weight half and own half of the activation tile; the leader's barrier counts the bytes of both CTAs
+                if (crank == 0) mbar_arrive_expect_tx(full_bar + stage, 2 * Cfg::kStageBytes);
+                const uint32_t lead_full = mapa_u32(full_bar + stage, 0);
+                tma_load_3d_cg2(sa, mb, lead_full, kc * kBK, mh * kTileM, tap);
+                const int hw = g.BH >= 2 ? 0 : (int)crank * (g.BW / 2), hh = g.BH >= 2 ? (int)crank * (g.BH / 2) : 0;
+                tma_load_4d_cg2(sb, &tmap_half, lead_full, kc * kBK, w0 + hw + g.in_pad + dx, h0 + hh + g.in_pad + dy, n);
+              } else if constexpr (!CL) {
+                // activations and weights land in the M-side (128 rows) or N-side (N_TILE rows) slot
+                mbar_arrive_expect_tx(full_bar + stage, Cfg::kStageBytes);
                 tma_load_4d(SWAP ? sb : sa, ma, full_bar + stage, kc * kBK, w0 + g.in_pad + dx, h0 + g.in_pad + dy, n);
                 tma_load_3d(SWAP ? sa : sb, mb, full_bar + stage, kc * kBK, mh * kTileM, tap);
               } else if constexpr (kMH == 2) {
                 // own weight half; rows [128 r, 128 r + 128) of the shared activation tile, multicast to both CTAs
+                mbar_arrive_expect_tx(full_bar + stage, Cfg::kStageBytes);
                 tma_load_3d(sa, mb, full_bar + stage, kc * kBK, mh * kTileM, tap);
                 const int hw = g.BH >= 2 ? 0 : (int)crank * (g.BW / 2), hh = g.BH >= 2 ? (int)crank * (g.BH / 2) : 0;
                 tma_load_4d_mc(sb + crank * (N_TILE / 2) * kRowBytes, &tmap_half, full_bar + stage, kc * kBK,
                                w0 + hw + g.in_pad + dx, h0 + hh + g.in_pad + dy, n, (uint16_t)3);
               } else {
                 // own activation tile; rows [64 r, 64 r + 64) of the shared weights, multicast to both CTAs
+                mbar_arrive_expect_tx(full_bar + stage, Cfg::kStageBytes);
                 tma_load_4d(sb, ma, full_bar + stage, kc * kBK, w0 + g.in_pad + dx, h0 + g.in_pad + dy, n);
                 tma_load_3d_mc(sa + crank * (kTileM / 2) * kRowBytes, &tmap_half, full_bar + stage, kc * kBK,
                                (int)crank * (kTileM / 2), tap, (uint16_t)3);
@@ -160,14 +178,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    if (lane == 0 && (CG == 1 || crank == 0)) {              // CTA pairs: the leader issues for both SMs
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
       for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++local) {
         const int ab = local & 1;
         const uint32_t acc_phase = (local >> 1) & 1;
-        mbar_wait(acc_empty + ab, acc_phase ^ 1);            // epilogue has drained this accumulator
+        mbar_wait(acc_empty + ab, acc_phase ^ 1);            // epilogue (of both CTAs) has drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + ab * N_TILE;
         for (int k = 0; k < k_iters; ++k) {
@@ -179,13 +197,16 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
           for (int j = 0; j < kMmasPerStage; ++j) {
             // advance 32 bytes along K inside the swizzle span: +2 in the (addr >> 4) field
-            umma_ss<kTf32>(d_tmem, da + (uint64_t)(2 * j), db + (uint64_t)(2 * j), kIdesc, (k | j) != 0);
+            if constexpr (CG == 2) umma_ss_cg2<kTf32>(d_tmem, da + (uint64_t)(2 * j), db + (uint64_t)(2 * j), kIdesc, (k | j) != 0);
+            else umma_ss<kTf32>(d_tmem, da + (uint64_t)(2 * j), db + (uint64_t)(2 * j), kIdesc, (k | j) != 0);
           }
-          if constexpr (CL) umma_commit_mc(empty_bar + stage, (uint16_t)3);   // both producers write this slot
+          if constexpr (CG == 2) umma_commit_cg2(empty_bar + stage, (uint16_t)3);  // the slot is free in both CTAs
+          else if constexpr (CL) umma_commit_mc(empty_bar + stage, (uint16_t)3);   // both producers write this slot
           else umma_commit(empty_bar + stage);               // frees the smem slot when the MMAs retire
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(acc_full + ab);                          // accumulator complete
+        if constexpr (CG == 2) umma_commit_cg2(acc_full + ab, (uint16_t)3);   // both halves of the accumulator complete
+        else umma_commit(acc_full + ab);                     // accumulator complete
       }
     }
   } else {
@@ -261,7 +282,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           if (c0 + 64 >= N_TILE) {                           // this warp's last chunk: its part of the accumulator is read
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(acc_empty + ab);
+            if (lane == 0) {
+              if constexpr (CG == 2) mbar_arrive_cluster(mapa_u32(acc_empty + ab, 0));   // the leader's barrier
+              else mbar_arrive(acc_empty + ab);
+            }
           }
           float v[32];
 #pragma unroll
@@ -359,7 +383,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           if (c0 + 64 >= N_TILE) {                           // this warp's last chunk: its part of the accumulator is read
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(acc_empty + ab);
+            if (lane == 0) {
+              if constexpr (CG == 2) mbar_arrive_cluster(mapa_u32(acc_empty + ab, 0));   // the leader's barrier
+              else mbar_arrive(acc_empty + ab);
+            }
           }
           float4* stg4 = reinterpret_cast<float4*>(stg);
           // thread = pixel (row = lane), registers = 32 channels
@@ -468,10 +495,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();                     // the pair's TMEM is released together: both epilogues are done
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    if constexpr (CG == 2) tmem_dealloc_cg2(tmem_base, Cfg::kTmemCols);
+    else tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
   if (CL) cluster_sync_all();                          // no CTA leaves while its peer may still signal its barriers
 }
@@ -513,10 +542,10 @@ int make_tmap(CUtensorMap* out, void* base, int elem_bytes, int rank, const uint
   return SDPC_OK;
 }
 
-template <typename T, int N_TILE, bool SWAP, int COUT, bool CL>
+template <typename T, int N_TILE, bool SWAP, int COUT, bool CL, int CG = 1>
 static int launch_t(const UmmaConvLaunch& L, cudaStream_t stream) {
-  using Cfg = UmmaCfg<N_TILE>;
-  auto kernel = conv_umma_kernel<T, N_TILE, SWAP, COUT, CL>;
+  using Cfg = UmmaCfg<N_TILE, CG>;
+  auto kernel = conv_umma_kernel<T, N_TILE, SWAP, COUT, CL, CG>;
   static bool attr_set = false;
   static int max_clusters = 0;
   if (!attr_set) {
@@ -568,6 +597,11 @@ bool conv_umma_swap256() {
   static const bool on = [] { const char* v = getenv("SDPC_SWAP256"); return !(v && v[0] == '0'); }();
   return on;
 }
+// Cout = 256 clusters run as CTA pairs on one cta_group::2 MMA when SDPC_CTA2=1 (A/B switch, read once; off by default)
+bool conv_umma_cta2() {
+  static const bool on = [] { const char* v = getenv("SDPC_CTA2"); return v && v[0] == '1'; }();
+  return on;
+}
 // tile_pixels(Cout): pixels per tile the kernel variant for this Cout uses (the host builds the TMA box from it)
 int conv_umma_tile_pixels(int Cout) { return (Cout == 128 || conv_umma_swap256()) ? 256 : 128; }
 // partial-statistics slots a tile leaves per pixel tile (score_types.cuh, EpiParams::stats)
@@ -588,10 +622,12 @@ int conv_umma_launch(const UmmaConvLaunch& L, cudaStream_t stream) {
   if (L.elem_bytes == 2) {
     if (g.Cout == 128) return cl ? launch_t<__nv_bfloat16, 256, true, 128, true>(L, stream) : launch_t<__nv_bfloat16, 256, true, 128, false>(L, stream);
     if (!swapped) return launch_t<__nv_bfloat16, 256, false, 256, false>(L, stream);
+    if (cl && conv_umma_cta2()) return launch_t<__nv_bfloat16, 256, true, 256, true, 2>(L, stream);
     return cl ? launch_t<__nv_bfloat16, 256, true, 256, true>(L, stream) : launch_t<__nv_bfloat16, 256, true, 256, false>(L, stream);
   }
   if (g.Cout == 128) return cl ? launch_t<float, 256, true, 128, true>(L, stream) : launch_t<float, 256, true, 128, false>(L, stream);
   if (!swapped) return launch_t<float, 256, false, 256, false>(L, stream);
+  if (cl && conv_umma_cta2()) return launch_t<float, 256, true, 256, true, 2>(L, stream);
   return cl ? launch_t<float, 256, true, 256, true>(L, stream) : launch_t<float, 256, true, 256, false>(L, stream);
 }
 

@@ -21,6 +21,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/sdpc_b200.h"
@@ -38,6 +39,8 @@ struct StepWorkspace {
   unsigned int* cnt;            // [B*R*W]
   unsigned long long* zpack;    // [B*R*W] (log-range bits with the low key_shift bits replaced by the source id)
   unsigned int* flag;           // [1]   set when a packed winner could not be confirmed -> exact winner pass runs
+  ulonglong2* zkey;             // [B*R*W] SDPC_XVIEW_CAS128=1: {.x = source id, .y = fp64 bits of its log-range}, the
+                                //         lexicographic minimum over (.y, .x) kept by a 128-bit compare-and-swap
   float* shared_img;            // [B,2,H,W] newImages when the caller does not ask for them
   uint8_t* shared_mask;         // [B,H,W]   imageMask & existMask[0] & sky
   size_t cells;
@@ -56,6 +59,7 @@ static size_t workspace_layout(int B, int H, int R, int W, char* base, StepWorks
   size_t o_si = take(cells * 8);
   size_t o_cnt = take(cells * 4);
   size_t o_zpack = take(cells * 8);
+  size_t o_zkey = take(cells * 16);
   size_t o_img = take((size_t)B * 2 * H * W * 4);
   size_t o_msk = take((size_t)B * H * W);
   if (ws) {
@@ -68,6 +72,7 @@ static size_t workspace_layout(int B, int H, int R, int W, char* base, StepWorks
     ws->sum_i = (long long*)(base + o_si);
     ws->cnt = (unsigned int*)(base + o_cnt);
     ws->zpack = (unsigned long long*)(base + o_zpack);
+    ws->zkey = (ulonglong2*)(base + o_zkey);
     ws->flag = (unsigned int*)(base + o_max + 64);
     ws->cells = cells;
   }
@@ -155,6 +160,33 @@ struct ScatterArgs {
   float sigma_mod, min_depth_thr;
   int key_shift;                // low bits of the packed key that hold the source id
 };
+
+// Exact (log-range, source id) minimum in ONE 16-byte word per cell (SDPC_XVIEW_CAS128=1): the nearest candidate and,
+// among candidates at exactly the same depth, the smallest source id - the same winner the packed-key path confirms
+// with its verification pass, without that pass and without the second 64-bit atomicMin.  Values only ever decrease,
+// so a stale (even torn) first read can only cost one extra CAS round, never a wrong skip.
+__device__ __forceinline__ ulonglong2 cas128(ulonglong2* p, ulonglong2 cmp, ulonglong2 val) {
+  ulonglong2 old;
+  asm volatile(
+      "{\n\t.reg .b128 c, s, o;\n\t"
+      "mov.b128 c, {%2, %3};\n\t"
+      "mov.b128 s, {%4, %5};\n\t"
+      "atom.relaxed.gpu.global.cas.b128 o, [%6], c, s;\n\t"
+      "mov.b128 {%0, %1}, o;\n\t}"
+      : "=l"(old.x), "=l"(old.y)
+      : "l"(cmp.x), "l"(cmp.y), "l"(val.x), "l"(val.y), "l"(p)
+      : "memory");
+  return old;
+}
+__device__ __forceinline__ void zkey_min(ulonglong2* p, unsigned long long key, unsigned src_id) {
+  const ulonglong2 mine = make_ulonglong2((unsigned long long)src_id, key);
+  ulonglong2 cur = *p;
+  while (mine.y < cur.y || (mine.y == cur.y && mine.x < cur.x)) {
+    const ulonglong2 old = cas128(p, cur, mine);
+    if (old.x == cur.x && old.y == cur.y) break;
+    cur = old;
+  }
+}
 
 template <int PASS>
 __global__ void __launch_bounds__(256) scatter_kernel(ScatterArgs a) {
@@ -251,6 +283,7 @@ __global__ void __launch_bounds__(256) scatter_kernel(ScatterArgs a) {
 // ------------------------------------------------------------------------------------------
 constexpr int kChunk = 1024;      // source pixels per block (4 per thread)
 
+template <bool CAS>
 __global__ void __launch_bounds__(256) scatter_fast_kernel(ScatterArgs a) {
   const int HW = a.geo.H * a.geo.W;
   const int src_a = blockIdx.y, g = blockIdx.z, b = g * a.A + src_a;
@@ -337,8 +370,12 @@ __global__ void __launch_bounds__(256) scatter_fast_kernel(ScatterArgs a) {
       if (!ok) continue;
       const size_t cell = (size_t)t * grid_cells + (size_t)cd.row * a.geo.W + cd.col;
       const unsigned long long key = (unsigned long long)__double_as_longlong(cd.nd);
-      atomicMin(a.ws.zmin + cell, key);
-      atomicMin(a.ws.zpack + cell, ((key >> a.key_shift) << a.key_shift) | (unsigned long long)src_id);
+      if constexpr (CAS) {
+        zkey_min(a.ws.zkey + cell, key, src_id);
+      } else {
+        atomicMin(a.ws.zmin + cell, key);
+        atomicMin(a.ws.zpack + cell, ((key >> a.key_shift) << a.key_shift) | (unsigned long long)src_id);
+      }
       atomicAdd(a.ws.cnt + cell, 1u);
       atomicAdd((unsigned long long*)(a.ws.sum_d + cell), (unsigned long long)depth_to_fixed(cd.nd));
       atomicAdd((unsigned long long*)(a.ws.sum_i + cell), (unsigned long long)inten_fx);
@@ -401,6 +438,7 @@ struct ResolveArgs {
   StepWorkspace ws;
   GeoConsts geo;
   int A, tgt_first, tgt_count;
+  int cas;                      // nearest depth and winner come from ws.zkey (SDPC_XVIEW_CAS128=1)
   float sigma_mod, corr_coef;
   double allowance;
 };
@@ -424,8 +462,15 @@ __global__ void __launch_bounds__(256) resolve_kernel(ResolveArgs a) {
   double min_d = 0.0;
   float min_i = 0.0f;
   if (cnt > 0) {
-    min_d = __longlong_as_double((long long)a.ws.zmin[cell]);
-    const unsigned w = a.ws.winner[cell];
+    unsigned w;
+    if (a.cas) {
+      const ulonglong2 kv = a.ws.zkey[cell];
+      min_d = __longlong_as_double((long long)kv.y);
+      w = (unsigned)kv.x;
+    } else {
+      min_d = __longlong_as_double((long long)a.ws.zmin[cell]);
+      w = a.ws.winner[cell];
+    }
     const int g = t / a.A;
     const int wa = w / HW, wp = w - wa * HW;
     min_i = a.x[((size_t)(g * a.A + wa) * 2 + 1) * HW + wp];
@@ -471,14 +516,16 @@ correct_kernel(float* __restrict__ x, const float* __restrict__ img, const uint8
 }
 
 // debug dump of the per-cell state (runs before resolve mutates x)
-__global__ void dump_cells_kernel(StepWorkspace ws, int32_t* cnt, int32_t* winner, double* min_d, size_t first, size_t n) {
+__global__ void dump_cells_kernel(StepWorkspace ws, int32_t* cnt, int32_t* winner, double* min_d, size_t first, size_t n,
+                                  int cas) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   size_t k = first + i;
   unsigned cn = ws.cnt[k];
   if (cnt) cnt[k] = (int32_t)cn;
-  if (winner) winner[k] = cn ? (int32_t)ws.winner[k] : -1;
-  if (min_d) min_d[k] = cn ? __longlong_as_double((long long)ws.zmin[k]) : 0.0;
+  const ulonglong2 kv = (cas && cn) ? ws.zkey[k] : make_ulonglong2(0ull, 0ull);
+  if (winner) winner[k] = cn ? (int32_t)(cas ? (unsigned)kv.x : ws.winner[k]) : -1;
+  if (min_d) min_d[k] = cn ? __longlong_as_double((long long)(cas ? kv.y : ws.zmin[k])) : 0.0;
 }
 
 }  // namespace sdpc
@@ -487,6 +534,13 @@ __global__ void dump_cells_kernel(StepWorkspace ws, int32_t* cnt, int32_t* winne
 // C ABI
 // ------------------------------------------------------------------------------------------
 using namespace sdpc;
+
+// SDPC_XVIEW_CAS128=1 (read once): the production scatter keeps the exact (depth, source id) minimum with a 128-bit CAS
+// instead of two 64-bit atomicMins + verification pass.  A/B switch, off by default until measured.
+static bool xview_cas128() {
+  static const bool on = [] { const char* v = getenv("SDPC_XVIEW_CAS128"); return v && v[0] == '1'; }();
+  return on;
+}
 
 static int check_params(const sdpc_step_params* p, const sdpc_step_buffers* b) {
   if (!p || !b) return set_error(SDPC_ERR_ARG, "null params/buffers");
@@ -554,20 +608,27 @@ extern "C" int sdpc_crossview_share(const sdpc_step_params* p, const sdpc_step_b
   const int tcount = p->tgt_count ? p->tgt_count : p->n_views;
   const size_t grid_cells = (size_t)p->big_rows * p->width;
   const size_t first = (size_t)p->tgt_first * grid_cells, n = (size_t)tcount * grid_cells;
+  const bool dbg_candidates = b->dbg_row && b->dbg_col && b->dbg_valid;
+  const bool fast = !dbg_candidates && HW % kChunk == 0;     // candidate-level debug output: legacy full kernel
+  const bool cas = fast && xview_cas128();
   // empty z-buffer: 0xFF.. keys / winners, zero sums and counts (only the target views' grids)
-  SDPC_CUDA(cudaMemsetAsync(ws.zmin + first, 0xFF, n * 8, stream));
-  SDPC_CUDA(cudaMemsetAsync(ws.winner + first, 0xFF, n * 4, stream));
+  if (cas) {
+    SDPC_CUDA(cudaMemsetAsync(ws.zkey + first, 0xFF, n * 16, stream));
+  } else {
+    SDPC_CUDA(cudaMemsetAsync(ws.zmin + first, 0xFF, n * 8, stream));
+    SDPC_CUDA(cudaMemsetAsync(ws.winner + first, 0xFF, n * 4, stream));
+    SDPC_CUDA(cudaMemsetAsync(ws.zpack + first, 0xFF, n * 8, stream));
+    SDPC_CUDA(cudaMemsetAsync(ws.flag, 0, sizeof(unsigned), stream));
+  }
   SDPC_CUDA(cudaMemsetAsync(ws.sum_d + first, 0, n * 8, stream));
   SDPC_CUDA(cudaMemsetAsync(ws.sum_i + first, 0, n * 8, stream));
   SDPC_CUDA(cudaMemsetAsync(ws.cnt + first, 0, n * 4, stream));
-  SDPC_CUDA(cudaMemsetAsync(ws.zpack + first, 0xFF, n * 8, stream));
-  SDPC_CUDA(cudaMemsetAsync(ws.flag, 0, sizeof(unsigned), stream));
 
   ScatterArgs sa;
   sa.x = b->x; sa.sky = b->sky; sa.exist = b->exist;
   sa.to_world = b->to_world; sa.from_world = b->from_world; sa.origins = b->origins;
   sa.cos_az = b->cos_az; sa.sin_az = b->sin_az; sa.cos_el = b->cos_el; sa.sin_el = b->sin_el;
-  sa.dbg_row = (b->dbg_row && b->dbg_col && b->dbg_valid) ? b->dbg_row : nullptr;
+  sa.dbg_row = dbg_candidates ? b->dbg_row : nullptr;
   sa.dbg_col = b->dbg_col; sa.dbg_valid = b->dbg_valid;
   sa.ws = ws;
   sa.geo.h_min = p->h_min; sa.geo.dh = p->dh; sa.geo.big_row_min = p->big_row_min; sa.geo.dv = p->dv;
@@ -580,20 +641,23 @@ extern "C" int sdpc_crossview_share(const sdpc_step_params* p, const sdpc_step_b
   while ((1 << sa.key_shift) < p->group_size * HW) ++sa.key_shift;
   if (p->key_shift_override > sa.key_shift && p->key_shift_override < 52) sa.key_shift = p->key_shift_override;
   dim3 grid((HW + 255) / 256, p->group_size, p->n_views / p->group_size);
-  const bool fast = sa.dbg_row == nullptr && HW % kChunk == 0;     // candidate-level debug output: legacy full kernel
   if (fast) {
     dim3 fgrid(HW / kChunk, p->group_size, p->n_views / p->group_size);
-    scatter_fast_kernel<<<fgrid, 256, 0, stream>>>(sa);
+    if (cas) scatter_fast_kernel<true><<<fgrid, 256, 0, stream>>>(sa);
+    else scatter_fast_kernel<false><<<fgrid, 256, 0, stream>>>(sa);
   } else {
     scatter_kernel<0><<<grid, 256, 0, stream>>>(sa);
   }
   SDPC_CUDA(cudaGetLastError());
-  verify_winner_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(sa);
-  SDPC_CUDA(cudaGetLastError());
-  scatter_kernel<1><<<grid, 256, 0, stream>>>(sa);              // exits immediately unless a winner was unconfirmed
-  SDPC_CUDA(cudaGetLastError());
+  if (!cas) {
+    verify_winner_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(sa);
+    SDPC_CUDA(cudaGetLastError());
+    scatter_kernel<1><<<grid, 256, 0, stream>>>(sa);            // exits immediately unless a winner was unconfirmed
+    SDPC_CUDA(cudaGetLastError());
+  }
   if (b->dbg_cnt || b->dbg_winner || b->dbg_min_d) {
-    dump_cells_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(ws, b->dbg_cnt, b->dbg_winner, b->dbg_min_d, first, n);
+    dump_cells_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(ws, b->dbg_cnt, b->dbg_winner, b->dbg_min_d, first, n,
+                                                                      cas ? 1 : 0);
     SDPC_CUDA(cudaGetLastError());
   }
   ResolveArgs ra;
@@ -602,6 +666,7 @@ extern "C" int sdpc_crossview_share(const sdpc_step_params* p, const sdpc_step_b
   ra.new_images = b->new_images; ra.too_high_out = b->too_high;
   ra.dbg_cnt = b->dbg_cnt; ra.dbg_winner = b->dbg_winner; ra.dbg_min_d = b->dbg_min_d;
   ra.ws = ws; ra.geo = sa.geo; ra.A = p->group_size; ra.tgt_first = p->tgt_first; ra.tgt_count = tcount;
+  ra.cas = cas ? 1 : 0;
   ra.sigma_mod = p->sigma_mod; ra.corr_coef = p->corr_coef; ra.allowance = p->allowance;
   dim3 rgrid((HW + 255) / 256, tcount);
   resolve_kernel<<<rgrid, 256, 0, stream>>>(ra);
