@@ -128,8 +128,11 @@ typedef struct sdpc_step_params {
   int32_t tgt_count;     /* number of target views, else n_views */
   int32_t scalar_div_recip; /* 1: tensor/python-scalar divisions as x*(1/s) like torch's CUDA kernels (matches the
                                reference on a GPU bit-for-bit); 0: IEEE division like torch's CPU kernels */
-  int32_t key_shift_override; /* test hook: bits of the log-range dropped from the packed (depth|source id) key; 0 = auto */
-  int32_t reserved;
+  int32_t key_shift_override; /* test hook (packed-key winner path): bits of the log-range dropped from the packed
+                                 (depth|source id) key; 0 = auto */
+  int32_t winner_mode;   /* how the z-buffer keeps the nearest candidate: 0 = library default (128-bit CAS on
+                            {log-range, source id}; SDPC_XVIEW_CAS128=0 in the environment selects the packed key),
+                            1 = packed 64-bit key + verification pass, 2 = 128-bit CAS.  Same results bit for bit. */
   float step_size;       /* eps: float32 value of step_lr*(sigma/sigmas[-1])**2 (KITTISampling.py:135) */
   float noise_scale;     /* float32 value of np.sqrt(step_size*2) (KITTISampling.py:156) */
   float grad_ref;        /* step_refer */

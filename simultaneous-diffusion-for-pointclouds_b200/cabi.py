@@ -19,7 +19,7 @@ class StepParams(C.Structure):
         ("n_views", C.c_int32), ("group_size", C.c_int32), ("height", C.c_int32), ("width", C.c_int32),
         ("big_rows", C.c_int32), ("variant", C.c_int32), ("share", C.c_int32), ("nan_to_num", C.c_int32),
         ("sky_filter", C.c_int32), ("tgt_first", C.c_int32), ("tgt_count", C.c_int32), ("scalar_div_recip", C.c_int32),
-        ("key_shift_override", C.c_int32), ("reserved", C.c_int32),
+        ("key_shift_override", C.c_int32), ("winner_mode", C.c_int32),
         ("step_size", C.c_float), ("noise_scale", C.c_float), ("grad_ref", C.c_float), ("corr_coef", C.c_float),
         ("sigma_mod", C.c_float), ("min_depth_thr", C.c_float),
         ("allowance", C.c_double), ("h_min", C.c_double), ("dh", C.c_double),

@@ -39,7 +39,7 @@ struct StepWorkspace {
   unsigned int* cnt;            // [B*R*W]
   unsigned long long* zpack;    // [B*R*W] (log-range bits with the low key_shift bits replaced by the source id)
   unsigned int* flag;           // [1]   set when a packed winner could not be confirmed -> exact winner pass runs
-  ulonglong2* zkey;             // [B*R*W] SDPC_XVIEW_CAS128=1: {.x = source id, .y = fp64 bits of its log-range}, the
+  ulonglong2* zkey;             // [B*R*W] default winner path: {.x = source id, .y = fp64 bits of its log-range}, the
                                 //         lexicographic minimum over (.y, .x) kept by a 128-bit compare-and-swap
   float* shared_img;            // [B,2,H,W] newImages when the caller does not ask for them
   uint8_t* shared_mask;         // [B,H,W]   imageMask & existMask[0] & sky
@@ -161,7 +161,7 @@ struct ScatterArgs {
   int key_shift;                // low bits of the packed key that hold the source id
 };
 
-// Exact (log-range, source id) minimum in ONE 16-byte word per cell (SDPC_XVIEW_CAS128=1): the nearest candidate and,
+// Exact (log-range, source id) minimum in ONE 16-byte word per cell (the default winner path): the nearest candidate and,
 // among candidates at exactly the same depth, the smallest source id - the same winner the packed-key path confirms
 // with its verification pass, without that pass and without the second 64-bit atomicMin.  Values only ever decrease,
 // so a stale (even torn) first read can only cost one extra CAS round, never a wrong skip.
@@ -438,7 +438,7 @@ struct ResolveArgs {
   StepWorkspace ws;
   GeoConsts geo;
   int A, tgt_first, tgt_count;
-  int cas;                      // nearest depth and winner come from ws.zkey (SDPC_XVIEW_CAS128=1)
+  int cas;                      // nearest depth and winner come from ws.zkey (128-bit CAS winner path)
   float sigma_mod, corr_coef;
   double allowance;
 };
@@ -535,10 +535,11 @@ __global__ void dump_cells_kernel(StepWorkspace ws, int32_t* cnt, int32_t* winne
 // ------------------------------------------------------------------------------------------
 using namespace sdpc;
 
-// SDPC_XVIEW_CAS128=1 (read once): the production scatter keeps the exact (depth, source id) minimum with a 128-bit CAS
-// instead of two 64-bit atomicMins + verification pass.  A/B switch, off by default until measured.
+// The production scatter keeps the exact (depth, source id) minimum with a 128-bit CAS instead of two 64-bit atomicMins
+// + verification pass (measured 152.9 -> 131.3 us per 8-view step, same results bit for bit) unless
+// SDPC_XVIEW_CAS128=0 (read once) or sdpc_step_params.winner_mode = 1 asks for the packed key.
 static bool xview_cas128() {
-  static const bool on = [] { const char* v = getenv("SDPC_XVIEW_CAS128"); return v && v[0] == '1'; }();
+  static const bool on = [] { const char* v = getenv("SDPC_XVIEW_CAS128"); return !(v && v[0] == '0'); }();
   return on;
 }
 
@@ -610,7 +611,7 @@ extern "C" int sdpc_crossview_share(const sdpc_step_params* p, const sdpc_step_b
   const size_t first = (size_t)p->tgt_first * grid_cells, n = (size_t)tcount * grid_cells;
   const bool dbg_candidates = b->dbg_row && b->dbg_col && b->dbg_valid;
   const bool fast = !dbg_candidates && HW % kChunk == 0;     // candidate-level debug output: legacy full kernel
-  const bool cas = fast && xview_cas128();
+  const bool cas = fast && (p->winner_mode == 2 || (p->winner_mode == 0 && xview_cas128()));
   // empty z-buffer: 0xFF.. keys / winners, zero sums and counts (only the target views' grids)
   if (cas) {
     SDPC_CUDA(cudaMemsetAsync(ws.zkey + first, 0xFF, n * 16, stream));

@@ -63,6 +63,7 @@ class StepRunner:
         # debug="cells": only the per-cell dumps, so the production (compacted, fp32-guarded) scatter runs
         self.debug = None
         self.key_shift_override = 0
+        self.winner_mode = 0          # sdpc_step_params.winner_mode: 0 library default, 1 packed key + verify, 2 128-bit CAS
         if debug:
             R = self.geo.R
             i32 = dict(device=device, dtype=torch.int32)
@@ -85,6 +86,7 @@ class StepRunner:
         p.tgt_first, p.tgt_count = self.tgt_first, self.tgt_count
         p.scalar_div_recip = int(self.scalar_div_recip)
         p.key_shift_override = int(self.key_shift_override)
+        p.winner_mode = int(self.winner_mode)
         p.step_size, p.noise_scale = float(step_size), float(noise_scale)
         p.grad_ref, p.corr_coef, p.sigma_mod = float(grad_ref), float(corr_coef), float(sigma_mod)
         p.min_depth_thr = min_depth_threshold(sigma_mod) if min_depth_filter else -1.0

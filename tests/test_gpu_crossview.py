@@ -46,9 +46,10 @@ def _oracle(kind, case, sigma, setting, dev):
     return ni, x2, th, d
 
 
-def _cuda_step(kind, case, sigma, setting, recip=None, debug=True, key_shift=0):
+def _cuda_step(kind, case, sigma, setting, recip=None, debug=True, key_shift=0, winner_mode=0):
     run = _runner(kind, case, scalar_div_recip=recip, debug=debug)
     run.key_shift_override = key_shift
+    run.winner_mode = winner_mode          # 0 library default (128-bit CAS), 1 packed key + verification, 2 128-bit CAS
     sm = sigma if sigma > 1 else 1
     if kind == "pose":
         p = run.params(0.0, 0.0, 0.0, case["coef"], sm, True, setting == 5, 10.0, False)
@@ -233,17 +234,19 @@ def test_samplers_vs_reference_goldens():
 
 @pytest.mark.parametrize("kind,sigma,setting", CASES)
 def test_production_scatter_equals_full_kernel(kind, sigma, setting):
-    """the compacted / fp32-guarded scatter with the packed winner key (production path) against the full fp64
-    two-pass kernels (selected by candidate-level debug output): every per-cell result must be bit-identical."""
+    """the compacted / fp32-guarded scatter (production path) with either winner mechanism - the 128-bit CAS on
+    {log-range, source id} (default) and the packed 64-bit key + verification pass - against the full fp64 two-pass
+    kernels (selected by candidate-level debug output): every per-cell result must be bit-identical."""
     case = cases.small_multiview(kind)
     x_a, ni_a, run_a = _cuda_step(kind, case, sigma, setting, debug=True)
-    x_b, ni_b, run_b = _cuda_step(kind, case, sigma, setting, debug="cells")
-    for k in ("cnt", "winner", "min_d"):
-        assert torch.equal(run_a.debug[k], run_b.debug[k]), k
-    assert torch.equal(ni_a, ni_b) and torch.equal(x_a, x_b)
+    for mode in (0, 1, 2):
+        x_b, ni_b, run_b = _cuda_step(kind, case, sigma, setting, debug="cells", winner_mode=mode)
+        for k in ("cnt", "winner", "min_d"):
+            assert torch.equal(run_a.debug[k], run_b.debug[k]), (k, mode)
+        assert torch.equal(ni_a, ni_b) and torch.equal(x_a, x_b), mode
     # truncating 44 more bits of the log-range in the packed key makes most packed winners wrong: the verification
     # must catch them and the exact winner pass must restore the same result
-    x_c, ni_c, run_c = _cuda_step(kind, case, sigma, setting, debug="cells", key_shift=50)
+    x_c, ni_c, run_c = _cuda_step(kind, case, sigma, setting, debug="cells", key_shift=50, winner_mode=1)
     for k in ("cnt", "winner", "min_d"):
         assert torch.equal(run_a.debug[k], run_c.debug[k]), k
     assert torch.equal(ni_a, ni_c) and torch.equal(x_a, x_c)
@@ -252,7 +255,8 @@ def test_production_scatter_equals_full_kernel(kind, sigma, setting):
 def test_production_scatter_full_size():
     case = cases.full_multiview()
     x_a, ni_a, run_a = _cuda_step("pose", case, 0.3, 5, debug=True)
-    x_b, ni_b, run_b = _cuda_step("pose", case, 0.3, 5, debug="cells")
-    for k in ("cnt", "winner", "min_d"):
-        assert torch.equal(run_a.debug[k], run_b.debug[k]), k
-    assert torch.equal(ni_a, ni_b) and torch.equal(x_a, x_b)
+    for mode in (1, 2):
+        x_b, ni_b, run_b = _cuda_step("pose", case, 0.3, 5, debug="cells", winner_mode=mode)
+        for k in ("cnt", "winner", "min_d"):
+            assert torch.equal(run_a.debug[k], run_b.debug[k]), (k, mode)
+        assert torch.equal(ni_a, ni_b) and torch.equal(x_a, x_b), mode

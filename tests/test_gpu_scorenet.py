@@ -124,21 +124,24 @@ def test_state_dict_roundtrip_and_ema():
 
 @pytest.mark.parametrize("shape", [(32, 128, 2), (64, 1024, 1)])
 def test_conv_kernel_variants_agree(shape, tmp_path):
-    """The shipped convolution path (swapped operands, 2-CTA clusters with TMA multicast) against its own fallbacks, each in
-    a fresh process: single CTAs (what the bf16x3 arm and odd tile counts use) must be bit-identical - same tiles, same K
-    order - and the unswapped 128-pixel x 256-channel tiling (statistics summed in another order) stays within the arm's tolerance.  32x128 exercises the two-row half box of the multicast, 64x1024 the half-row one."""
+    """The shipped convolution path (swapped operands, 2-CTA clusters: CTA pairs on one cta_group::2 MMA for Cout = 256,
+    TMA multicast of the weights for Cout = 128) against its own fallbacks, each in a fresh process: multicast clusters
+    without cta_group::2 and single CTAs (what the bf16x3 arm and odd tile counts use) must be bit-identical - same
+    tiles, same K order - and the unswapped 128-pixel x 256-channel tiling (statistics summed in another order) stays within the arm's tolerance.  32x128 exercises the two-row half box of the multicast, 64x1024 the half-row one."""
     import subprocess
     import sys
     H, W, B = shape
     probe = os.path.join(os.path.dirname(__file__), "_variant_probe.py")
     outs = {}
-    for tag, env in (("default", {}), ("single_cta", {"SDPC_CLUSTER": "0"}), ("unswapped", {"SDPC_SWAP256": "0", "SDPC_CLUSTER": "0"})):
+    for tag, env in (("default", {}), ("multicast", {"SDPC_CTA2": "0"}), ("single_cta", {"SDPC_CLUSTER": "0"}),
+                     ("unswapped", {"SDPC_SWAP256": "0", "SDPC_CLUSTER": "0"})):
         path = str(tmp_path / (tag + ".npy"))
         e = dict(os.environ)
         e.update(env)
         subprocess.run([sys.executable, probe, "bf16", str(H), str(W), str(B), path], check=True, env=e, timeout=600)
         outs[tag] = np.load(path)
     assert np.isfinite(outs["default"]).all()
+    assert np.array_equal(outs["default"], outs["multicast"])
     assert np.array_equal(outs["default"], outs["single_cta"])
     scale = np.abs(outs["default"]).max()
     dev = np.abs(outs["default"] - outs["unswapped"]).max() / scale
