@@ -265,7 +265,10 @@ def run_b200(args):
     ms_prof = timed(lambda: step(x), args.steps)
     conv_ms, conv_flops, conv_launches = net.profile_collect(x)
     net.set_profiling(x, False)
-    launches_per_step = (net.launch_count(x) - 1) + 1 + 4        # score kernels (minus its memset) + update + 4 share kernels
+    # our kernels per step: the score network's (its launch count includes one memset) + what the step call launches
+    # (update, scatter, resolve, correct; sdpc_step_kernel_launches) [+ the max merge of the sharded flow]
+    step_kernels = run.kernel_launches(p, run.buffers(x, x, x, new_images=new_images)) + (1 if world > 1 else 0)
+    launches_per_step = (net.launch_count(x) - 1) + step_kernels
 
     # ---- end-to-end arm: host buffers, copies inside the timed region ------------------------------
     x_host = g["x"].clone().pin_memory()

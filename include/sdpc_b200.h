@@ -184,6 +184,9 @@ int sdpc_step_read_max(void* workspace, float* out_max, void* stream);
  * re-project, z-buffer (count, sums, nearest), fusion, crop/mirror, correction. */
 int sdpc_crossview_share(const sdpc_step_params* p, const sdpc_step_buffers* b,
                          void* workspace, size_t workspace_bytes, void* stream);
+/* Kernels (not memsets) one sdpc_langevin_reproject_step call with these parameters and buffers launches
+ * (for bench.py's gpu_launches): update [+ scatter, (verify, exact-winner pass), (cell dump), resolve, correct]. */
+int sdpc_step_kernel_launches(const sdpc_step_params* p, const sdpc_step_buffers* b);
 /* update followed by share (when p->share != 0) on one stream. */
 int sdpc_langevin_reproject_step(const sdpc_step_params* p, const sdpc_step_buffers* b,
                                  void* workspace, size_t workspace_bytes, void* stream);

@@ -72,6 +72,7 @@ SYMBOLS = [
     ("sdpc_step_merge_max", _I, [_P, _P, _I, _P]),
     ("sdpc_step_read_max", _I, [_P, _P, _P]),
     ("sdpc_crossview_share", _I, [C.POINTER(StepParams), C.POINTER(StepBuffers), _P, _SZ, _P]),
+    ("sdpc_step_kernel_launches", _I, [C.POINTER(StepParams), C.POINTER(StepBuffers)]),
     ("sdpc_langevin_reproject_step", _I, [C.POINTER(StepParams), C.POINTER(StepBuffers), _P, _SZ, _P]),
     ("sdpc_projection_workspace_bytes", _SZ, [_I, _I]),
     ("sdpc_pointcloud_to_range_image", _I, [C.POINTER(ProjectionParams), _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),

@@ -556,6 +556,24 @@ static int check_params(const sdpc_step_params* p, const sdpc_step_buffers* b) {
   return SDPC_OK;
 }
 
+// the 128-bit CAS winner path serves the production scatter (no candidate-level debug output, H*W a multiple of the chunk)
+static bool use_cas128(const sdpc_step_params* p, const sdpc_step_buffers* b) {
+  const bool dbg_candidates = b->dbg_row && b->dbg_col && b->dbg_valid;
+  const bool fast = !dbg_candidates && (p->height * p->width) % kChunk == 0;
+  return fast && (p->winner_mode == 2 || (p->winner_mode == 0 && xview_cas128()));
+}
+
+extern "C" int sdpc_step_kernel_launches(const sdpc_step_params* p, const sdpc_step_buffers* b) {
+  if (!p || !b) return set_error(SDPC_ERR_ARG, "null params/buffers");
+  int n = 1;                                                   // update
+  if (p->share) {
+    n += 3;                                                    // scatter, resolve, correct
+    if (!use_cas128(p, b)) n += 2;                             // verification + exact-winner pass (launched, exits at once)
+    if (b->dbg_cnt || b->dbg_winner || b->dbg_min_d) n += 1;   // cell dump
+  }
+  return n;
+}
+
 extern "C" size_t sdpc_step_workspace_bytes(int n_views, int height, int width, int big_rows) {
   return workspace_layout(n_views, height, big_rows, width, nullptr, nullptr);
 }
@@ -611,7 +629,7 @@ extern "C" int sdpc_crossview_share(const sdpc_step_params* p, const sdpc_step_b
   const size_t first = (size_t)p->tgt_first * grid_cells, n = (size_t)tcount * grid_cells;
   const bool dbg_candidates = b->dbg_row && b->dbg_col && b->dbg_valid;
   const bool fast = !dbg_candidates && HW % kChunk == 0;     // candidate-level debug output: legacy full kernel
-  const bool cas = fast && (p->winner_mode == 2 || (p->winner_mode == 0 && xview_cas128()));
+  const bool cas = use_cas128(p, b);
   // empty z-buffer: 0xFF.. keys / winners, zero sums and counts (only the target views' grids)
   if (cas) {
     SDPC_CUDA(cudaMemsetAsync(ws.zkey + first, 0xFF, n * 16, stream));

@@ -120,6 +120,12 @@ class StepRunner:
                                                    self.workspace.numel(), self._stream())
         cabi.check(self.lib, st, "sdpc_langevin_reproject_step")
 
+    def kernel_launches(self, p, b):
+        """kernels one step() call with these parameters launches (bench.py's gpu_launches)."""
+        n = self.lib.sdpc_step_kernel_launches(C.byref(p), C.byref(b))
+        cabi.check(self.lib, min(n, 0), "sdpc_step_kernel_launches")
+        return int(n)
+
     def update_only(self, p, b):
         st = self.lib.sdpc_langevin_update(C.byref(p), C.byref(b), _ptr(self.workspace), self.workspace.numel(),
                                            self._stream())

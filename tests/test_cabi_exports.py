@@ -49,3 +49,20 @@ def test_product_path_fails_loudly_without_cuda():
     x = torch.zeros(1, 2, 16, 64)
     with pytest.raises(cabi.SdpcError):
         anneal_Langevin_dynamics_inpainting(x, x, torch.zeros_like(x).int(), None, [1.0])
+
+
+def test_step_kernel_launches_follow_the_winner_mode():
+    """host-only query behind bench.py's gpu_launches: update + (scatter, resolve, correct), + verification and
+    exact-winner pass only for the packed-key mode, + the cell dump when cell-level debug output is requested."""
+    import ctypes as C
+    lib = cabi.load()
+    p, b = cabi.StepParams(), cabi.StepBuffers()
+    p.height, p.width, p.share = 64, 1024, 1
+    assert lib.sdpc_step_kernel_launches(C.byref(p), C.byref(b)) == (4 if os.environ.get("SDPC_XVIEW_CAS128") != "0" else 6)
+    p.winner_mode = 2
+    assert lib.sdpc_step_kernel_launches(C.byref(p), C.byref(b)) == 4
+    p.winner_mode = 1
+    assert lib.sdpc_step_kernel_launches(C.byref(p), C.byref(b)) == 6
+    p.share = 0
+    assert lib.sdpc_step_kernel_launches(C.byref(p), C.byref(b)) == 1
+    assert lib.sdpc_step_kernel_launches(None, None) < 0
