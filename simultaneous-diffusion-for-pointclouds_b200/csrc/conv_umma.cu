@@ -13,6 +13,8 @@
 // Weights: repacked to [tap][Cout][Cin] (K-major), 3-D TMA box {BK, 128, 1}.
 // Clusters: CTAs run in pairs on tiles that share one operand (the activation tile for the two channel halves, the
 //   weights for two neighbouring pixel tiles); each CTA fetches half of it and TMA-multicasts it into both.
+//   Cout = 256: the pair is driven by ONE tcgen05.mma.cta_group::2 (M = 256 = both channel halves) issued by the leader,
+//   the activation tile split between the two CTAs' shared memories instead of multicast (template parameter CG = 2).
 // Accumulator: fp32 in TMEM, double buffered (2 x 256 columns) so the epilogue of tile i overlaps the MMAs of
 //   tile i+1.  Persistent CTAs, one per SM, static round-robin tiles.
 // Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane) + TMEM allocator,

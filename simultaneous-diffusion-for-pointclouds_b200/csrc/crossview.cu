@@ -4,16 +4,18 @@
 //   a-4 LiDARGen/models/KITTISampling.py:137-490  (pose matrices)
 //   a-5 LiDARGen/models/__init__.py:240-582       (translations)
 // (about 25*B small kernels + 3*B radix sorts + 6*B sparse->dense scatters per step) with four
-// launches: update, scatter (z-buffer build), winner, resolve.
+// launches: update, scatter (z-buffer build incl. the nearest candidate), resolve, correct.
 //
 //   update  : x <- x + eps*g + rho*(-mask*(x-ref)) + s*z ; block max of |x0| -> atomicMax
 //   scatter : one thread per SOURCE pixel: decode range (fp32), un-project (fp64), to world,
 //             then for every target view of the group: from-world, spherical re-projection,
 //             validity, and order-independent atomics into the target's R x W grid:
-//             atomicMin on the fp64 bit pattern of the log-range (nearest depth),
-//             atomicAdd count / fixed-point depth sum / fixed-point intensity sum.
-//   winner  : same traversal; the candidate whose log-range equals the grid minimum claims the
-//             pixel (atomicMin on the source id -> deterministic tie break).
+//             atomicAdd count / fixed-point depth sum / fixed-point intensity sum, and the nearest
+//             candidate as {fp64 bits of the log-range, source id}: lexicographic minimum by a
+//             128-bit compare-and-swap (deterministic tie break: smallest source id).
+//   winner  : legacy / cross-check paths only (candidate-level debug output, winner_mode = 1): 64-bit
+//             atomicMin on the key, then the candidate whose log-range equals the grid minimum claims
+//             the pixel, either through a packed key + verification or a second traversal.
 //   resolve : one thread per OUTPUT pixel: average / controlled average, crop + mirror for
 //             negative ranges, existMask, correction, in-place x update, optional newImages.
 //
