@@ -9,6 +9,10 @@ namespace sdpc {
 // Records a thread-local message and returns `code` (sdpc_last_error() reads it back).
 int set_error(int code, const char* fmt, ...);
 
+// Function attributes (opt-in shared memory, cluster occupancy) belong to a device, not to the process: one-time
+// set-up is remembered per device ordinal so that a process driving several GPUs (DataParallel-style) stays correct.
+constexpr int kMaxDevices = 64;
+
 // Kernel launch with programmatic dependent launch (PDL): the kernel may start while its predecessor on the stream is
 // still draining; every kernel launched this way executes pdl_sync() (griddepcontrol.wait) before its first global
 // memory access, so data and buffer-reuse hazards are ordered exactly as without PDL while launch latency and the

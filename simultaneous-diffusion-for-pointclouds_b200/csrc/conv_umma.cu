@@ -548,8 +548,13 @@ template <typename T, int N_TILE, bool SWAP, int COUT, bool CL, int CG = 1>
 static int launch_t(const UmmaConvLaunch& L, cudaStream_t stream) {
   using Cfg = UmmaCfg<N_TILE, CG>;
   auto kernel = conv_umma_kernel<T, N_TILE, SWAP, COUT, CL, CG>;
-  static bool attr_set = false;
-  static int max_clusters = 0;
+  static bool attr_set_dev[kMaxDevices] = {};
+  static int max_clusters_dev[kMaxDevices] = {};
+  int dev = 0;
+  SDPC_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= kMaxDevices) return set_error(SDPC_ERR_UNSUPPORTED, "conv_umma: device ordinal %d >= %d", dev, kMaxDevices);
+  bool& attr_set = attr_set_dev[dev];
+  int& max_clusters = max_clusters_dev[dev];
   if (!attr_set) {
     SDPC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     if (CL) {

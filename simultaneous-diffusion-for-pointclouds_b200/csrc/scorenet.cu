@@ -748,10 +748,13 @@ struct Builder {
       const float *wg = h->P("end_conv.weight"), *bs = h->P("end_conv.bias"), *sg = h->P("sigmas");
       const int n = N, fast = h->cfg.precision != SDPC_PREC_FP32;
       push([=](cudaStream_t s, const float*, const int64_t* labels, float* out) -> int {
-        static bool attr_set = false;
-        if (!attr_set) {
+        static bool attr_set[kMaxDevices] = {};
+        int dev = 0;
+        SDPC_CUDA(cudaGetDevice(&dev));
+        if (dev < 0 || dev >= kMaxDevices) return set_error(SDPC_ERR_UNSUPPORTED, "end_conv: device ordinal %d >= %d", dev, kMaxDevices);
+        if (!attr_set[dev]) {
           SDPC_CUDA(cudaFuncSetAttribute(end_conv_norm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kEndSmemBytes));
-          attr_set = true;
+          attr_set[dev] = true;
         }
         const size_t strips = (size_t)n * (H / kEndRows) * (W / 8);
         const int wpb = kEndThreads / 32;
@@ -831,6 +834,8 @@ extern "C" int sdpc_score_destroy(sdpc_score_t* h) {
   if (!h) return SDPC_OK;
   h->plan.reset_graph();
   if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
+  for (auto& r : h->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   for (auto& p : h->params) if (p.dev) cudaFree(p.dev);
   for (auto& kv : h->convs) { if (kv.second.w_tc) cudaFree(kv.second.w_tc); if (kv.second.w_tc_lo) cudaFree(kv.second.w_tc_lo); if (kv.second.w_simt) cudaFree(kv.second.w_simt); }
   delete h;
@@ -989,9 +994,13 @@ extern "C" int sdpc_score_profile_collect(sdpc_score_t* h, double* total_ms, dou
   const char* dump = getenv("SDPC_PROFILE_DUMP");             // per-launch csv (name, flops, ms) for tools/conv_layers.py
   FILE* df = dump ? fopen(dump, "a") : nullptr;
   for (auto& r : h->prof) {
-    SDPC_CUDA(cudaEventSynchronize(r.b));
     float t = 0.0f;
-    SDPC_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
+    cudaError_t ce = cudaEventSynchronize(r.b);
+    if (ce == cudaSuccess) ce = cudaEventElapsedTime(&t, r.a, r.b);
+    if (ce != cudaSuccess) {
+      if (df) fclose(df);
+      return set_error(SDPC_ERR_CUDA, "profile_collect: %s", cudaGetErrorString(ce));
+    }
     if (df) fprintf(df, "%s,%.0f,%.6f\n", r.name.c_str(), r.flops, t);
     ms += t;
     fl += r.flops;
