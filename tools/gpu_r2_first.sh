@@ -1,0 +1,28 @@
+#!/bin/bash
+# First box call of round 2 (about 6 box-minutes): the evidence the last session of round 1 could not collect.
+#   1. full test suite, smoke, both bench arms (plain runs)
+#   2. ncu launch list of the bench command (per-kernel share of the step)
+#   3. ncu --set full of the CTA-pair convolution (CG = 2) and, for comparison, the multicast variant (SDPC_CTA2=0)
+#   4. ncu --set full of the cross-view step kernels with the 128-bit CAS winners
+cd "${GRAFT_REPO_ROOT:-/root/repo}"
+mkdir -p gpurun_out
+run() { name=$1; shift; timeout 900 "$@" > gpurun_out/$name.log 2>&1; rc=$?; echo "$name rc=$rc"; tail -n ${TAILN:-1} gpurun_out/$name.log | cut -c1-300; return $rc; }
+TAILN=3 run r2_tests python -m pytest tests -m gpu -x -q
+run r2_smoke python __graft_entry__.py --smoke
+run r2_bench_ref python bench.py --impl reference --steps 3 --warmup 1
+run r2_bench python bench.py
+CMD="python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-parity-arm"
+if run r2_bench_plain $CMD; then
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 800 -c 300 --csv --log-file gpurun_out/r2_launches.csv $CMD > gpurun_out/r2_ncu_launches.log 2>&1; echo "ncu launches rc=$?"
+fi
+LAY="python tools/conv_layers.py 8 bf16 1"
+if run r2_layers $LAY; then
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_umma -s 250 -c 6 -o gpurun_out/r2_prof_conv_cg2 $LAY > gpurun_out/r2_ncu_conv_cg2.log 2>&1; echo "ncu conv cg2 rc=$?"
+  SDPC_CTA2=0 timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_umma -s 250 -c 6 -o gpurun_out/r2_prof_conv_mc $LAY > gpurun_out/r2_ncu_conv_mc.log 2>&1; echo "ncu conv multicast rc=$?"
+fi
+STEP="python tools/time_step.py"
+if run r2_time_step $STEP; then
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:"scatter_fast|resolve_kernel|langevin_update|correct_kernel" -s 8 -c 4 -o gpurun_out/r2_prof_step $STEP > gpurun_out/r2_ncu_step.log 2>&1; echo "ncu step rc=$?"
+fi
+for B in 1 2 4; do python tools/quick_time.py $B bf16 2>&1 | grep forward; done > gpurun_out/r2_small_batches.log
+cat gpurun_out/r2_small_batches.log
