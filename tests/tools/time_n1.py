@@ -1,6 +1,6 @@
 """Row N1 timing: CUDA point_cloud_to_range_image (device-resident points, CUDA events) next to the numpy oracle port."""
 import ctypes as C, math, os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import torch
 import sdpc_b200  # noqa

@@ -1,6 +1,6 @@
 """Row N3 timing: CUDA range image -> point cloud and error sums (device-resident, CUDA events) next to the numpy oracle."""
 import os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import torch
 import sdpc_b200  # noqa

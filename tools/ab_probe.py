@@ -19,16 +19,14 @@ def run(prefix, time_b):
     import torch
     import sdpc_b200  # noqa: F401
     from sdpc_b200.scorenet import NCSN_LiDAR_small
-    from oracle.weights import make_state_dict
     NS = argparse.Namespace
     dev = "cuda:0"
-    sd = make_state_dict(num_classes=10)
     for prec, H, W, B in CASES:
         cfg = NS(data=NS(logit_transform=False, rescaled=False, channels=2, image_size=H, image_width=W),
                  model=NS(ngf=128, num_classes=10, nonlinearity="elu", normalization="InstanceNorm++",
                           sigma_dist="geometric", sigma_begin=50, sigma_end=0.01, spec_norm=False), device=dev)
+        torch.manual_seed(1234)      # the module's own random init, identical in every process
         net = NCSN_LiDAR_small(cfg, precision=prec).to(dev)
-        net.load_state_dict(sd)
         g = torch.Generator().manual_seed(5)
         x = torch.rand(B, 2, H, W, generator=g).to(dev)
         y = torch.arange(B, device=dev, dtype=torch.long) % 10

@@ -11,7 +11,6 @@ import sdpc_b200  # noqa: F401
 from sdpc_b200 import cabi
 from sdpc_b200.scorenet import NCSN_LiDAR_small
 from sdpc_b200.step import StepRunner
-from oracle.weights import make_state_dict
 from tests.golden import cases
 
 N = argparse.Namespace
@@ -38,12 +37,11 @@ def main():
     cfg = N(data=N(logit_transform=False, rescaled=False, channels=2, image_size=H, image_width=W),
             model=N(ngf=128, num_classes=232, nonlinearity="elu", normalization="InstanceNorm++", sigma_dist="geometric",
                     sigma_begin=50, sigma_end=0.01, spec_norm=False), device=DEV)
-    sd = make_state_dict()
+    torch.manual_seed(1234)          # random-init weights of the module itself (timing only)
     x = torch.rand(B, 2, H, W, device=DEV)
     y = torch.full((B,), 100, device=DEV, dtype=torch.long)
     for prec in precs:
         net = NCSN_LiDAR_small(cfg, precision=prec).to(DEV)
-        net.load_state_dict(sd)
         ms = timeit(lambda: net(x, y), warm=2, it=3 if prec == "fp32" else 10)
         fl = net.flops_per_view(x) * B
         print(f"forward {prec} B={B}: {ms:.3f} ms  -> {B / ms * 1e3:.1f} view-fwd/s, {fl / ms / 1e9:.1f} TFLOP/s, launches={net.launch_count(x)}", flush=True)
