@@ -1,9 +1,9 @@
 """A/B aid for kernel-variant switches that are read once per process (SDPC_CTA2, SDPC_CLUSTER, ...): one process per
 setting saves score-network outputs on fixed inputs and prints the forward time; `compare` checks two runs bit for bit.
 
-    SDPC_CTA2=1 python tools/ab_probe.py run gpurun_out/ab_cta2
+    SDPC_X3_CLUSTER=1 python tools/ab_probe.py run gpurun_out/ab_x3cl
     python tools/ab_probe.py run gpurun_out/ab_def
-    python tools/ab_probe.py compare gpurun_out/ab_def gpurun_out/ab_cta2
+    python tools/ab_probe.py compare gpurun_out/ab_def gpurun_out/ab_x3cl
 """
 import argparse
 import os
@@ -12,7 +12,7 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 
-CASES = [("bf16", 32, 128, 2), ("bf16", 64, 1024, 1), ("tf32", 32, 128, 2)]
+CASES = [("bf16", 32, 128, 2), ("bf16", 64, 1024, 1), ("tf32", 32, 128, 2), ("bf16x3", 32, 128, 2), ("bf16x3", 64, 1024, 1)]
 
 
 def run(prefix, time_b):
