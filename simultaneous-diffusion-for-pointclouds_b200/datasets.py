@@ -9,6 +9,7 @@ kitti360_im_simultenous_densification.py pick other poses / origins but run the 
   truth.  The points stay on the GPU from the .bin bytes to the finished images.
 * `KITTI360Line`         -- file-backed `Dataset` with the reference's item layout for the Line configuration (root path as
   an argument instead of the hard-coded /data/KITTI-360).
+* `ItemBatches`          -- consecutive items collated into the batch tuple the runners unpack (`b200.data_root` in the yml).
 
 CUDA only: there is no CPU fallback."""
 import ctypes as C
@@ -121,3 +122,23 @@ class KITTI360Line(torch.utils.data.Dataset):
                              self.Tr_pose_world[self.frames[wanted]], None, self.return_remission, self.rowMax,
                              self.colMax, self.device)
         return item + (int(frame),)
+
+
+class ItemBatches:
+    """`batch(i)`: items [i*B, (i+1)*B) of a multi-view dataset stacked the way the DataLoader's default collate hands them
+    to the runners (ncsn_runner_kitti_simultaneous.py:543-556 unpacks exactly this tuple).  Batches are walked in order;
+    the reference's `MySampler` shuffles the batch order even with random=False (SURVEY.md 8a quirk ix)."""
+
+    def __init__(self, dataset, batch_size):
+        self.dataset, self.batch_size = dataset, int(batch_size)
+
+    def __len__(self):
+        return len(self.dataset) // self.batch_size
+
+    def batch(self, index):
+        if not 0 <= index < len(self):
+            raise IndexError(f"batch {index} outside [0, {len(self)})")
+        items = [self.dataset[i] for i in range(index * self.batch_size, (index + 1) * self.batch_size)]
+        cols = list(zip(*items))
+        out = [torch.from_numpy(np.stack([np.asarray(v) for v in c])) for c in cols[:-1]]
+        return tuple(out) + (torch.as_tensor(np.asarray(cols[-1])),)

@@ -5,7 +5,7 @@ sampler) and LiDARGen/runners/ncsn_runner_AllForOne.py:466-1000 (Inpainting.yml 
 translation sampler): checkpoint + EMA loading, existTotal mask preprocessing, the `doThis` ablation loop
 with the reference's hard-coded hyper-parameters, output post-processing and .npy naming.  It is a boundary
 row of SURVEY.md 8 (keep the API), not a kernel target; the data source is the synthetic generator unless
-`b200.data_root` points at KITTI-360 (the dataset readers themselves are out of scope).
+`b200.data_root` points at KITTI-360 (Line configuration: `datasets.KITTI360Line`, row N2 of SURVEY 8f).
 """
 import logging
 import os
@@ -96,6 +96,13 @@ class _Base:
 
     def dataset(self, mode):
         cfg = self.config
+        root = getattr(getattr(cfg, "b200", None), "data_root", None)
+        if root:                                            # KITTI-360 on disk: row N2's GPU dataset assembly
+            if mode != "line":
+                raise NotImplementedError("b200.data_root is wired for the Line configuration (KITTI360_im_8batch); the "
+                                          "AllForOne / densification pose selections are arguments of datasets.assemble_view")
+            from .datasets import ItemBatches, KITTI360Line
+            return ItemBatches(KITTI360Line(root, cfg, device=cfg.device), cfg.sampling.batch_size)
         return SyntheticMultiView(cfg.data.image_size, cfg.data.image_width, cfg.sampling.batch_size,
                                   cfg.sampling.actualBatchSize, mode=mode, seed=self.args.seed)
 

@@ -99,3 +99,30 @@ def test_cuda_assembly_matches_oracle_and_golden(tmp_path):
     assert int((np.abs(item[0][0] - G["i5:real"][0]) > 1e-12).sum()) <= 8
     with pytest.raises(RuntimeError):
         ds.load_scan(99999)
+
+
+def test_item_batches_collate_like_the_dataloader():
+    """CPU: `ItemBatches.batch(i)` stacks consecutive items into the tuple the runners unpack (stub dataset: the CUDA
+    assembly itself is covered by the gpu test above)."""
+    import torch
+    import sdpc_b200  # noqa: F401
+    from sdpc_b200 import datasets
+
+    class Stub:
+        def __len__(self):
+            return 7
+
+        def __getitem__(self, i):
+            f = np.full
+            return (f((2, 4, 8), float(i)), f((2, 4, 8), i % 2 == 0), f((1, 4, 8), True), f((1, 4, 8), float(i)),
+                    f((1, 4, 4), float(i)), f((1, 4, 4), -float(i)), f((2, 4, 8), 0.5 * i), f((4, 4), float(i)), 100 + i)
+
+    b = datasets.ItemBatches(Stub(), 3)
+    assert len(b) == 2
+    real, known, notsky, index, to_w, from_w, goal, to_og, frames = b.batch(1)
+    assert real.shape == (3, 2, 4, 8) and real.dtype == torch.float64 and known.dtype == torch.bool
+    assert notsky.shape == (3, 1, 4, 8) and index.shape == (3, 1, 4, 8) and goal.shape == (3, 2, 4, 8)
+    assert to_w.shape == (3, 1, 4, 4) and from_w.shape == (3, 1, 4, 4) and to_og.shape == (3, 4, 4)
+    assert frames.tolist() == [103, 104, 105] and real[:, 0, 0, 0].tolist() == [3.0, 4.0, 5.0]
+    with pytest.raises(IndexError):
+        b.batch(2)
