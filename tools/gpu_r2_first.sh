@@ -33,3 +33,6 @@ SDPC_X3_CLUSTER=1 python tools/quick_time.py 8 bf16x3 2>&1 | grep forward | tee 
 rm -f gpurun_out/ab_*.npy
 for B in 1 2 4; do python tools/quick_time.py $B bf16 2>&1 | grep forward; done > gpurun_out/r2_small_batches.log
 cat gpurun_out/r2_small_batches.log
+# BASELINE config 5 on one GPU: 16 / 32 / 64 views in groups of 8 (forward + step per call)
+for B in 16 32 64; do python tools/quick_time.py $B bf16 8 2>&1 | grep -E "forward|step"; done > gpurun_out/r2_view_sweep.log
+cat gpurun_out/r2_view_sweep.log

@@ -46,8 +46,9 @@ def main():
         fl = net.flops_per_view(x) * B
         print(f"forward {prec} B={B}: {ms:.3f} ms  -> {B / ms * 1e3:.1f} view-fwd/s, {fl / ms / 1e9:.1f} TFLOP/s, launches={net.launch_count(x)}", flush=True)
         del net
-    case = cases.full_multiview(B=B, A=B)
-    run = StepRunner(case["x"].shape, DEV, case["refer"], case["mask"], case["sky"], case["exist"], B,
+    A = int(sys.argv[3]) if len(sys.argv) > 3 else min(B, 8)          # views per group (B / A groups in the call)
+    case = cases.full_multiview(B=B, A=A)
+    run = StepRunner(case["x"].shape, DEV, case["refer"], case["mask"], case["sky"], case["exist"], A,
                      cabi.SDPC_VARIANT_POSE, to_world=case["toWorld"], from_world=case["fromWorld"])
     xx = case["x"].to(DEV)
     g = torch.randn_like(xx)
@@ -55,7 +56,7 @@ def main():
     p = run.params(1e-5, 4e-3, 1.0, 0.01, 1.0, True, True, 10.0, False)
     b = run.buffers(xx, g, z)
     ms = timeit(lambda: run.step(p, b), warm=3, it=20)
-    print(f"langevin+crossview step B=A={B}: {ms * 1e3:.1f} us", flush=True)
+    print(f"langevin+crossview step B={B} A={A}: {ms * 1e3:.1f} us", flush=True)
 
 
 if __name__ == "__main__":
