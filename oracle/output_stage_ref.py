@@ -5,8 +5,11 @@
   make_golden_n3.py executes the reference's own statements (read from /root/reference at generation time) and the
   committed fixture is compared with this restatement in tests/test_n3_output_stage.py.
 * `error_sums_ref` follows cell 1 of MeasureResults/QuantifyingNotebookSynthesis_Line.ipynb (GTdistance / InputDist
-  un-log, `inputMask`, the `distanceError` ... `totalDistanceInput` sums with `mask = np.ones_like(mask)`).  The
-  notebook reads files of a finished run and cannot be executed here: PARITY UNPINNED for this function.
+  un-log, `inputMask`, the `distanceError` ... `totalDistanceInput` sums with `mask = np.ones_like(mask)`).  Pinned:
+  tests/golden/make_golden_n3_errors.py writes a synthetic run directory in the reference runner's naming / layout and
+  executes the CELL'S OWN SOURCE on it (stand-in cv2 for the classical baselines this repo does not restate); the totals
+  it leaves (n3_errors.npz) are bit-identical to this restatement summed in the cell's order
+  (tests/test_n3_output_stage.py::test_error_sums_oracle_matches_reference_notebook_golden).
 """
 import numpy as np
 

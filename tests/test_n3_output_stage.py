@@ -1,5 +1,6 @@
 """Row N3: range image -> xyz point cloud and the evaluation error sums.
-CPU: the numpy oracle against the golden fixture produced by executing the reference's own statements.
+CPU: the numpy oracle against the golden fixtures produced by executing the reference's own statements (visualize_tensor
+for the points, the evaluation notebook's cell for the error sums).
 GPU: the CUDA path (through the C ABI / host mirror) against the oracle and the golden fixture."""
 import os
 
@@ -18,6 +19,32 @@ def test_oracle_matches_reference_golden():
     assert np.array_equal(np.packbits(mask), G["mask"])
     assert np.array_equal(xyz[::37], G["xyz_every37"])                 # same statements, same dtypes: bit-exact
     assert np.array_equal(xyz.sum(0), G["xyz_sum"])
+
+
+def test_error_sums_oracle_matches_reference_notebook_golden():
+    """`error_sums_ref` against the totals the reference's own notebook cell (QuantifyingNotebookSynthesis_Line.ipynb, cell 1)
+    left behind when tests/golden/make_golden_n3_errors.py executed it on a synthetic run directory: 42 views in 6 groups
+    of 7, settings 0..6 (setting s keeps min(s + 2, 7) views per group).  The cell adds its float32 sums into float64
+    accumulators group by group; summing the restatement's per-view values in the same order is bit-identical."""
+    from tests.golden.make_golden_n3_errors import BATCH, GROUP, SETTINGS, case_arrays, views_kept
+    E = np.load(os.path.join(os.path.dirname(__file__), "golden", "n3_errors.npz"))
+    gt, inp, preds = case_arrays(int(E["seed"]))
+    groups = BATCH // GROUP
+    names = {"depth_l1": "totalDistanceError", "intensity_l1": "totalIntensityError",
+             "depth_l1_input": "totalDistanceErrorInput", "intensity_l1_input": "totalIntensityErrorInput",
+             "depth_sum_input": "totalDistanceInput"}
+    for s in range(SETTINGS):
+        k = views_kept(s)
+        idx = np.array([GROUP * g + j for g in range(groups) for j in range(k)])
+        e = osr.error_sums_ref(preds[s], gt[idx], inp[idx])
+        for ours, theirs in names.items():
+            got = np.zeros(GROUP)
+            for g in range(groups):                                   # the cell's accumulation order
+                got[:k] += e[ours].reshape(groups, k)[g]
+            assert np.array_equal(got, E[theirs][s]), (s, ours)
+    full = osr.error_sums_ref(preds[SETTINGS - 1], gt, inp)            # last setting keeps all 7 views of every group
+    assert np.array_equal(full["pixels"].reshape(groups, GROUP).sum(0), E["totalPixels"])
+    assert np.array_equal(full["input_pixels"].reshape(groups, GROUP).sum(0), E["totalInputPixels"])
 
 
 def test_error_sums_oracle_properties():
