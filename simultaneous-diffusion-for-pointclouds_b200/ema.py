@@ -29,8 +29,10 @@ class EMAHelper(object):
         _, params = _trainable(module)
         keep = self.mu
         for name, p in params:
-            # (1 - mu) * theta + mu * shadow, one rounding per product like the reference expression
-            self.shadow[name] = torch.add(p.detach() * (1. - keep), self.shadow[name], alpha=keep)
+            # (1 - mu) * theta + mu * shadow with one rounding per product and one for the sum, like the reference
+            # expression (models/ema.py:20); torch.add(..., alpha=mu) would fuse the second product into the sum
+            fresh, old = p.detach() * (1. - keep), self.shadow[name] * keep
+            self.shadow[name] = fresh + old
 
     @torch.no_grad()
     def ema(self, module):

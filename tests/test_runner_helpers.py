@@ -1,0 +1,59 @@
+"""CPU: the runner-layer helpers around the hot path against golden vectors produced by the reference's own
+statements / module (tests/golden/make_golden_runner.py): existTotal mask preprocessing, the [2B,3,H,W] layout of the
+saved arrays, and the EMA helper that turns a checkpoint's shadow weights into the sampling weights."""
+import argparse
+import os
+
+import numpy as np
+import torch
+
+import sdpc_b200  # noqa: F401
+from sdpc_b200 import runner
+from sdpc_b200.ema import EMAHelper
+from tests.golden.make_golden_runner import exist_counts, perturb, sample_images, small_module
+
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "runner_helpers.npz"))
+NS = argparse.Namespace
+
+
+def test_exist_mask_preprocessing_matches_reference_statements(tmp_path):
+    path = str(tmp_path / "existTotal.npy")
+    np.save(path, exist_counts())
+    cfg = NS(data=NS(image_size=64, image_width=1024), device="cpu", b200=NS(exist_mask=path))
+    m = runner.exist_mask(cfg, 3)
+    assert m.dtype == torch.bool and tuple(m.shape) == tuple(G["exist_shape"])
+    assert np.array_equal(np.packbits(m.numpy()), G["exist"])
+    # the fallback erosion (no scipy) is the same operator
+    raw = exist_counts() > np.max(exist_counts()) / 3
+    import scipy.ndimage
+    want = scipy.ndimage.binary_erosion(raw[2:], border_value=1, iterations=4)
+    p = raw[2:].copy()
+    for _ in range(4):
+        q = np.pad(p, 1, constant_values=True)
+        p = q[1:-1, 1:-1] & q[:-2, 1:-1] & q[2:, 1:-1] & q[1:-1, :-2] & q[1:-1, 2:]
+    assert np.array_equal(p, want)
+
+
+def test_saved_array_layout_matches_reference_statements():
+    out = runner._to_grid_layout(sample_images())
+    assert np.array_equal(out.numpy(), G["grid"])
+
+
+def test_ema_helper_matches_reference_module():
+    m = small_module()
+    h = EMAHelper(mu=0.9)
+    h.register(torch.nn.DataParallel(m))
+    for step in range(3):
+        perturb(m, step)
+        h.update(m)
+    shadow = h.state_dict()
+    assert sorted(shadow) == sorted(k[7:] for k in G.files if k.startswith("shadow:"))      # frozen parameter skipped
+    for k, v in shadow.items():
+        assert np.array_equal(v.numpy(), G["shadow:" + k]), k
+    twin = small_module(seed=7)
+    h2 = EMAHelper(mu=0.9)
+    h2.register(twin)
+    h2.load_state_dict(shadow)
+    h2.ema(twin)
+    for k, v in twin.state_dict().items():
+        assert np.array_equal(v.detach().numpy(), G["after:" + k]), k
