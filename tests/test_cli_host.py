@@ -1,0 +1,58 @@
+"""CPU: the re-hosted CLI boundary (LiDARGen/main.py:17-163,177-209) - flags, YAML keys, forced overrides, output folder,
+and the reference's error convention (an exception while sampling is logged with its traceback, the process returns 0)."""
+import logging
+import os
+
+import pytest
+import torch
+import yaml
+
+import sdpc_b200  # noqa: F401
+from sdpc_b200 import main as cli
+
+CFG_DIR = os.path.join(os.path.dirname(os.path.abspath(sdpc_b200.__file__)), "configs")
+
+
+@pytest.mark.parametrize("name,dataset", [("Line.yml", "KITTI360_im_8batch"), ("Inpainting.yml", None), ("Densification.yml", None)])
+def test_shipped_configs_parse_with_reference_flags(tmp_path, name, dataset):
+    exp = str(tmp_path / "exp")
+    args, cfg = cli.parse_args_and_config(["--sample", "--ni", "--config", name, "--exp", exp, "--doc", "d", "-i", "imgs",
+                                           "--seed", "7"])
+    assert args.image_folder == os.path.join(exp, "image_samples", "imgs") and os.path.isdir(args.image_folder)
+    assert args.log_path == os.path.join(exp, "logs", "d")
+    # forced overrides of the reference (main.py:46-48)
+    assert cfg.sampling.inpainting is True and cfg.sampling.interpolation is False and cfg.sampling.densification is False
+    # keys the samplers and runners read
+    for key in ("batch_size", "actualBatchSize", "n_steps_each", "step_lr", "denoise", "ckpt_id"):
+        assert hasattr(cfg.sampling, key), key
+    for key in ("channels", "image_size", "image_width", "dataset", "logit_transform", "rescaled"):
+        assert hasattr(cfg.data, key), key
+    for key in ("ngf", "num_classes", "sigma_begin", "sigma_end", "sigma_dist", "normalization", "nonlinearity", "ema", "ema_rate"):
+        assert hasattr(cfg.model, key), key
+    assert cfg.sampling.batch_size % cfg.sampling.actualBatchSize == 0
+    if dataset:
+        assert cfg.data.dataset == dataset
+    else:
+        assert hasattr(cfg.data, "modifications") and len(cfg.data.modifications) >= cfg.sampling.actualBatchSize
+    assert torch.initial_seed() == 7
+
+
+def test_only_sampling_is_supported(tmp_path):
+    with pytest.raises(SystemExit):
+        cli.parse_args_and_config(["--ni", "--config", "Line.yml", "--exp", str(tmp_path)])
+
+
+def test_sampling_errors_are_logged_and_return_zero(tmp_path, caplog):
+    """without a CUDA device the samplers raise (no CPU fallback); like the reference's main(), the CLI logs the
+    traceback and still returns 0"""
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only check")
+    cfg = yaml.safe_load(open(os.path.join(CFG_DIR, "Line.yml")))
+    cfg["sampling"].update(batch_size=4, actualBatchSize=2, n_steps_each=1)
+    cfg["data"].update(image_size=16, image_width=64)
+    cfg["model"].update(num_classes=3)
+    p = tmp_path / "Line.yml"
+    p.write_text(yaml.safe_dump(cfg))
+    with caplog.at_level(logging.ERROR):
+        assert cli.main(["--sample", "--ni", "--config", str(p), "--exp", str(tmp_path / "exp")]) == 0
+    assert "no CPU fallback" in caplog.text or "CUDA" in caplog.text
