@@ -124,3 +124,33 @@ def test_emulated_sharded_targets_equal_full(emul):
         outs.append((x, ni.clone()))
     for x, ni in outs[1:]:
         assert torch.equal(x, outs[0][0]) and torch.equal(ni, outs[0][1])
+
+
+def _emul_share(emul, case, sigma=0.3, setting=5):
+    run = _runner("pose", case)
+    p = run.params(0.0, 0.0, 0.0, case["coef"], sigma if sigma > 1 else 1, True, setting == 5, 10.0, False)
+    x = case["x"].clone()
+    ni = torch.full_like(x, 7.0)
+    b = run.buffers(x, None, None, new_images=ni)
+    assert emul.emul_langevin_reproject_step(C.byref(p), C.byref(b)) == 0
+    return x, ni, run
+
+
+def test_emulated_edge_no_source_pixel_exists(emul):
+    """existMask all False: no candidate reaches any z-buffer - the shared images are zero, nothing is corrected"""
+    case = cases.small_multiview("pose")
+    case["exist"] = torch.zeros_like(case["exist"])
+    x, ni, run = _emul_share(emul, case)
+    assert int(run.debug["cnt"].abs().sum()) == 0 and int((run.debug["winner"] != -1).sum()) == 0
+    assert float(ni.abs().max()) == 0.0
+    assert torch.equal(x, case["x"]) and int(run.too_high.item()) == 0
+
+
+def test_emulated_edge_every_pixel_known(emul):
+    """refer_mask all ones: the shared images do not depend on the mask, the correction (1 - mask) vanishes"""
+    case = cases.small_multiview("pose")
+    _, ni_ref, _ = _emul_share(emul, case)
+    case["mask"] = torch.ones_like(case["mask"])
+    x, ni, _ = _emul_share(emul, case)
+    assert torch.equal(ni, ni_ref) and float(ni.abs().max()) > 0.0
+    assert torch.equal(x, case["x"])
