@@ -1,5 +1,5 @@
 #!/bin/bash
-# First box call of round 2 (about 6 box-minutes): the evidence the last session of round 1 could not collect.
+# First box call of round 2 (about 10 box-minutes): the evidence the last session of round 1 could not collect.
 #   1. full test suite, smoke, both bench arms (plain runs)
 #   2. ncu launch list of the bench command (per-kernel share of the step)
 #   3. ncu --set full of the CTA-pair convolution (CG = 2) and, for comparison, the multicast variant (SDPC_CTA2=0)
