@@ -281,7 +281,8 @@ __global__ void __launch_bounds__(256) scatter_kernel(ScatterArgs a) {
 
 
 // ------------------------------------------------------------------------------------------
-// production scatter: compacted valid source pixels, fp32-guarded re-projection, packed winner key
+// production scatter: compacted valid source pixels, fp32-guarded re-projection; nearest candidate by a 128-bit CAS on
+// {log-range, source id} (CAS = true, default) or by the packed 64-bit key that verify_winner_kernel confirms (CAS = false)
 // ------------------------------------------------------------------------------------------
 constexpr int kChunk = 1024;      // source pixels per block (4 per thread)
 
