@@ -1,0 +1,59 @@
+"""Signatures of the reference's hot-path entry points, for the drop-in boundary test.
+
+Imports the UNMODIFIED reference `models` package (build container only) and records, for every function / class the
+reference runners import from it, the parameter names in order with their defaults - the runners pass most arguments
+positionally, so the order is the contract.  The fixture travels, /root/reference does not.
+
+    python tests/golden/make_golden_signatures.py
+"""
+import inspect
+import json
+import os
+import sys
+
+sys.dont_write_bytecode = True
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, "/root/reference/LiDARGen")
+
+WANTED = {
+    "models": ["anneal_Langevin_dynamics", "anneal_Langevin_dynamics_densification", "anneal_Langevin_dynamics_inpainting",
+               "anneal_Langevin_dynamics_inpainting_simultaneous_basic", "get_sigmas"],
+    "models.KITTISampling": ["anneal_Langevin_dynamics_inpainting_simultaneous_basic_kitti"],
+    "models.ncsnv2": ["NCSN_LiDAR_small.__init__", "NCSN_LiDAR_small.forward"],
+    "models.ema": ["EMAHelper.__init__", "EMAHelper.register", "EMAHelper.update", "EMAHelper.ema", "EMAHelper.ema_copy",
+                   "EMAHelper.state_dict", "EMAHelper.load_state_dict"],
+}
+
+
+def describe(fn):
+    out = []
+    for p in inspect.signature(fn).parameters.values():
+        out.append([p.name, None if p.default is inspect.Parameter.empty else repr(p.default)])
+    return out
+
+
+def resolve(module, dotted):
+    obj = module
+    for part in dotted.split("."):
+        obj = getattr(obj, part)
+    return obj
+
+
+def main():
+    import importlib
+    import torch
+    if not torch.cuda.is_available():                       # models/ncsnv2.py calls .cuda() at import-free run time only
+        pass
+    table = {}
+    for mod, names in WANTED.items():
+        m = importlib.import_module(mod)
+        for n in names:
+            table[mod + ":" + n] = describe(resolve(m, n))
+    with open(os.path.join(HERE, "signatures.json"), "w") as f:
+        json.dump(table, f, indent=1, sort_keys=True)
+    for k, v in table.items():
+        print(k, [a for a, _ in v])
+
+
+if __name__ == "__main__":
+    main()
