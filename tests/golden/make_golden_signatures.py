@@ -51,6 +51,19 @@ def main():
             table[mod + ":" + n] = describe(resolve(m, n))
     with open(os.path.join(HERE, "signatures.json"), "w") as f:
         json.dump(table, f, indent=1, sort_keys=True)
+    # state_dict inventory of the reference module: ordered keys with shapes (what a checkpoint's states[0] holds,
+    # behind the DataParallel 'module.' prefix)
+    import argparse
+    N = argparse.Namespace
+    cfg = N(data=N(logit_transform=False, rescaled=False, channels=2, image_size=64, image_width=1024),
+            model=N(ngf=128, num_classes=232, nonlinearity="elu", normalization="InstanceNorm++", sigma_dist="geometric",
+                    sigma_begin=50, sigma_end=0.01, spec_norm=False), device=torch.device("cpu"))
+    net = importlib.import_module("models.ncsnv2").NCSN_LiDAR_small(cfg)
+    inv = [[k, list(v.shape)] for k, v in net.state_dict().items()]
+    named = [k for k, _ in net.named_parameters()]
+    with open(os.path.join(HERE, "state_dict_inventory.json"), "w") as f:
+        json.dump({"state_dict": inv, "named_parameters": named}, f, indent=0)
+    print("state_dict keys", len(inv), "parameters", len(named))
     for k, v in table.items():
         print(k, [a for a, _ in v])
 
