@@ -34,6 +34,7 @@ def parse_args_and_config(argv=None):
     parser.add_argument('--verbose', type=str, default='info', help='Verbose level: info | debug | warning | critical')
     parser.add_argument('--test', action='store_true', help='Whether to test the model (not supported: out of scope)')
     parser.add_argument('--sample', action='store_true', help='Whether to produce samples from the model')
+    parser.add_argument('--nvs', action='store_true', help='(not supported: the reference path behind it imports a missing module)')
     parser.add_argument('--fast_fid', action='store_true', help='(not supported: out of scope)')
     parser.add_argument('--resume_training', action='store_true', help='(not supported: out of scope)')
     parser.add_argument('-i', '--image_folder', type=str, default='images', help="The folder name of samples")
@@ -46,13 +47,15 @@ def parse_args_and_config(argv=None):
         path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'configs', args.config)
     with open(path, 'r') as f:
         config = yaml.safe_load(f)
+    if "image_width" not in config["data"]:                        # main.py:43-44
+        config["data"]["image_width"] = config["data"]["image_size"]
     new_config = dict2namespace(config)
     # forced overrides of the reference (main.py:46-48)
     new_config.sampling.inpainting = True
     new_config.sampling.interpolation = False
     new_config.sampling.densification = args.densification
     if not args.sample:
-        raise SystemExit("only --sample is supported: training / test / fast_fid are outside the hot path (SURVEY.md 8)")
+        raise SystemExit("only --sample is supported: training / test / nvs / fast_fid are outside the hot path (SURVEY.md 8)")
     os.makedirs(os.path.join(args.exp, 'image_samples'), exist_ok=True)
     args.image_folder = os.path.join(args.exp, 'image_samples', args.image_folder)
     if os.path.exists(args.image_folder) and not args.ni:

@@ -64,6 +64,18 @@ def main():
     with open(os.path.join(HERE, "state_dict_inventory.json"), "w") as f:
         json.dump({"state_dict": inv, "named_parameters": named}, f, indent=0)
     print("state_dict keys", len(inv), "parameters", len(named))
+    # command-line flags of LiDARGen/main.py (read from its source: importing it pulls in runners -> h5py)
+    import ast
+    flags = []
+    tree = ast.parse(open("/root/reference/LiDARGen/main.py").read())
+    for node in ast.walk(tree):
+        if isinstance(node, ast.Call) and getattr(node.func, "attr", "") == "add_argument":
+            names = [a.value for a in node.args if isinstance(a, ast.Constant)]
+            kw = {k.arg: ast.literal_eval(k.value) for k in node.keywords if k.arg in ("default", "action")}
+            flags.append({"names": names, "action": kw.get("action"), "default": kw.get("default")})
+    with open(os.path.join(HERE, "cli_flags.json"), "w") as f:
+        json.dump(flags, f, indent=1)
+    print("cli flags", [f["names"][-1] for f in flags])
     for k, v in table.items():
         print(k, [a for a, _ in v])
 

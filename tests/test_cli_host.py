@@ -56,3 +56,29 @@ def test_sampling_errors_are_logged_and_return_zero(tmp_path, caplog):
     with caplog.at_level(logging.ERROR):
         assert cli.main(["--sample", "--ni", "--config", str(p), "--exp", str(tmp_path / "exp")]) == 0
     assert "no CPU fallback" in caplog.text or "CUDA" in caplog.text
+
+
+def test_cli_accepts_every_reference_flag(tmp_path):
+    """flags of the reference's main.py (tests/golden/cli_flags.json, read from its source): every one parses here with
+    the same action; defaults are the reference's except the three site-specific ones (--config, --exp, --doc)"""
+    import json
+    flags = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "cli_flags.json")))
+    assert {"--sample", "--ni", "--config", "--seed", "--exp", "--doc", "--image_folder"} <= {f["names"][-1] for f in flags}
+    argv = ["--config", "Line.yml", "--exp", str(tmp_path), "--ni"]
+    for f in flags:
+        name = f["names"][-1]
+        if f["action"] == "store_true" and name not in ("--ni",):
+            argv.append(name)
+    args, _ = cli.parse_args_and_config(argv)                           # --sample is among them, so parsing succeeds
+    for f in flags:
+        dest = f["names"][-1].lstrip("-")
+        assert hasattr(args, dest), dest
+        if f["action"] == "store_true":
+            assert getattr(args, dest) is True, dest
+    args, _ = cli.parse_args_and_config(["--config", "Line.yml", "--exp", str(tmp_path), "--ni", "--sample"])
+    for f in flags:
+        dest = f["names"][-1].lstrip("-")
+        if dest in ("config", "exp", "doc", "sample", "ni", "image_folder"):
+            continue
+        want = False if f["action"] == "store_true" else f["default"]
+        assert getattr(args, dest) == want, (dest, getattr(args, dest), want)
