@@ -76,6 +76,16 @@ def main():
     with open(os.path.join(HERE, "cli_flags.json"), "w") as f:
         json.dump(flags, f, indent=1)
     print("cli flags", [f["names"][-1] for f in flags])
+    # the data / model / sampling sections of the three configurations the reference README names
+    import yaml
+    names = {"Line.yml": "HDVMine_Line.yml", "Inpainting.yml": "HDVMine_Circle.yml", "Densification.yml": "HDVMine_Densification.yml"}
+    cfgs = {}
+    for ours, theirs in names.items():
+        c = yaml.safe_load(open(os.path.join("/root/reference/LiDARGen/configs", theirs)))
+        cfgs[ours] = {"reference_file": theirs, **{sec: c[sec] for sec in ("data", "model", "sampling")}}
+    with open(os.path.join(HERE, "reference_configs.json"), "w") as f:
+        json.dump(cfgs, f, indent=1, sort_keys=True)
+    print("configs", {k: v["reference_file"] for k, v in cfgs.items()})
     for k, v in table.items():
         print(k, [a for a, _ in v])
 

@@ -82,3 +82,15 @@ def test_cli_accepts_every_reference_flag(tmp_path):
             continue
         want = False if f["action"] == "store_true" else f["default"]
         assert getattr(args, dest) == want, (dest, getattr(args, dest), want)
+
+
+@pytest.mark.parametrize("name", ["Line.yml", "Inpainting.yml", "Densification.yml"])
+def test_shipped_configs_carry_the_reference_values(name):
+    """data / model / sampling sections equal the reference's configuration files key for key (HDVMine_Line.yml,
+    HDVMine_Circle.yml, HDVMine_Densification.yml; tests/golden/reference_configs.json); only the `b200` section is new"""
+    import json
+    ref = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_configs.json")))[name]
+    ours = yaml.safe_load(open(os.path.join(CFG_DIR, name)))
+    for sec in ("data", "model", "sampling"):
+        assert ours[sec] == ref[sec], (name, sec)
+    assert set(ours) - {"data", "model", "sampling"} == {"b200"}
