@@ -3,7 +3,7 @@
 Yields the tuple the reference datasets return (datasets/kitti360_im_8Batch.py:304,
 kitti360_im_AllForOne.py, kitti360_im_simultenous_densification.py):
   (real [B,2,H,W] f64, mask bool [B,2,H,W], sky bool [B,1,H,W], indices [B,1,H,W], toWorld [B,1,4,4] f64,
-   fromWorld [B,1,4,4] f64, goalImages [B,2,H,W], toOGView [B,1,4,4], saveNum [B])
+   fromWorld [B,1,4,4] f64, goalImages [B,2,H,W], toOGView [B,4,4], saveNum [B])
 for batches of `batch_size` views in groups of `group` poses.  No KITTI-360 data exists offline; geometry is a
 ground plane plus a few vertical walls ray-cast per view, so that neighbouring views really overlap."""
 import math
@@ -77,4 +77,5 @@ class SyntheticMultiView:
         sky = torch.ones(self.B, 1, self.H, self.W, dtype=torch.bool)               # always True
         indices = torch.arange(self.H * self.W).view(1, 1, self.H, self.W).repeat(self.B, 1, 1, 1)
         save_num = torch.arange(index * self.B, (index + 1) * self.B)
-        return real, mask, sky, indices, to_world, from_world, real.clone(), from_world.clone(), save_num
+        # toOGView is a bare 4x4 per item in the reference (no expand_dims, kitti360_im_8Batch.py:299-304): [B,4,4] after collate
+        return real, mask, sky, indices, to_world, from_world, real.clone(), from_world.clone().squeeze(1), save_num

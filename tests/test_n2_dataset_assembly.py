@@ -126,3 +126,25 @@ def test_item_batches_collate_like_the_dataloader():
     assert frames.tolist() == [103, 104, 105] and real[:, 0, 0, 0].tolist() == [3.0, 4.0, 5.0]
     with pytest.raises(IndexError):
         b.batch(2)
+
+
+def test_synthetic_batches_have_the_dataset_tuple_layout():
+    """CPU: the synthetic stand-in yields the tuple the reference datasets return after the DataLoader's collate
+    (kitti360_im_8Batch.py:299-304), i.e. the same layout `ItemBatches` produces from file-backed items"""
+    import torch
+    import sdpc_b200  # noqa: F401
+    from sdpc_b200.synthetic_data import SyntheticMultiView
+    B, A, Hs, Ws = 6, 3, 16, 64
+    for mode in ("line", "allforone", "densification"):
+        real, mask, sky, index, to_w, from_w, goal, to_og, frames = SyntheticMultiView(Hs, Ws, B, A, mode=mode, seed=3).batch(1)
+        assert real.shape == (B, 2, Hs, Ws) and real.dtype == torch.float64 and goal.shape == real.shape
+        assert mask.shape == (B, 2, Hs, Ws) and mask.dtype == torch.bool and torch.equal(mask[:, 0], mask[:, 1])
+        assert sky.shape == (B, 1, Hs, Ws) and sky.dtype == torch.bool and bool(sky.all())      # SURVEY quirk (x)
+        assert index.shape == (B, 1, Hs, Ws)
+        assert to_w.shape == (B, 1, 4, 4) and from_w.shape == (B, 1, 4, 4) and to_w.dtype == torch.float64
+        assert to_og.shape == (B, 4, 4) and frames.shape == (B,)
+        eye = torch.eye(4, dtype=torch.float64).expand(B, 4, 4)
+        assert torch.allclose(torch.matmul(from_w[:, 0], to_w[:, 0]), eye, atol=1e-12)
+        assert float(real.min()) >= 0.0 and float(real[:, 0].max()) <= 1.0
+        if mode == "densification":                                                              # target keeps every 4th beam
+            assert not bool(mask[0, 0, 1].any()) and bool(mask[0, 0, 0].any()) and bool(mask[1, 0, 1].any())
