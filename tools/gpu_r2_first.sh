@@ -24,13 +24,16 @@ STEP="python tools/time_step.py"
 if run r2_time_step $STEP; then
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:"scatter_fast|resolve_kernel|langevin_update|correct_kernel" -s 8 -c 4 -o gpurun_out/r2_prof_step $STEP > gpurun_out/r2_ncu_step.log 2>&1; echo "ncu step rc=$?"
 fi
-# bf16x3 arm in clusters / CTA pairs (SDPC_X3_CLUSTER=1, not yet validated): bit-for-bit against the single-CTA path
-timeout 120 python tools/ab_probe.py run gpurun_out/ab_def 0 > gpurun_out/r2_ab_def.log 2>&1
-SDPC_X3_CLUSTER=1 timeout 120 python tools/ab_probe.py run gpurun_out/ab_x3cl 0 > gpurun_out/r2_ab_x3cl.log 2>&1
-python tools/ab_probe.py compare gpurun_out/ab_def gpurun_out/ab_x3cl | tee gpurun_out/r2_ab_x3_cmp.log
-python tools/quick_time.py 8 bf16x3 2>&1 | grep forward | tee gpurun_out/r2_x3_time.log
-SDPC_X3_CLUSTER=1 python tools/quick_time.py 8 bf16x3 2>&1 | grep forward | tee -a gpurun_out/r2_x3_time.log
-rm -f gpurun_out/ab_*.npy
+# bf16x3 arm in clusters / CTA pairs: only when tools/patches/x3_cluster.patch has been applied and built (it adds the
+# SDPC_X3_CLUSTER switch); bit-for-bit against the single-CTA path, then the forward time of both
+if grep -q conv_umma_x3_cluster simultaneous-diffusion-for-pointclouds_b200/csrc/conv_umma.h; then
+  timeout 120 python tools/ab_probe.py run gpurun_out/ab_def 0 > gpurun_out/r2_ab_def.log 2>&1
+  SDPC_X3_CLUSTER=1 timeout 120 python tools/ab_probe.py run gpurun_out/ab_x3cl 0 > gpurun_out/r2_ab_x3cl.log 2>&1
+  python tools/ab_probe.py compare gpurun_out/ab_def gpurun_out/ab_x3cl | tee gpurun_out/r2_ab_x3_cmp.log
+  python tools/quick_time.py 8 bf16x3 2>&1 | grep forward | tee gpurun_out/r2_x3_time.log
+  SDPC_X3_CLUSTER=1 python tools/quick_time.py 8 bf16x3 2>&1 | grep forward | tee -a gpurun_out/r2_x3_time.log
+  rm -f gpurun_out/ab_*.npy
+fi
 for B in 1 2 4; do python tools/quick_time.py $B bf16 2>&1 | grep forward; done > gpurun_out/r2_small_batches.log
 cat gpurun_out/r2_small_batches.log
 # BASELINE config 5 on one GPU: 16 / 32 / 64 views in groups of 8 (forward + step per call)
