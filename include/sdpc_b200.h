@@ -64,7 +64,8 @@ typedef struct sdpc_score_config {
   int32_t num_classes; /* config.model.num_classes = length of the `sigmas` buffer */
   int32_t precision;   /* enum sdpc_precision */
   int32_t max_views;   /* largest batch a forward will see (sizes the activation arena) */
-  int32_t reserved;
+  int32_t reserved;    /* flags, 0 for production use: bit 0 keeps every intermediate alive for sdpc_score_read_tap (tests),
+                          bit 1 launches the kernels eagerly instead of replaying the captured CUDA graph */
 } sdpc_score_config;
 
 int sdpc_score_create(const sdpc_score_config* cfg, sdpc_score_t** out);
