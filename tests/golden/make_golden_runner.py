@@ -3,6 +3,8 @@
 * existTotal mask preprocessing and the saved-array layout: the statements of
   LiDARGen/runners/ncsn_runner_kitti_simultaneous.py (:528-532 and the `maskedSample` lines at :866-868) are read from
   /root/reference at generation time and executed on seeded inputs (`import runners` itself needs h5py / open3d).
+* sensor-model constants (angles per pixel, grid minima, bigRowCount) and the azimuth / elevation tables: the statements of
+  LiDARGen/models/KITTISampling.py:29-102 executed on stand-in samples.
 * EMAHelper: LiDARGen/models/ema.py is imported as a file (it only needs torch) and driven through
   register / update / state_dict / load_state_dict / ema on a small module.
 Run in the build container only; the fixture travels, /root/reference does not.
@@ -18,6 +20,7 @@ import torch
 HERE = os.path.dirname(os.path.abspath(__file__))
 RUNNER = "/root/reference/LiDARGen/runners/ncsn_runner_kitti_simultaneous.py"
 EMA = "/root/reference/LiDARGen/models/ema.py"
+SAMPLER = "/root/reference/LiDARGen/models/KITTISampling.py"
 
 
 def exist_counts(seed=3, H=64, W=1024):
@@ -88,7 +91,23 @@ def main():
     h2.load_state_dict(h.state_dict())
     h2.ema(twin)
     after = {k: v.detach().clone().numpy() for k, v in twin.state_dict().items()}
-    np.savez_compressed(os.path.join(HERE, "runner_helpers.npz"), exist=np.packbits(exist), exist_shape=np.array(exist.shape),
+    # ---- sensor-model constants and angle tables of the samplers: the statements of KITTISampling.py between
+    #      `rowMax = x_mod.shape[-2]` and the `elevation = ...` line, executed on stand-in samples of two sizes
+    import math
+    src = open(SAMPLER).read().splitlines()
+    i0 = next(k for k, l in enumerate(src) if l.strip().startswith("rowMax = x_mod.shape[-2]"))
+    i1 = next(k for k, l in enumerate(src) if l.strip().startswith("elevation = torch.from_numpy"))
+    body = "\n".join(l[4:] if l.startswith("    ") else l for l in src[i0:i1 + 1])
+    geo = {}
+    for Hh, Ww in ((64, 1024), (16, 64)):
+        env = {"np": np, "torch": torch, "math": math, "x_mod": torch.zeros(2, 2, Hh, Ww)}
+        exec(body, env)
+        for k in ("horizontalAngles", "verticalAngles", "horizontalMin", "verticalMin", "bigRowMin"):
+            geo[f"geo{Hh}x{Ww}:{k}"] = np.float64(env[k])
+        geo[f"geo{Hh}x{Ww}:bigRowCount"] = np.int64(env["bigRowCount"])
+        geo[f"geo{Hh}x{Ww}:azimuth"] = env["azimuth"].numpy()
+        geo[f"geo{Hh}x{Ww}:elevation"] = env["elevation"].numpy()
+    np.savez_compressed(os.path.join(HERE, "runner_helpers.npz"), exist=np.packbits(exist), exist_shape=np.array(exist.shape), **geo,
                         grid=grid, **{"shadow:" + k: v for k, v in shadow.items()},
                         **{"after:" + k: v for k, v in after.items()})
     print("exist", exist.shape, int(exist.sum()), "grid", grid.shape, "shadow keys", sorted(shadow))

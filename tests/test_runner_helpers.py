@@ -57,3 +57,18 @@ def test_ema_helper_matches_reference_module():
     h2.ema(twin)
     for k, v in twin.state_dict().items():
         assert np.array_equal(v.detach().numpy(), G["after:" + k]), k
+
+
+def test_sensor_geometry_matches_reference_statements():
+    """constants and angle tables handed to the kernels against the sampler's own statements (KITTISampling.py:29-102)"""
+    from sdpc_b200.geometry import sensor_geometry
+    for H, W in ((64, 1024), (16, 64)):
+        g = sensor_geometry(H, W, "cpu")
+        t = f"geo{H}x{W}:"
+        assert g.dh == float(G[t + "horizontalAngles"]) and g.dv == float(G[t + "verticalAngles"])
+        assert g.h_min == float(G[t + "horizontalMin"]) and g.v_min == float(G[t + "verticalMin"])
+        assert g.big_row_min == float(G[t + "bigRowMin"]) and g.R == int(G[t + "bigRowCount"])
+        az, el = torch.from_numpy(G[t + "azimuth"]).reshape(-1), torch.from_numpy(G[t + "elevation"]).reshape(-1)
+        assert torch.equal(g.cos_az, torch.cos(az)) and torch.equal(g.sin_az, torch.sin(az))      # KITTISampling.py:176
+        assert torch.equal(g.cos_el, torch.cos(el)) and torch.equal(g.sin_el, torch.sin(el))
+    assert int(G["geo64x1024:bigRowCount"]) == 114
