@@ -21,6 +21,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 RUNNER = "/root/reference/LiDARGen/runners/ncsn_runner_kitti_simultaneous.py"
 EMA = "/root/reference/LiDARGen/models/ema.py"
 SAMPLER = "/root/reference/LiDARGen/models/KITTISampling.py"
+MODELS_INIT = "/root/reference/LiDARGen/models/__init__.py"
+# data.modifications of the Inpainting / Densification configurations plus zero, +-3 and a large offset
+MODIFICATIONS = [[0, 0, 0], [5, -5, 0], [-5, -5, 0], [0, 5, 0], [-10, 10, 0], [10, 10, 0], [-10, 0, 0], [3, -3, 1], [200, 0, -7]]
 
 
 def exist_counts(seed=3, H=64, W=1024):
@@ -107,6 +110,16 @@ def main():
         geo[f"geo{Hh}x{Ww}:bigRowCount"] = np.int64(env["bigRowCount"])
         geo[f"geo{Hh}x{Ww}:azimuth"] = env["azimuth"].numpy()
         geo[f"geo{Hh}x{Ww}:elevation"] = env["elevation"].numpy()
+    # ---- a-5's view origins: the statements of models/__init__.py (:201, :215, :224-225, :231) on the configured offsets
+    src = open(MODELS_INIT).read().splitlines()
+    pick = []
+    for marker in ("originListOG = torch.unsqueeze(torch.unsqueeze(modificationList,-1),-1)", "heWhoModsTheModMan = 1",
+                   "originList = ((torch.log2(torch.abs(originListOG)+1)) / 6) * heWhoModsTheModMan",
+                   "originList = (torch.pow(2,(originList*6))-1)", "originList = originList/(originListOG+0.00000001) * 10"):
+        pick.append(next(l.strip() for l in src if l.strip() == marker))
+    env = {"torch": torch, "modificationList": torch.tensor(MODIFICATIONS)}
+    exec("\n".join(pick), env)
+    geo["origins"] = env["originList"].numpy()
     np.savez_compressed(os.path.join(HERE, "runner_helpers.npz"), exist=np.packbits(exist), exist_shape=np.array(exist.shape), **geo,
                         grid=grid, **{"shadow:" + k: v for k, v in shadow.items()},
                         **{"after:" + k: v for k, v in after.items()})

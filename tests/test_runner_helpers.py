@@ -72,3 +72,13 @@ def test_sensor_geometry_matches_reference_statements():
         assert torch.equal(g.cos_az, torch.cos(az)) and torch.equal(g.sin_az, torch.sin(az))      # KITTISampling.py:176
         assert torch.equal(g.cos_el, torch.cos(el)) and torch.equal(g.sin_el, torch.sin(el))
     assert int(G["geo64x1024:bigRowCount"]) == 114
+
+
+def test_translation_origins_match_reference_statements():
+    """a-5's view origins (models/__init__.py:201-231: an fp32 log2 / pow round trip of |m| divided by m + 1e-8, times 10):
+    sign(m) * 10 up to the round trip's last bits, whatever the configured magnitude (SURVEY.md 8a quirk iii)"""
+    from sdpc_b200.step import translation_origins
+    from tests.golden.make_golden_runner import MODIFICATIONS
+    got = translation_origins(torch.tensor(MODIFICATIONS))
+    assert got.dtype == torch.float32 and np.array_equal(got.numpy(), G["origins"])
+    assert np.allclose(np.abs(G["origins"][np.array(MODIFICATIONS) != 0]), 10.0, atol=1e-4)
