@@ -112,3 +112,28 @@ def test_single_process_emulation_matches_reference_golden(emul_path):
     assert len(im) == int(g["n_images"])
     for i, t in enumerate(im):
         assert int((np.abs(t.numpy() - g[f"images{i}"]) > 2e-4).sum()) <= 16
+
+
+def test_samplers_own_their_buffers(emul_path):
+    """ownership contract of the reference: the caller's x_mod / refer_image / refer_mask / sky / existMask
+    are never written, and every returned image is a fresh CPU float32 tensor that aliases neither the inputs nor the
+    other outputs"""
+    import sdpc_b200  # noqa: F401
+    from sdpc_b200 import samplers
+    from tests.golden import cases
+    lib = _emul_lib(emul_path)
+    case = cases.small_multiview("pose")
+    keep = {k: case[k].clone() for k in ("x", "refer", "mask", "sky", "exist", "toWorld", "fromWorld")}
+    sig = cases.short_sigmas()
+    im, targets, shared = samplers.anneal_Langevin_dynamics_inpainting_simultaneous_basic_kitti(
+        case["x"], case["refer"], case["mask"], case["sky"], None, 0, 5, 10, cases.fake_score(sig), sig, case["fromWorld"],
+        case["toWorld"], 2, n_steps_each=2, step_lr=6.2e-6, existMask=case["exist"], denoise=True, verbose=False,
+        grad_ref=1, correlation_coefficient=0.01, _lib=lib)
+    for k, v in keep.items():
+        assert torch.equal(case[k], v), k
+    assert targets == [] and len(shared) == 2 and len(im) == 3        # shared: level 0 x 2 steps; images: last level x 2 + final
+    outs = im + shared
+    ptrs = {t.data_ptr() for t in outs}
+    assert len(ptrs) == len(outs) and case["x"].data_ptr() not in ptrs
+    for t in outs:
+        assert t.device.type == "cpu" and t.dtype == torch.float32 and tuple(t.shape) == tuple(case["x"].shape)
