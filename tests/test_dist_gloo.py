@@ -137,3 +137,16 @@ def test_samplers_own_their_buffers(emul_path):
     assert len(ptrs) == len(outs) and case["x"].data_ptr() not in ptrs
     for t in outs:
         assert t.device.type == "cpu" and t.dtype == torch.float32 and tuple(t.shape) == tuple(case["x"].shape)
+
+
+def test_reference_print_quirk_is_kept(emul_path, capsys):
+    """the pose sampler prints its diagnostics at levels 1 and 2 even with verbose=False
+    (KITTISampling.py:492-500); the translation sampler does not; both print the `grad_ref:` line after the denoise step"""
+    lib = _emul_lib(emul_path)
+    _run("pose", 2, None, lib)
+    out = capsys.readouterr().out
+    assert "level: 1," in out and "level: 2," in out and "level: 0," not in out and "level: 3," not in out
+    assert out.count("grad_ref: 1") == 3                              # levels 1, 2 and the line after the denoise step
+    _run("trans", 2, None, lib)
+    out = capsys.readouterr().out
+    assert "level:" not in out and out.count("grad_ref: 1") == 1
