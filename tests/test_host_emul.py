@@ -154,3 +154,33 @@ def test_emulated_edge_every_pixel_known(emul):
     x, ni, _ = _emul_share(emul, case)
     assert torch.equal(ni, ni_ref) and float(ni.abs().max()) > 0.0
     assert torch.equal(x, case["x"])
+
+
+def _identity_case(B=2, H=16, W=64, seed=9):
+    """B views of one group at the SAME pose: smooth positive ranges, a little per-view noise, every pixel exists"""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    base = cases.smooth_range_image(1, H, W, seed)
+    base[:, 0] = base[:, 0].clamp(0.25, 0.9)                      # away from the min-depth filter and from the far end
+    x = (base.repeat(B, 1, 1, 1) + torch.from_numpy(rng.normal(0, 1e-3, size=(B, 2, H, W)).astype(np.float32))).contiguous()
+    eye = torch.eye(4, dtype=torch.float64).reshape(1, 1, 4, 4).repeat(B, 1, 1, 1)
+    return dict(B=B, A=B, H=H, W=W, R=cases.big_rows(H), x=x, refer=x.clone(), coef=0.25,
+                mask=torch.zeros(B, 2, H, W, dtype=torch.int32), sky=torch.ones(B, 1, H, W, dtype=torch.bool),
+                exist=torch.ones(B, H, W, dtype=torch.bool), toWorld=eye, fromWorld=eye.clone())
+
+
+def test_emulated_identity_poses_shift_the_group_mean_down_one_row(emul):
+    """the reference's hidden invariant: with identical poses every view receives the mean of the group's
+    views shifted DOWN by one row - row 0 stays empty, source row H-1 is dropped - because verticalMin and bigRowMin
+    floor half a pixel apart (KITTISampling.py:68-78)"""
+    case = _identity_case()
+    x, ni, run = _emul_share(emul, case)
+    mean = case["x"].double().mean(0, keepdim=True).float()
+    assert float(ni[:, :, 0].abs().max()) == 0.0                                  # row 0: no candidate lands there
+    assert torch.allclose(ni[:, :, 1:], mean[:, :, :-1].expand_as(ni[:, :, 1:]), rtol=0, atol=2e-6)
+    cnt = run.debug["cnt"]                                                        # [B, R, W] grid: rows R-H .. R-1 are the crop
+    crop = cnt[:, case["R"] - case["H"]:]
+    assert int(crop[:, 0].sum()) == 0 and bool((crop[:, 1:] == case["B"]).all())
+    # correction pulls every view towards the shifted mean with weight coef on unknown pixels (mask = 0)
+    want = case["x"] + case["coef"] * (-(case["x"] - ni))
+    want[:, :, 0] = case["x"][:, :, 0]
+    assert torch.allclose(x, want, rtol=0, atol=1e-6)

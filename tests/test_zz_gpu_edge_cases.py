@@ -29,3 +29,22 @@ def test_every_pixel_known(winner_mode):
     x, ni, _ = _cuda_step("pose", case, 0.3, 5, debug="cells", winner_mode=winner_mode)
     assert torch.equal(ni, ni_ref) and float(ni.abs().max()) > 0.0
     assert torch.equal(x.cpu(), case["x"])
+
+
+@pytest.mark.parametrize("shape", [(2, 16, 64), (4, 64, 1024)])
+def test_identity_poses_shift_the_group_mean_down_one_row(shape):
+    """size-independent property at the small and at the full image size (the reference's hidden invariant):
+    with identical poses every view receives the mean of the group's views shifted down by one row; row 0 stays empty"""
+    from tests.test_host_emul import _identity_case
+    B, H, W = shape
+    case = _identity_case(B, H, W)
+    x, ni, run = _cuda_step("pose", case, 0.3, 5, debug="cells")
+    x, ni = x.cpu(), ni.cpu()
+    mean = case["x"].double().mean(0, keepdim=True).float()
+    assert float(ni[:, :, 0].abs().max()) == 0.0
+    assert torch.allclose(ni[:, :, 1:], mean[:, :, :-1].expand_as(ni[:, :, 1:]), rtol=0, atol=2e-6)
+    crop = run.debug["cnt"].cpu()[:, case["R"] - H:]
+    assert int(crop[:, 0].sum()) == 0 and bool((crop[:, 1:] == B).all())
+    want = case["x"] + case["coef"] * (-(case["x"] - ni))
+    want[:, :, 0] = case["x"][:, :, 0]
+    assert torch.allclose(x, want, rtol=0, atol=1e-6)
