@@ -94,11 +94,15 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def stop(self, t0, t1):
+    def stop(self, t0, t1, t_loaded=None):
+        """Samples of the timed region [t0, t1]; if the region was shorter than one sampling period, the samples up to
+        `t_loaded` (the roofline / end-to-end passes that follow without a pause: same kernels, same load)."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
-        rows = [r for t, r in self.rows if t0 <= t <= t1] or [r for _, r in self.rows]
+        rows, window = [r for t, r in self.rows if t0 <= t <= t1], "timed region"
+        if not rows and t_loaded is not None:
+            rows, window = [r for t, r in self.rows if t0 <= t <= t_loaded], "timed region + the passes that follow it under the same load"
         sm, mx, reasons = [], None, set()
         for r in rows:
             try:
@@ -110,7 +114,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "window": window}
 
 
 def measured_peaks():
@@ -249,13 +253,12 @@ def run_b200(args):
         return ms
 
     # ---- device-resident arm -------------------------------------------------------------------
+    clocks = ClockSampler(local) if rank == 0 else None          # started before the warm-up: nvidia-smi needs a moment to stream
     for _ in range(max(args.warmup, 3)):
         step(x)
-    clocks = ClockSampler(local) if rank == 0 else None
     t0 = time.time()
     ms = timed(lambda: step(x), args.steps)
     t1 = time.time()
-    clk = clocks.stop(t0, t1) if clocks else None
     value = world * B * args.steps / (ms / 1e3)
     # roofline pass: the same K steps again with every tensor-core convolution launch bracketed by CUDA events
     # on the launching stream (this disables the CUDA-graph replay of the forward, the kernels are identical)
@@ -289,6 +292,7 @@ def run_b200(args):
     e2e_steps = max(3, args.steps // 2)
     ms_e2e = timed(e2e_step, e2e_steps)
     e2e_value = world * B * e2e_steps / (ms_e2e / 1e3)
+    clk = clocks.stop(t0, t1, time.time()) if clocks else None
     nbytes = x_host.numel() * 4
 
     # fp32-parity arm on the tensor cores (bf16x3: hi/lo operand split, 2e-4 of the fp32 oracle), same step
