@@ -1004,10 +1004,12 @@ extern "C" int sdpc_score_profile_collect(sdpc_score_t* h, double* total_ms, dou
     if (df) fprintf(df, "%s,%.0f,%.6f\n", r.name.c_str(), r.flops, t);
     ms += t;
     fl += r.flops;
+  }
+  if (df) fclose(df);
+  for (auto& r : h->prof) {                                   // only now: an error above leaves every record owned by `prof`
     h->ev_pool.push_back(r.a);
     h->ev_pool.push_back(r.b);
   }
-  if (df) fclose(df);
   if (total_ms) *total_ms = ms;
   if (total_flops) *total_flops = fl;
   if (n_launches) *n_launches = (int)h->prof.size();
