@@ -66,3 +66,33 @@ def assemble_view(scan, goal_scan, to_world_src, to_world_dst, H, W, origin=None
     goal, _, _ = postprocess(g["depth"], g["intensity"], None, None)
     return dict(real=real, known=known, notsky=notsky, index=r["index"][None], toWorld=to_world_dst[None],
                 fromWorld=from_world[None], goalDepth=goal, toOGView=to_og_view, moved=moved)
+
+
+def allforone_selection(pose_num, n_frames):
+    """kitti360_im_AllForOne.py:160-171: every view of a group re-renders its frame's scan from the pose 2 * 5 frames
+    ahead (the last pose when the drive ends earlier); the view only chooses the origin, `config.data.modifications[view]`."""
+    return min(pose_num + 2 * 5, n_frames - 1)
+
+
+def assemble_view_densification(scan, to_world, modifications, view, H, W):
+    """kitti360_im_simultenous_densification.py `__getitem__`: no pose change.  The scan is first rendered from
+    `modifications[0]`, the first quarter of the columns is blanked, and only the points that own a remaining pixel are
+    kept (in row-major pixel order); that thinned scan is rendered from `modifications[view]`, the full scan from the same
+    origin is the ground truth.  View 0 replaces its unknown-pixel mask by the blanked quarter alone.
+    Pinned by tests/golden/make_golden_n2_variants.py (the reference's own source lines)."""
+    modifications = np.asarray(modifications)
+    first = lp.point_cloud_to_range_image(scan, modifications[0], True, H, W)
+    index = first["index"].copy()
+    index[:, :(W // 4)] = -2
+    thinned = scan[index[index >= 0].astype(int)]
+    origin = modifications[view]
+    r = lp.point_cloud_to_range_image(thinned, origin, True, H, W)
+    real, known, notsky = postprocess(r["depth"], r["intensity"], r["obfuscation"], r["sky"])
+    if view == 0:
+        known = np.ones_like(known)
+        known[:, :, :(W // 4)] = False
+    g = lp.point_cloud_to_range_image(scan, origin, True, H, W)
+    goal, _, _ = postprocess(g["depth"], g["intensity"], None, None)
+    to_og_view = np.linalg.inv(to_world)
+    return dict(real=real, known=known, notsky=notsky, index=r["index"][None], toWorld=to_world[None],
+                fromWorld=to_og_view[None], goalDepth=goal, toOGView=to_og_view, thinned=thinned)

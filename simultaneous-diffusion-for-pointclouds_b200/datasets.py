@@ -7,8 +7,10 @@ kitti360_im_simultenous_densification.py pick other poses / origins but run the 
 * `assemble_view`        -- one dataset item: the raw scan is moved into the target frame's sensor coordinates, projected to
   a range image (row N1 kernels) and post-processed into the sampler's inputs; the target frame's own scan gives the ground
   truth.  The points stay on the GPU from the .bin bytes to the finished images.
-* `KITTI360Line`         -- file-backed `Dataset` with the reference's item layout for the Line configuration (root path as
-  an argument instead of the hard-coded /data/KITTI-360).
+* `assemble_densification_view` -- the densification dataset's item: no pose change, the scan is thinned to the points
+  that own a pixel outside the blanked quarter of the columns, then rendered from the view's origin.
+* `KITTI360Line` / `KITTI360AllForOne` / `KITTI360Densification` -- file-backed `Dataset`s with the reference's item layout
+  for Line.yml / Inpainting.yml / Densification.yml (root path as an argument instead of the hard-coded /data/KITTI-360).
 * `ItemBatches`          -- consecutive items collated into the batch tuple the runners unpack (`b200.data_root` in the yml).
 
 CUDA only: there is no CPU fallback."""
@@ -86,6 +88,39 @@ def assemble_view(scan, goal_scan, to_world_src, to_world_dst, origin=None, retu
             index.cpu().numpy()[None], to_dst[None], from_world[None], goal_real.cpu().numpy(), to_og_view)
 
 
+def assemble_densification_view(scan, to_world, modifications, view, return_remission=True, rowMax=64, colMax=1024,
+                                device="cuda"):
+    """One item of `KITTI360_im_simultaneous_densification` (kitti360_im_simultenous_densification.py, `__getitem__`).
+    scan: float32 [N,4] raw points of the frame, to_world: its velo -> world matrix, modifications: [>=A,3] origins.
+    The scan is rendered from `modifications[0]`, the first colMax // 4 columns are blanked and only the points that own
+    one of the remaining pixels survive, in row-major pixel order (`scanPoints[index[index >= 0]]`); the thinned scan is
+    rendered from `modifications[view]`, the full scan from the same origin is the ground truth.  View 0 replaces its
+    unknown-pixel mask by the blanked quarter alone.  Returns the tuple of `assemble_view`."""
+    lib = cabi.load()
+    if not torch.cuda.is_available():
+        raise cabi.SdpcError("assemble_densification_view needs a CUDA device: there is no CPU fallback")
+    dev = torch.device(device)
+    H, W = int(rowMax), int(colMax)
+    mods = np.asarray(modifications, dtype=np.float64)
+    to_world = np.ascontiguousarray(to_world, dtype=np.float64)
+    to_og_view = np.linalg.inv(to_world)
+    with torch.cuda.device(dev):
+        full = torch.as_tensor(np.ascontiguousarray(scan, dtype=np.float64)).to(dev)
+        _, _, _, _, owner = project_device(full, mods[0], return_remission, H, W)
+        owner[:, :W // 4] = -2
+        thinned = full.index_select(0, owner[owner >= 0].long()).contiguous()
+        depth, inten, obf, sky, index = project_device(thinned, mods[view], return_remission, H, W)
+        real, known, notsky = _postprocess(lib, dev, depth, inten, obf, sky, H, W, True)
+        gdepth, ginten, _, _, _ = project_device(full, mods[view], return_remission, H, W)
+        goal_real, _, _ = _postprocess(lib, dev, gdepth, ginten, None, None, H, W, False)
+    known = known.cpu().numpy().astype(bool)
+    if view == 0:
+        known = np.ones_like(known)
+        known[:, :, :W // 4] = False
+    return (real.cpu().numpy(), known, notsky.cpu().numpy().astype(bool), index.cpu().numpy()[None], to_world[None],
+            to_og_view[None], goal_real.cpu().numpy(), to_og_view)
+
+
 class KITTI360Line(torch.utils.data.Dataset):
     """Line configuration (`KITTI360_im_8batch`, kitti360_im_8Batch.py): item idx = (frame idx // A, view idx % A); view k
     re-renders the frame's scan from the pose 5 * (k + 1) frames ahead and pairs it with that frame's own scan."""
@@ -121,6 +156,36 @@ class KITTI360Line(torch.utils.data.Dataset):
         item = assemble_view(self.load_scan(frame), self.load_scan(self.frames[wanted]), self.Tr_pose_world[frame],
                              self.Tr_pose_world[self.frames[wanted]], None, self.return_remission, self.rowMax,
                              self.colMax, self.device)
+        return item + (int(frame),)
+
+
+class KITTI360AllForOne(KITTI360Line):
+    """Inpainting configuration (`KITTI360_im_AllForOne`, kitti360_im_AllForOne.py:94-355): every view of a group re-renders
+    the frame's scan from the pose 2 * 5 frames ahead; view k looks at it from the origin `config.data.modifications[k]`."""
+
+    def __init__(self, root, config, drive="2013_05_28_drive_0000_sync", device="cuda"):
+        super().__init__(root, config, drive, device)
+        self.modifications = np.array(config.data.modifications)
+
+    def __getitem__(self, idx):
+        view, pose_num = idx % self.batchSize, idx // self.batchSize
+        frame = self.frames[pose_num]
+        wanted = min(pose_num + 2 * 5, len(self.frames) - 1)                   # goalMovement * movementModifier (:160-171)
+        item = assemble_view(self.load_scan(frame), self.load_scan(self.frames[wanted]), self.Tr_pose_world[frame],
+                             self.Tr_pose_world[self.frames[wanted]], self.modifications[view], self.return_remission,
+                             self.rowMax, self.colMax, self.device)
+        return item + (int(frame),)
+
+
+class KITTI360Densification(KITTI360AllForOne):
+    """Densification configuration (`KITTI360_im_simultaneous_densification`): the frame's own scan, thinned, seen from
+    `config.data.modifications[k]`; see `assemble_densification_view`."""
+
+    def __getitem__(self, idx):
+        view, pose_num = idx % self.batchSize, idx // self.batchSize
+        frame = self.frames[pose_num]
+        item = assemble_densification_view(self.load_scan(frame), self.Tr_pose_world[frame], self.modifications, view,
+                                           self.return_remission, self.rowMax, self.colMax, self.device)
         return item + (int(frame),)
 
 

@@ -5,7 +5,8 @@ sampler) and LiDARGen/runners/ncsn_runner_AllForOne.py:466-1000 (Inpainting.yml 
 translation sampler): checkpoint + EMA loading, existTotal mask preprocessing, the `doThis` ablation loop
 with the reference's hard-coded hyper-parameters, output post-processing and .npy naming.  It is a boundary
 row of SURVEY.md 8 (keep the API), not a kernel target; the data source is the synthetic generator unless
-`b200.data_root` points at KITTI-360 (Line configuration: `datasets.KITTI360Line`, row N2 of SURVEY 8f).
+`b200.data_root` points at KITTI-360 (`datasets.KITTI360Line` / `KITTI360AllForOne` / `KITTI360Densification`, row N2 of
+SURVEY 8f).
 """
 import logging
 import os
@@ -98,11 +99,10 @@ class _Base:
         cfg = self.config
         root = getattr(getattr(cfg, "b200", None), "data_root", None)
         if root:                                            # KITTI-360 on disk: row N2's GPU dataset assembly
-            if mode != "line":
-                raise NotImplementedError("b200.data_root is wired for the Line configuration (KITTI360_im_8batch); the "
-                                          "AllForOne / densification pose selections are arguments of datasets.assemble_view")
-            from .datasets import ItemBatches, KITTI360Line
-            return ItemBatches(KITTI360Line(root, cfg, device=cfg.device), cfg.sampling.batch_size)
+            from . import datasets
+            reader = {"line": datasets.KITTI360Line, "allforone": datasets.KITTI360AllForOne,
+                      "densification": datasets.KITTI360Densification}[mode]
+            return datasets.ItemBatches(reader(root, cfg, device=cfg.device), cfg.sampling.batch_size)
         return SyntheticMultiView(cfg.data.image_size, cfg.data.image_width, cfg.sampling.batch_size,
                                   cfg.sampling.actualBatchSize, mode=mode, seed=self.args.seed)
 

@@ -139,6 +139,7 @@ def synthetic_scan(n, seed):
 N2_SHAPE = (32, 256)           # rowMax, colMax of the fixture
 N2_FRAMES = 24
 N2_BATCH = 3                   # actualBatchSize: views per item group
+N2_MODIFICATIONS = [[0, 0, 0], [5, -5, 0], [-5, -5, 0]]     # config.data.modifications (first rows of Inpainting.yml)
 
 
 def n2_calibration():

@@ -148,3 +148,164 @@ def test_synthetic_batches_have_the_dataset_tuple_layout():
         assert float(real.min()) >= 0.0 and float(real[:, 0].max()) <= 1.0
         if mode == "densification":                                                              # target keeps every 4th beam
             assert not bool(mask[0, 0, 1].any()) and bool(mask[0, 0, 0].any()) and bool(mask[1, 0, 1].any())
+
+
+# ---- the other two datasets of the row: AllForOne (Inpainting.yml) and simultaneous densification (Densification.yml) ----
+GV = np.load(os.path.join(os.path.dirname(__file__), "golden", "dataset_assembly_variants.npz"))
+MODS = np.array(cases.N2_MODIFICATIONS)
+AFO_ITEMS, DEN_ITEMS = (4, 8), (0, 4)
+
+
+def _write_drive(root):
+    """synthetic drive with the reference's directory layout (KITTI-360 root)"""
+    cam_to_velo, cam_to_pose, poses = cases.n2_calibration()
+    drive = "2013_05_28_drive_0000_sync"
+    (root / "calibration").mkdir(parents=True)
+    (root / "data_poses" / drive).mkdir(parents=True)
+    data = root / "data_3d_raw" / drive / "velodyne_points" / "data"
+    data.mkdir(parents=True)
+    np.savetxt(root / "calibration" / "calib_cam_to_velo.txt", cam_to_velo[None])
+    np.savetxt(root / "calibration" / "calib_cam_to_pose.txt", cam_to_pose)
+    np.savetxt(root / "data_poses" / drive / "poses.txt", poses)
+    for f in poses[:, 0] - 1:
+        cases.n2_scan(f).tofile(data / (str(int(f)).zfill(10) + ".bin"))
+    import argparse
+    NS = argparse.Namespace
+    return NS(data=NS(channels=2, image_size=H, image_width=W, modifications=cases.N2_MODIFICATIONS),
+              sampling=NS(actualBatchSize=cases.N2_BATCH))
+
+
+def test_oracle_variants_match_reference_golden():
+    """the restatements of the AllForOne and densification items against the fixture made by executing the reference's own
+    `__getitem__` source (tests/golden/make_golden_n2_variants.py): bit-identical images, masks and matrices"""
+    cam_to_velo, cam_to_pose, poses = cases.n2_calibration()
+    frames, table = da.pose_chain(cam_to_velo, cam_to_pose[0], poses)
+
+    def same(r, t):
+        assert np.array_equal(r["toWorld"], GV[t + "toWorld"]) and np.array_equal(r["fromWorld"], GV[t + "fromWorld"])
+        assert np.array_equal(r["toOGView"], GV[t + "toOGView"])
+        assert np.array_equal(r["real"], GV[t + "real"]) and np.array_equal(r["goalDepth"], GV[t + "goal"])
+        assert np.array_equal(np.packbits(r["known"]), GV[t + "known"])
+        assert np.array_equal(np.packbits(r["notsky"]), GV[t + "notsky"]) and r["notsky"].all()
+        assert int((r["index"].astype(np.int32) != GV[t + "index"]).sum()) <= 50           # exact depth ties (quirk xii)
+
+    for idx in AFO_ITEMS:
+        view, pose = idx % cases.N2_BATCH, idx // cases.N2_BATCH
+        ahead = da.allforone_selection(pose, len(frames))
+        assert ahead == pose + 10
+        f0, f1 = frames[pose], frames[ahead]
+        r = da.assemble_view(cases.n2_scan(f0), cases.n2_scan(f1), table[f0], table[f1], H, W, origin=MODS[view])
+        assert int(f0) == int(GV[f"afo{idx}:scan"])
+        same(r, f"afo{idx}:")
+    for idx in DEN_ITEMS:
+        view, pose = idx % cases.N2_BATCH, idx // cases.N2_BATCH
+        f0 = frames[pose]
+        r = da.assemble_view_densification(cases.n2_scan(f0), table[f0], MODS, view, H, W)
+        same(r, f"den{idx}:")
+        assert np.array_equal(r["fromWorld"][0], r["toOGView"])                           # no pose change in this dataset
+        assert 0 < len(r["thinned"]) < 0.75 * H * W                                       # at most one point per kept pixel
+        if view == 0:                                                                     # only the blanked quarter is unknown
+            assert not r["known"][:, :, :W // 4].any() and r["known"][:, :, W // 4:].all()
+    assert da.allforone_selection(len(frames) - 3, len(frames)) == len(frames) - 1        # the drive ends: last pose
+
+
+def test_file_backed_variants_select_frames_and_origins(tmp_path, monkeypatch):
+    """CPU: which scans, poses and origins `KITTI360AllForOne` / `KITTI360Densification` hand to the assembly (the CUDA
+    assembly is replaced by a recorder; the gpu test below runs the real one)"""
+    import sdpc_b200  # noqa: F401
+    from sdpc_b200 import datasets
+    cfg = _write_drive(tmp_path / "KITTI-360")
+    calls = []
+
+    def fake_view(scan, goal, t_src, t_dst, origin, remission, rows, cols, device):
+        calls.append(("view", scan, goal, t_src, t_dst, origin, remission, rows, cols))
+        return tuple(range(8))
+
+    def fake_dens(scan, t, mods, view, remission, rows, cols, device):
+        calls.append(("dens", scan, t, mods, view, remission, rows, cols))
+        return tuple(range(8))
+
+    monkeypatch.setattr(datasets, "assemble_view", fake_view)
+    monkeypatch.setattr(datasets, "assemble_densification_view", fake_dens)
+    afo = datasets.KITTI360AllForOne(str(tmp_path / "KITTI-360"), cfg, device="cpu")
+    frames, table = afo.frames, afo.Tr_pose_world
+    assert len(afo) == len(frames) * cases.N2_BATCH
+    item = afo[8]                                                       # frame 2, view 2
+    kind, scan, goal, t_src, t_dst, origin, remission, rows, cols = calls.pop()
+    assert kind == "view" and item == tuple(range(8)) + (int(frames[2]),) and item[-1] == int(GV["afo8:scan"])
+    assert np.array_equal(scan, cases.n2_scan(frames[2])) and np.array_equal(goal, cases.n2_scan(frames[12]))
+    assert np.array_equal(t_src, table[frames[2]]) and np.array_equal(t_dst, table[frames[12]])
+    assert np.array_equal(np.linalg.inv(t_dst)[None], GV["afo8:fromWorld"])
+    assert np.array_equal(origin, MODS[2]) and remission and (rows, cols) == (H, W)
+    afo[3 * (len(frames) - 2) + 1]                                      # two frames before the end: clamps to the last pose
+    assert np.array_equal(calls.pop()[4], table[frames[-1]])
+    den = datasets.KITTI360Densification(str(tmp_path / "KITTI-360"), cfg, device="cpu")
+    item = den[4]                                                       # frame 1, view 1
+    kind, scan, t, mods, view, remission, rows, cols = calls.pop()
+    assert kind == "dens" and item[-1] == int(frames[1]) and view == 1 and np.array_equal(mods, MODS)
+    assert np.array_equal(scan, cases.n2_scan(frames[1])) and np.array_equal(t[None], GV["den4:toWorld"])
+    with pytest.raises(RuntimeError):
+        den.load_scan(99999)
+
+
+def test_runner_picks_the_reader_of_its_configuration(tmp_path):
+    """CPU: with `b200.data_root` set the runners read KITTI-360 through the dataset of their configuration (constructors
+    only parse the calibration and pose files)"""
+    import argparse
+    import sdpc_b200  # noqa: F401
+    from sdpc_b200 import datasets, runner
+    cfg = _write_drive(tmp_path / "KITTI-360")
+    cfg.b200 = argparse.Namespace(data_root=str(tmp_path / "KITTI-360"))
+    cfg.device = "cpu"
+    cfg.sampling.batch_size = 2 * cases.N2_BATCH
+    base = runner._Base(argparse.Namespace(seed=0), cfg)
+    for mode, cls in (("line", datasets.KITTI360Line), ("allforone", datasets.KITTI360AllForOne),
+                      ("densification", datasets.KITTI360Densification)):
+        data = base.dataset(mode)
+        assert type(data) is datasets.ItemBatches and type(data.dataset) is cls
+        assert len(data) == cases.N2_FRAMES * cases.N2_BATCH // cfg.sampling.batch_size
+    cfg.b200.data_root = None
+    assert type(base.dataset("allforone")).__name__ == "SyntheticMultiView"
+
+
+def test_densification_host_logic_on_stand_in_kernels(monkeypatch):
+    """CPU: the host side of `assemble_densification_view` (which points survive the thinning and in which order, the
+    view-0 mask, the returned matrices) with the two C-ABI calls replaced by the oracle's projection / post-processing on
+    CPU tensors; the result must equal the reference fixture.  The CUDA kernels themselves are covered by the gpu tests."""
+    import contextlib
+    import torch
+    import sdpc_b200  # noqa: F401
+    from oracle import lidar_projection_ref as lp
+    from sdpc_b200 import cabi, datasets
+
+    def project(pc, origin, remission, rows, cols):
+        r = lp.point_cloud_to_range_image(pc.numpy(), np.asarray(origin), remission, rows, cols)
+        t = torch.from_numpy
+        return (t(r["depth"].copy()), t(r["intensity"].copy()), t(r["obfuscation"].astype(np.uint8)),
+                t(r["sky"].astype(np.uint8)), t(r["index"].copy()))
+
+    def post(lib, dev, depth, inten, obf, sky, rows, cols, want_masks):
+        real, known, notsky = da.postprocess(depth.numpy(), inten.numpy(), obf.numpy().astype(bool) if want_masks else None,
+                                             sky.numpy().astype(bool) if want_masks else None)
+        if not want_masks:
+            return torch.from_numpy(real), None, None
+        return torch.from_numpy(real), torch.from_numpy(known.astype(np.uint8)), torch.from_numpy(notsky.astype(np.uint8))
+
+    monkeypatch.setattr(datasets, "project_device", project)
+    monkeypatch.setattr(datasets, "_postprocess", post)
+    monkeypatch.setattr(cabi, "load", lambda: None)
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    monkeypatch.setattr(torch.cuda, "device", lambda dev: contextlib.nullcontext())
+    cam_to_velo, cam_to_pose, poses = cases.n2_calibration()
+    frames, table = datasets.velo_to_world_poses(cam_to_velo, cam_to_pose[0], poses)
+    for idx in DEN_ITEMS:
+        view, pose = idx % cases.N2_BATCH, idx // cases.N2_BATCH
+        real, known, notsky, index, toW, fromW, goal, toOG = datasets.assemble_densification_view(
+            cases.n2_scan(frames[pose]), table[frames[pose]], cases.N2_MODIFICATIONS, view, rowMax=H, colMax=W, device="cpu")
+        t = f"den{idx}:"
+        assert np.array_equal(real, GV[t + "real"]) and np.array_equal(goal, GV[t + "goal"])
+        assert known.dtype == bool and np.array_equal(np.packbits(known), GV[t + "known"])
+        assert notsky.dtype == bool and np.array_equal(np.packbits(notsky), GV[t + "notsky"])
+        assert np.array_equal(index.astype(np.int32), GV[t + "index"])
+        assert np.array_equal(toW, GV[t + "toWorld"]) and np.array_equal(fromW, GV[t + "fromWorld"])
+        assert np.array_equal(toOG, GV[t + "toOGView"])
