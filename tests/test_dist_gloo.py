@@ -150,3 +150,22 @@ def test_reference_print_quirk_is_kept(emul_path, capsys):
     _run("trans", 2, None, lib)
     out = capsys.readouterr().out
     assert "level:" not in out and out.count("grad_ref: 1") == 1
+
+
+def test_single_view_call_is_accepted(emul_path):
+    """deliberate deviation (SURVEY.md 8a quirk viii): the reference's pose sampler cannot be called with one view
+    (`torch.squeeze` turns its [1,1,4,4] poses into [4,4] and the batched product fails, KITTISampling.py:22-23,185);
+    here B = A = 1 runs: the view is re-projected into itself"""
+    import sdpc_b200  # noqa: F401
+    from sdpc_b200 import samplers
+    from tests.golden import cases
+    case = cases.small_multiview("pose")
+    sig = cases.short_sigmas()
+    one = {k: v[:1].clone() for k, v in case.items() if k in ("x", "refer", "mask", "sky", "toWorld", "fromWorld")}
+    im, targets, shared = samplers.anneal_Langevin_dynamics_inpainting_simultaneous_basic_kitti(
+        one["x"], one["refer"], one["mask"], one["sky"], None, 0, 5, 10, cases.fake_score(sig), sig, one["fromWorld"],
+        one["toWorld"], 1, n_steps_each=2, step_lr=6.2e-6, existMask=case["exist"], denoise=True, verbose=False,
+        grad_ref=1, correlation_coefficient=0.01, _lib=_emul_lib(emul_path))
+    assert len(im) == 3 and targets == [] and all(tuple(t.shape) == (1, 2, case["H"], case["W"]) for t in im + shared)
+    assert all(bool(torch.isfinite(t).all()) for t in im)
+    assert float(shared[0].abs().max()) > 0.0                         # the cross-view block ran and filled pixels
