@@ -106,7 +106,33 @@ class _Base:
         return SyntheticMultiView(cfg.data.image_size, cfg.data.image_width, cfg.sampling.batch_size,
                                   cfg.sampling.actualBatchSize, mode=mode, seed=self.args.seed)
 
-    def save_outputs(self, doThis, saveNum, n_views, all_outputs):
+    def save_grid(self, images, nrow, name):
+        """PNG rendering of a [N,3,H,W] stack, `make_grid` + `save_image` like the reference (presentation only: a missing
+        torchvision is logged, the .npy arrays next to it are the data)."""
+        try:
+            from torchvision.utils import make_grid, save_image
+        except ImportError as e:
+            logging.warning("PNG grid %s not written: %s", name, e)
+            return
+        save_image(make_grid(images.cpu().detach().float(), max(1, int(nrow))), os.path.join(self.args.image_folder, name))
+
+    def save_inputs(self, doThis, saveNum, grid_tag, refer_images_full, refer_mask_full, goalImages, refer_sky):
+        """Known pixels, ground truth and sky mask of the batch, written once per batch (doThis == 0):
+        ncsn_runner_kitti_simultaneous.py:650-696 (grids named by batch number), ncsn_runner_AllForOne.py:662-711 (by ids)."""
+        cfg, out = self.config, self.args.image_folder
+        tag = '_{}.pth'.format(cfg.sampling.ckpt_id)
+        nrow = int(np.sqrt(cfg.sampling.batch_size))
+        known = _to_grid_layout(inverse_data_transform(cfg, refer_images_full * refer_mask_full))
+        self.save_grid(known, nrow, str(doThis) + '_' + grid_tag + '_Input_image_grid_{}.png'.format(cfg.sampling.ckpt_id))
+        np.save(os.path.join(out, str(doThis) + '_' + saveNum + '_Input_completion' + tag), known.cpu().detach().numpy())
+        goal = _to_grid_layout(inverse_data_transform(cfg, goalImages))
+        self.save_grid(goal, nrow, str(doThis) + '_' + grid_tag + '_GT_image_grid_{}.png'.format(cfg.sampling.ckpt_id))
+        np.save(os.path.join(out, str(doThis) + '_' + saveNum + '_GT_completion' + tag), goal.cpu().detach().numpy())
+        np.save(os.path.join(out, str(doThis) + '_' + saveNum + '_SKY' + tag), refer_sky.clone().cpu().detach().numpy())
+
+    def save_outputs(self, doThis, saveNum, n_views, all_outputs, grid_tag=None, nrow=None, shared_initial=False):
+        """`all_outputs[-1]` as `<doThis>_<ids>_Masked_completion_<ckpt>.pth.npy` (+ PNG grid); with `shared_initial` also
+        `all_outputs[-2]` as `..._Shared_completion_initial<ckpt>.pth.npy` (ncsn_runner_AllForOne.py:911,976-994)."""
         cfg = self.config
         shp = (n_views, cfg.data.channels, cfg.data.image_size, cfg.data.image_width)
         sample = inverse_data_transform(cfg, all_outputs[-1].view(*shp))
@@ -114,6 +140,15 @@ class _Base:
         np.save(os.path.join(self.args.image_folder,
                              str(doThis) + '_' + saveNum + '_Masked_completion_{}.pth'.format(cfg.sampling.ckpt_id)),
                 masked.cpu().detach().numpy())
+        nrow = int(np.sqrt(cfg.sampling.batch_size)) if nrow is None else nrow
+        grid_tag = saveNum if grid_tag is None else grid_tag
+        self.save_grid(masked, nrow, str(doThis) + '_' + grid_tag + '_Masked_image_grid_{}.png'.format(cfg.sampling.ckpt_id))
+        if shared_initial:
+            first = _to_grid_layout(inverse_data_transform(cfg, all_outputs[-2].view(*shp)))
+            np.save(os.path.join(self.args.image_folder,
+                                 str(doThis) + '_' + saveNum + '_Shared_completion_initial{}.pth'.format(cfg.sampling.ckpt_id)),
+                    first.cpu().detach().numpy())
+            self.save_grid(first, nrow, str(doThis) + '_' + saveNum + '_Shared_image_grid_initial{}.png'.format(cfg.sampling.ckpt_id))
         return masked
 
 
@@ -145,13 +180,8 @@ class NCSNRunnerKITTISimultaneous(_Base):
                 toWorld, fromWorld = toWorld_full.clone(), fromWorld_full.clone()
                 init_samples = torch.rand(Bsz, cfg.data.channels, cfg.data.image_size, cfg.data.image_width, device=dev)
                 if doThis == 0:
-                    tag = '_{}.pth'.format(cfg.sampling.ckpt_id)
-                    np.save(os.path.join(args.image_folder, str(doThis) + '_' + saveNum + '_Input_completion' + tag),
-                            _to_grid_layout(inverse_data_transform(cfg, refer_images_full * refer_mask_full)).numpy())
-                    np.save(os.path.join(args.image_folder, str(doThis) + '_' + saveNum + '_GT_completion' + tag),
-                            _to_grid_layout(inverse_data_transform(cfg, goalImages)).numpy())
-                    np.save(os.path.join(args.image_folder, str(doThis) + '_' + saveNum + '_SKY' + tag),
-                            refer_sky.clone().cpu().detach().numpy())
+                    self.save_inputs(doThis, saveNum, str(batchesToDo), refer_images_full, refer_mask_full, goalImages,
+                                     refer_sky)
                 start_time = time.time()
                 if doThis == A - 1:                                                           # LiDARGen baseline arm
                     n_views = Bsz
@@ -177,7 +207,8 @@ class NCSNRunnerKITTISimultaneous(_Base):
                 timeTaken[doThis] += (time.time() - start_time)
                 print("--- %s seconds ---" % (timeTaken[doThis] / (batchesToDo + 1)))
                 np.save(os.path.join(args.image_folder, str(doThis) + '_' + saveNum + '_TimeTaken.npy'), timeTaken[doThis])
-                self.save_outputs(doThis, saveNum, n_views, all_outputs)
+                self.save_outputs(doThis, saveNum, n_views, all_outputs, grid_tag=str(batchesToDo),
+                                  nrow=int(np.sqrt((doThis + 2) * G)) if doThis < A - 2 else None)       # :872-884
         return 0
 
 
@@ -212,6 +243,8 @@ class NCSNRunnerAllForOne(_Base):
                 init_samples = torch.rand(Bsz, cfg.data.channels, cfg.data.image_size, cfg.data.image_width, device=dev)
                 img = (cfg.data.channels, cfg.data.image_size, cfg.data.image_width)
                 one = (1, cfg.data.image_size, cfg.data.image_width)
+                if doThis == 0:
+                    self.save_inputs(doThis, saveNum, saveNum, refer_images_full, refer_mask_full, goalImages, refer_sky)
 
                 def keep(t, shape, k):
                     t = torch.reshape(t, (G, A, -1))
@@ -236,5 +269,11 @@ class NCSNRunnerAllForOne(_Base):
                 timeTaken[doThis] += (time.time() - start_time)
                 print("--- %s seconds ---" % (timeTaken[doThis] / (batchesToDo + 1)))
                 np.save(os.path.join(args.image_folder, str(doThis) + '_' + saveNum + '_TimeTaken.npy'), timeTaken[doThis])
-                self.save_outputs(doThis, saveNum, n_views, all_outputs)
+                if doThis + toAdd == A - 1:                                                    # :944-994
+                    nrow = int(np.sqrt(G))
+                elif doThis + toAdd < A - 2:
+                    nrow = int(np.sqrt((doThis + 2) * G))
+                else:
+                    nrow = None
+                self.save_outputs(doThis, saveNum, n_views, all_outputs, nrow=nrow, shared_initial=True)
         return 0

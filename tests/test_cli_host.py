@@ -94,3 +94,79 @@ def test_shipped_configs_carry_the_reference_values(name):
     for sec in ("data", "model", "sampling"):
         assert ours[sec] == ref[sec], (name, sec)
     assert set(ours) - {"data", "model", "sampling"} == {"b200"}
+
+
+@pytest.mark.parametrize("name,arms", [("Line.yml", 3), ("Inpainting.yml", 3), ("Densification.yml", 2)])
+def test_runner_flow_with_stand_in_samplers(tmp_path, monkeypatch, name, arms):
+    """CPU dry run of `runner.sample()`: the three sampler entry points and the model loader are replaced by stand-ins that
+    check what they are called with and return image lists of the right shapes, so the ablation loop (`doThis`), the view
+    selection per group and every output file of a batch are exercised without a GPU
+    (ncsn_runner_kitti_simultaneous.py:527-893, ncsn_runner_AllForOne.py:540-994)"""
+    import glob
+    import numpy as np
+    from sdpc_b200 import runner
+    cfg = yaml.safe_load(open(os.path.join(CFG_DIR, name)))
+    cfg["sampling"].update(batch_size=6, actualBatchSize=3, n_steps_each=1)
+    cfg["data"].update(image_size=16, image_width=64)
+    cfg["model"].update(num_classes=4)
+    cfg["b200"].update(max_batches=1)
+    p = tmp_path / name
+    p.write_text(yaml.safe_dump(cfg))
+    calls = []
+
+    def images(x):
+        return [torch.full(tuple(x.shape), 0.25).reshape(-1), torch.full(tuple(x.shape), 0.75).reshape(-1)]
+
+    def pose(x, refer, mask, sky, idx, start, setting, allowance, score, sigmas, fromW, toW, A, n_steps, lr, existMask=None,
+             denoise=True, verbose=True, grad_ref=0.1, correlation_coefficient=0.1, sampling_step=16):
+        assert x.shape == refer.shape == mask.shape and sky.shape[0] == x.shape[0] and x.shape[0] % A == 0
+        assert tuple(fromW.shape) == (x.shape[0], 4, 4) and tuple(toW.shape) == (x.shape[0], 4, 4)
+        assert (start, setting, allowance, grad_ref, correlation_coefficient) == (2, 5, 10, 1, 0.01) and len(sigmas) == 4
+        calls.append(("pose", x.shape[0], A))
+        return images(x), [], []
+
+    def trans(x, refer, mask, sky, idx, start, setting, score, sigmas, mods, A, n_steps, lr, existMask=None, denoise=True,
+              verbose=True, grad_ref=0.1, correlation_coefficient=0.1, sampling_step=16):
+        assert x.shape == refer.shape == mask.shape and x.shape[0] % A == 0 and mods.shape[0] >= A and mods.shape[1] == 3
+        assert (start, setting, grad_ref, correlation_coefficient) == (2, 7, 1, 0.01)
+        calls.append(("trans", x.shape[0], A))
+        return images(x), [], []
+
+    def single(x, refer, mask, score, sigmas, n_steps, lr, denoise=True, verbose=True, grad_ref=0.1, sampling_step=16):
+        assert x.shape == refer.shape == mask.shape and grad_ref == 1
+        calls.append(("single", x.shape[0], 1))
+        return images(x), []
+
+    monkeypatch.setattr(runner, "anneal_Langevin_dynamics_inpainting_simultaneous_basic_kitti", pose)
+    monkeypatch.setattr(runner, "anneal_Langevin_dynamics_inpainting_simultaneous_basic", trans)
+    monkeypatch.setattr(runner, "anneal_Langevin_dynamics_inpainting", single)
+    monkeypatch.setattr(runner._Base, "load_score", lambda self: None)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)      # main.py then configures cuda:0; nothing below touches it
+    real_rand = torch.rand
+    monkeypatch.setattr(torch, "rand", lambda *a, **k: real_rand(*a, **{**k, "device": "cpu"}))
+    exp = str(tmp_path / "exp")
+    args, config = cli.parse_args_and_config(["--sample", "--ni", "--config", str(p), "--exp", exp, "-i", "out"])
+    config.device = torch.device("cpu")
+    cls = runner.NCSNRunnerKITTISimultaneous if name == "Line.yml" else runner.NCSNRunnerAllForOne
+    assert cls(args, config).sample() == 0
+    if name == "Line.yml":            # 2 views of each group, then all 3, then the single-view baseline on all 6
+        assert calls == [("pose", 4, 2), ("pose", 6, 3), ("single", 6, 1)]
+    elif name == "Inpainting.yml":    # same arms, but the baseline only runs on view 0 of each group
+        assert calls == [("trans", 4, 2), ("trans", 6, 3), ("single", 2, 1)]
+    else:                             # densification: the full group, then the baseline
+        assert calls == [("trans", 6, 3), ("single", 2, 1)]
+    out = os.path.join(exp, "image_samples", "out")
+    count = lambda pat: len(glob.glob(os.path.join(out, pat)))
+    assert count("*_Masked_completion_897.pth.npy") == arms and count("*_TimeTaken.npy") == arms
+    assert count("*_Masked_image_grid_897.png") == arms
+    assert count("0_*_Input_completion_897.pth.npy") == 1 and count("0_*_GT_completion_897.pth.npy") == 1
+    assert count("0_*_SKY_897.pth.npy") == 1 and count("*_Input_image_grid_897.png") == 1 and count("*_GT_image_grid_897.png") == 1
+    assert count("toWorld_*.npy") == 1 and count("fromWorld_*.npy") == 1
+    assert count("*_Shared_completion_initial897.pth.npy") == (0 if name == "Line.yml" else arms)
+    for f in glob.glob(os.path.join(out, "*_Masked_completion_897.pth.npy")):
+        a = np.load(f)
+        n = [c for c in calls][int(os.path.basename(f)[0])][1]
+        assert a.shape == (2 * n, 3, 16, 64) and float(a.min()) == 0.75 and float(a.max()) == 0.75
+    for f in glob.glob(os.path.join(out, "*_Shared_completion_initial897.pth.npy")):
+        assert float(np.load(f).max()) == 0.25

@@ -40,6 +40,10 @@ def test_cli_sample_writes_reference_outputs(tmp_path, name, n_variants):
         a = np.load(f)
         assert a.ndim == 4 and a.shape[1:] == (3, 16, 64) and a.shape[0] % 2 == 0
         assert np.isfinite(a).all() and a.min() >= 0.0 and a.max() <= 1.0          # inverse_data_transform clamp
+    for kind in ("Input_completion_897", "GT_completion_897", "SKY_897"):          # once per batch (doThis = 0)
+        assert len(glob.glob(os.path.join(out, "0_*_" + kind + ".pth.npy"))) == 1, (kind, files)
+    shared = glob.glob(os.path.join(out, "*_Shared_completion_initial897.pth.npy"))
+    assert len(shared) == (0 if name == "Line.yml" else n_variants), files     # only the AllForOne runner writes them
     if name == "Line.yml":
         # doThis = 0: 2 of 3 views per group, 2 groups -> 4 views -> [8,3,16,64]; last variant = baseline on all 6 views
         assert np.load(masked[0]).shape[0] == 8 and np.load(masked[-1]).shape[0] == 12

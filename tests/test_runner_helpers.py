@@ -95,3 +95,39 @@ def test_exist_mask_on_the_reference_fixture():
     m = runner.exist_mask(cfg, 2).numpy()
     assert m.shape == (2, 64, 1024) and np.array_equal(m[0], m[1])
     assert abs(m[0].mean() - 0.680) < 5e-4 and int(m[0].any(axis=1).sum()) == 57
+
+
+def test_runner_output_files_have_the_reference_names_and_layouts(tmp_path):
+    """CPU: the files a batch leaves behind (ncsn_runner_kitti_simultaneous.py:650-696,838-893; ncsn_runner_AllForOne.py:
+    662-711,905-994): known pixels / ground truth / sky once per batch, the completion (and, for the AllForOne runner, the
+    second-to-last entry of the sampler's image list) per ablation arm, each as [2B,3,H,W] float arrays clamped to [0,1] plus
+    a PNG grid rendered like `make_grid` + `save_image`"""
+    B, Hs, Ws = 4, 8, 32
+    cfg = NS(data=NS(channels=2, image_size=Hs, image_width=Ws, logit_transform=False, rescaled=False),
+             sampling=NS(batch_size=B, actualBatchSize=2, ckpt_id=897), device="cpu")
+    base = runner._Base(NS(image_folder=str(tmp_path), seed=0), cfg)
+    g = torch.Generator().manual_seed(5)
+    refer = torch.rand(B, 2, Hs, Ws, generator=g, dtype=torch.float64)
+    mask = torch.rand(B, 2, Hs, Ws, generator=g) > 0.4
+    goal = torch.rand(B, 2, Hs, Ws, generator=g, dtype=torch.float64)
+    sky = torch.ones(B, 1, Hs, Ws, dtype=torch.bool)
+    base.save_inputs(0, "11_12_", "0", refer, mask, goal, sky)
+    load = lambda name: np.load(os.path.join(str(tmp_path), name))
+    inp, gt = load("0_11_12__Input_completion_897.pth.npy"), load("0_11_12__GT_completion_897.pth.npy")
+    assert inp.shape == (2 * B, 3, Hs, Ws) and gt.shape == (2 * B, 3, Hs, Ws)
+    assert np.array_equal(inp[:B, 0], (refer * mask)[:, 0].numpy()) and np.array_equal(inp[B:, 2], (refer * mask)[:, 1].numpy())
+    assert np.array_equal(gt[:B, 1], goal[:, 0].numpy())
+    assert np.array_equal(load("0_11_12__SKY_897.pth.npy"), sky.numpy())
+    outs = [torch.randn(3 * 2 * Hs * Ws, generator=g), torch.randn(3 * 2 * Hs * Ws, generator=g)]       # flat, like the samplers' snapshots viewed by the runner
+    masked = base.save_outputs(1, "11_12_", 3, outs, grid_tag="0", nrow=2, shared_initial=True)
+    m = load("1_11_12__Masked_completion_897.pth.npy")
+    assert m.shape == (6, 3, Hs, Ws) and np.array_equal(m, masked.numpy()) and m.min() >= 0.0 and m.max() <= 1.0
+    assert np.array_equal(m[:3, 0], outs[-1].view(3, 2, Hs, Ws)[:, 0].clamp(0, 1).numpy())
+    first = load("1_11_12__Shared_completion_initial897.pth.npy")
+    assert np.array_equal(first[3:, 0], outs[-2].view(3, 2, Hs, Ws)[:, 1].clamp(0, 1).numpy())
+    pngs = sorted(f for f in os.listdir(str(tmp_path)) if f.endswith(".png"))
+    assert pngs == ["0_0_GT_image_grid_897.png", "0_0_Input_image_grid_897.png", "1_0_Masked_image_grid_897.png",
+                    "1_11_12__Shared_image_grid_initial897.png"]
+    from PIL import Image
+    im = Image.open(os.path.join(str(tmp_path), "1_0_Masked_image_grid_897.png"))
+    assert im.size == (2 * (Ws + 2) + 2, 3 * (Hs + 2) + 2)                       # make_grid: 6 tiles, 2 per row, 2 px padding
