@@ -39,3 +39,15 @@ cat gpurun_out/r2_small_batches.log
 # BASELINE config 5 on one GPU: 16 / 32 / 64 views in groups of 8 (forward + step per call)
 for B in 16 32 64; do python tools/quick_time.py $B bf16 8 2>&1 | grep -E "forward|step"; done > gpurun_out/r2_view_sweep.log
 cat gpurun_out/r2_view_sweep.log
+# library variants built from tools/patches with tools/build_variant.py (gpurun_ab/*.so travels with the snapshot, the shipped
+# library is untouched): score-network outputs bit for bit against the shipped build, then the forward time of both, alternating
+if ls gpurun_ab/*.so > /dev/null 2>&1; then
+  timeout 120 python tools/ab_probe.py run gpurun_out/ab_def 0 > gpurun_out/r2_ab_def.log 2>&1
+  for lib in gpurun_ab/*.so; do
+    name=$(basename $lib .so)
+    SDPC_LIB=$PWD/$lib timeout 120 python tools/ab_probe.py run gpurun_out/ab_$name 0 > gpurun_out/r2_ab_$name.log 2>&1
+    python tools/ab_probe.py compare gpurun_out/ab_def gpurun_out/ab_$name | tee gpurun_out/r2_ab_${name}_cmp.log
+    bash tools/gpu_ab_lib.sh $lib 2>&1 | tee gpurun_out/r2_ab_${name}_time.log
+  done
+  rm -f gpurun_out/ab_*.npy
+fi
