@@ -39,6 +39,17 @@ cat gpurun_out/r2_small_batches.log
 # BASELINE config 5 on one GPU: 16 / 32 / 64 views in groups of 8 (forward + step per call)
 for B in 16 32 64; do python tools/quick_time.py $B bf16 8 2>&1 | grep -E "forward|step"; done > gpurun_out/r2_view_sweep.log
 cat gpurun_out/r2_view_sweep.log
+# the same switch in a variant library (tools/build_variant.py gpurun_ab/lib_x3cl.so tools/patches/x3_cluster.patch): the switch is
+# off by default, so the generic loop below checks that the variant equals the shipped build; this block turns it on
+if [ -f gpurun_ab/lib_x3cl.so ]; then
+  timeout 120 python tools/ab_probe.py run gpurun_out/ab_def 0 > gpurun_out/r2_ab_def.log 2>&1
+  SDPC_LIB=$PWD/gpurun_ab/lib_x3cl.so SDPC_X3_CLUSTER=1 timeout 120 python tools/ab_probe.py run gpurun_out/ab_x3cl_on 0 > gpurun_out/r2_ab_x3cl_on.log 2>&1
+  python tools/ab_probe.py compare gpurun_out/ab_def gpurun_out/ab_x3cl_on | tee gpurun_out/r2_ab_x3cl_on_cmp.log
+  for i in 1 2; do
+    python tools/quick_time.py 8 bf16x3 2>&1 | grep forward
+    SDPC_LIB=$PWD/gpurun_ab/lib_x3cl.so SDPC_X3_CLUSTER=1 python tools/quick_time.py 8 bf16x3 2>&1 | grep forward
+  done | tee gpurun_out/r2_x3cl_time.log
+fi
 # library variants built from tools/patches with tools/build_variant.py (gpurun_ab/*.so travels with the snapshot, the shipped
 # library is untouched): score-network outputs bit for bit against the shipped build, then the forward time of both, alternating
 if ls gpurun_ab/*.so > /dev/null 2>&1; then
