@@ -36,8 +36,12 @@ VIEWS_PER_GPU = 8
 STEP_LR = 6.2e-6
 
 
-WORKLOAD = ("Line.yml step (a-4): NCSN_LiDAR_small forward + Langevin update + cross-view (setting 5, minStepToShare "
-            "passed), 8 line poses per GPU (B=A=8), 2x64x1024, random-init 29.7M-param net, noise level 116/232")
+def workload(B=VIEWS_PER_GPU, A=VIEWS_PER_GPU):
+    return ("Line.yml step (a-4): NCSN_LiDAR_small forward + Langevin update + cross-view (setting 5, minStepToShare "
+            f"passed), {B} line poses per GPU (B={B}, A={A}), 2x64x1024, random-init 29.7M-param net, noise level 116/232")
+
+
+WORKLOAD = workload()
 
 
 def parse():
@@ -48,6 +52,9 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default=os.environ.get("SDPC_PRECISION", "bf16"), choices=["bf16", "bf16x3", "tf32", "fp32"])
     ap.add_argument("--views-per-gpu", type=int, default=VIEWS_PER_GPU)
+    ap.add_argument("--group-size", type=int, default=8,
+                    help="actualBatchSize A: views that share information; --views-per-gpu 16/32/64 with the default 8 is "
+                         "BASELINE.json's view-count sweep (groups of 8)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity-arm", action="store_true", help="skip the extra bf16x3 (fp32-parity) timing")
     return ap.parse_args()
@@ -60,8 +67,10 @@ def config_ns(device):
                      sigma_dist="geometric", sigma_begin=50, sigma_end=0.01, spec_norm=False), device=device)
 
 
-def synthetic_group(B, seed):
-    """B views of one group: the dataset tuple of kitti360_im_8Batch.py:304 with synthetic content."""
+def synthetic_group(B, seed, A=None):
+    """B views in groups of A (default: one group): the dataset tuple of kitti360_im_8Batch.py:304 with synthetic content
+    (SURVEY 8d)."""
+    A = B if A is None else A
     import numpy as np
     import torch
     from tests.golden import cases
@@ -70,7 +79,7 @@ def synthetic_group(B, seed):
     mask = torch.from_numpy((r.uniform(size=(B, 1, H, W)) < 0.6).astype(np.int32)).repeat(1, 2, 1, 1).contiguous()
     sky = torch.ones(B, 1, H, W, dtype=torch.bool)
     exist = torch.from_numpy(r.uniform(size=(1, H, W)) < 0.68).repeat(B, 1, 1).contiguous()
-    to_world, from_world = cases.line_poses(B, B, step=5.0, yaw=0.01)
+    to_world, from_world = cases.line_poses(B, A, step=5.0, yaw=0.01)
     x0 = torch.from_numpy(r.uniform(size=(B, 2, H, W)).astype(np.float32))
     return dict(x=x0, refer=refer, mask=mask, sky=sky, exist=exist, toWorld=to_world, fromWorld=from_world)
 
@@ -204,12 +213,15 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B = args.views_per_gpu
-    g = synthetic_group(B, 1234 + rank)
+    A = min(B, args.group_size)
+    if B % A:
+        raise SystemExit(f"--views-per-gpu {B} is not a multiple of --group-size {A}")
+    g = synthetic_group(B, 1234 + rank, A)
     cfg = config_ns(dev)
     sig = get_sigmas(cfg).cpu().numpy()
     torch.manual_seed(1234)                                           # random-init weights (nn.Conv2d-style init of the module)
     net = NCSN_LiDAR_small(cfg, precision=args.precision).to(dev)
-    run = StepRunner((B, 2, H, W), dev, g["refer"], g["mask"], g["sky"], g["exist"], B, cabi.SDPC_VARIANT_POSE,
+    run = StepRunner((B, 2, H, W), dev, g["refer"], g["mask"], g["sky"], g["exist"], A, cabi.SDPC_VARIANT_POSE,
                      to_world=g["toWorld"], from_world=g["fromWorld"])
     x = g["x"].to(dev)
     labels = torch.full((B,), LEVEL, device=dev, dtype=torch.long)
@@ -327,8 +339,9 @@ def run_b200(args):
         "metric": "view-steps/sec", "value": value, "unit": "view-steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
-        "config": {"workload": WORKLOAD,
-                   "views_per_gpu": B, "global_views": world * B, "parallelism": f"views x{world} (one group per rank)",
+        "config": {"workload": workload(B, A),
+                   "views_per_gpu": B, "group_size": A, "global_views": world * B,
+                   "parallelism": f"views x{world} ({B // A} group{'s' if B // A > 1 else ''} of {A} per rank)",
                    "l2": "per-step working set (activations, >2 GB) exceeds the 126 MB L2; no explicit flush",
                    "exchange": "1-float all-reduce(MAX) per step (tooHigh gate)" if world > 1 else "none"},
         "e2e": {"value": e2e_value, "unit": "view-steps/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": 2 * nbytes,
