@@ -62,3 +62,6 @@ if ls gpurun_ab/*.so > /dev/null 2>&1; then
   done
   rm -f gpurun_out/ab_*.npy
 fi
+# the same sweep through bench.py (full JSON line per view count: value, e2e, roofline)
+for B in 16 32 64; do timeout 600 python bench.py --views-per-gpu $B --steps 5 --warmup 3 --no-cpu-baseline --no-parity-arm 2>&1 | tail -1; done > gpurun_out/r2_bench_sweep.log
+cut -c1-260 gpurun_out/r2_bench_sweep.log
