@@ -111,10 +111,9 @@ class _Base:
         torchvision is logged, the .npy arrays next to it are the data)."""
         try:
             from torchvision.utils import make_grid, save_image
-        except ImportError as e:
+            save_image(make_grid(images.cpu().detach().float(), max(1, int(nrow))), os.path.join(self.args.image_folder, name))
+        except ImportError as e:                        # torchvision or its PIL back end
             logging.warning("PNG grid %s not written: %s", name, e)
-            return
-        save_image(make_grid(images.cpu().detach().float(), max(1, int(nrow))), os.path.join(self.args.image_folder, name))
 
     def save_inputs(self, doThis, saveNum, grid_tag, refer_images_full, refer_mask_full, goalImages, refer_sky):
         """Known pixels, ground truth and sky mask of the batch, written once per batch (doThis == 0):
