@@ -3,21 +3,29 @@
 
 Contract: `python bench.py --gpus N --steps K --warmup W [--impl reference]` prints ONE JSON line.
 
-A step = one Langevin step of the Line.yml sampler (a-4, KITTISampling.py:137-490) over one batch of
-synthetic views: score-network forward + noise draw + Langevin update + cross-view block.
-Workload (BASELINE.json configs[1]): 8 synthetic line poses per GPU (B = A = 8, one group per rank),
-2x64x1024 range/intensity images, random-init NCSN_LiDAR_small (29.7 M parameters), noise level
-c = 116 of 232 (sigmaMod = 1, sharing on, setting 5).  Weak scaling: every rank owns one whole group
-of 8 views, so the only exchange is the 1-float MAX all-reduce of the tooHigh gate
-(KITTISampling.py:162 takes the max over ALL views of the call).
+A step = one Langevin step of a simultaneous sampler over one batch of synthetic views: score-network
+forward + noise draw + Langevin update + cross-view block.  Default workload (BASELINE.json configs[1]):
+the Line.yml sampler (a-4, KITTISampling.py:137-490), 8 synthetic line poses per GPU (B = A = 8, one group
+per rank), 2x64x1024 range/intensity images, random-init NCSN_LiDAR_small (29.7 M parameters), noise level
+c = 116 of 232 (sigmaMod = 1, sharing on, setting 5).  `--variant inpainting|densification` runs configs 3 / 4
+(the translation sampler a-5, models/__init__.py:240-582, setting 7); `--views-per-gpu 16|32|64` is config 5.
 
-  value    : view-steps/s, inputs resident in HBM, CUDA-event timed, max over ranks
-  e2e      : same metric with the step's x copied host->device (pinned) before the score forward and
-             x + newImages copied back device->host inside the timed region
-  roofline : tensor-core convolutions (the dominant kernel family): algorithmic 2*M*N*K FLOPs of the
-             launches in the timed region / their summed CUDA-event time on the launching stream
-  cpu_baseline / --impl reference : the oracle port (oracle/*.py, torch CPU ops like the reference)
-             on the box's host cores, bounded sample of 1 view (A = 1) per step
+  value          : view-steps/s, inputs resident in HBM, CUDA-event timed, max over ranks (weak scaling:
+                   every rank owns whole groups, the only exchange is the 1-float MAX of the tooHigh gate)
+  e2e            : the same metric through the host-facing C-ABI call sdpc_langevin_reproject_step_host
+                   (x in pinned HOST memory: H2D copy, score forward, update, cross-view, D2H of x and newImages
+                   inside the timed region)
+  roofline       : the tensor-core convolutions (the dominant kernel family): algorithmic 2*M*N*K FLOPs of the
+                   launches in the timed region / their summed CUDA-event time on the launching stream
+  fp32_parity_arm: the same three blocks for the bf16x3 arm (1e-3 of the fp32 oracle, north_star's parity bound)
+  sharded_group  : (N > 1) ONE group of 8 views split over the N ranks, per-step NCCL all-gather of the updated
+                   planes (north_star's sharding, BASELINE configs 3/4), view-steps/s of that group
+  torch_gpu_baseline : stock PyTorch on the same GPU (the oracle port's torch ops = the reference's op sequence:
+                   cuDNN convolutions as LiDARGen/main.py:161 configures them; TF32 on / off; channels_last +
+                   bf16 autocast), forward and full step.  A baseline, never part of `value`.
+  cpu_baseline / --impl reference : the oracle port (oracle/*.py, torch CPU ops like the reference) on the
+                   box's host cores; one step = one view-step of the SAME B = A = 8 workload (1 forward + update +
+                   all 8 source views re-projected into that view's z-buffer)
 """
 import argparse
 import json
@@ -34,14 +42,14 @@ sys.path.insert(0, ROOT)
 H, W, LEVELS, LEVEL = 64, 1024, 232, 116
 VIEWS_PER_GPU = 8
 STEP_LR = 6.2e-6
+VARIANTS = {"line": "Line.yml step (a-4, pose matrices, setting 5)",
+            "inpainting": "Inpainting.yml step (a-5, translations, existTotal mask, setting 7)",
+            "densification": "Densification.yml step (a-5, target view keeps rows 0::4 = 16 of 64 beams, setting 7)"}
 
 
-def workload(B=VIEWS_PER_GPU, A=VIEWS_PER_GPU):
-    return ("Line.yml step (a-4): NCSN_LiDAR_small forward + Langevin update + cross-view (setting 5, minStepToShare "
-            f"passed), {B} line poses per GPU (B={B}, A={A}), 2x64x1024, random-init 29.7M-param net, noise level 116/232")
-
-
-WORKLOAD = workload()
+def workload(B=VIEWS_PER_GPU, A=VIEWS_PER_GPU, variant="line"):
+    return (f"{VARIANTS[variant]}: NCSN_LiDAR_small forward + Langevin update + cross-view (minStepToShare passed), "
+            f"{B} views per GPU (B={B}, A={A}), 2x64x1024, random-init 29.7M-param net, noise level 116/232")
 
 
 def parse():
@@ -50,13 +58,17 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("SDPC_PRECISION", "bf16"), choices=["bf16", "bf16x3", "tf32", "fp32"])
+    ap.add_argument("--precision", default=os.environ.get("SDPC_PRECISION", "bf16"),
+                    choices=["bf16", "bf16x3", "fp16", "tf32", "fp32"])
+    ap.add_argument("--variant", default="line", choices=sorted(VARIANTS))
     ap.add_argument("--views-per-gpu", type=int, default=VIEWS_PER_GPU)
     ap.add_argument("--group-size", type=int, default=8,
                     help="actualBatchSize A: views that share information; --views-per-gpu 16/32/64 with the default 8 is "
                          "BASELINE.json's view-count sweep (groups of 8)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-parity-arm", action="store_true", help="skip the extra bf16x3 (fp32-parity) timing")
+    ap.add_argument("--no-parity-arm", action="store_true", help="skip the bf16x3 (fp32-parity) arm")
+    ap.add_argument("--no-torch-baseline", action="store_true", help="skip the stock-PyTorch-on-this-GPU baseline")
+    ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the one-group-over-N-ranks measurement")
     return ap.parse_args()
 
 
@@ -67,21 +79,19 @@ def config_ns(device):
                      sigma_dist="geometric", sigma_begin=50, sigma_end=0.01, spec_norm=False), device=device)
 
 
-def synthetic_group(B, seed, A=None):
+def synthetic_group(B, seed, A=None, variant="line"):
     """B views in groups of A (default: one group): the dataset tuple of kitti360_im_8Batch.py:304 with synthetic content
-    (SURVEY 8d)."""
-    A = B if A is None else A
+    (SURVEY 8d); generator: sdpc_b200.synthetic_data.bench_group."""
+    import sdpc_b200  # noqa: F401
+    from sdpc_b200.synthetic_data import bench_group
+    return bench_group(B, B if A is None else A, H, W, seed, variant)
+
+
+def step_constants(sig):
+    """numpy-scalar arithmetic of the samplers (KITTISampling.py:135,156)."""
     import numpy as np
-    import torch
-    from tests.golden import cases
-    refer = cases.smooth_range_image(B, H, W, seed)
-    r = np.random.Generator(np.random.PCG64([seed, 7]))
-    mask = torch.from_numpy((r.uniform(size=(B, 1, H, W)) < 0.6).astype(np.int32)).repeat(1, 2, 1, 1).contiguous()
-    sky = torch.ones(B, 1, H, W, dtype=torch.bool)
-    exist = torch.from_numpy(r.uniform(size=(1, H, W)) < 0.68).repeat(B, 1, 1).contiguous()
-    to_world, from_world = cases.line_poses(B, A, step=5.0, yaw=0.01)
-    x0 = torch.from_numpy(r.uniform(size=(B, 2, H, W)).astype(np.float32))
-    return dict(x=x0, refer=refer, mask=mask, sky=sky, exist=exist, toWorld=to_world, fromWorld=from_world)
+    step_size = STEP_LR * (sig[LEVEL] / sig[-1]) ** 2
+    return step_size, np.sqrt(step_size * 2)
 
 
 class ClockSampler:
@@ -133,12 +143,30 @@ def measured_peaks():
         return None
 
 
+def measured_conv_traffic(precision):
+    """dram__bytes_read.sum + dram__bytes_write.sum per tensor-core convolution launch, from the ncu --set full capture
+    of the shipped kernels that tools/ncu_traffic.py summarised into profiles/conv_traffic.json.  None when there is no
+    capture for this arm or the capture was taken of other kernel sources than the ones this library was built from."""
+    try:
+        import sdpc_b200  # noqa: F401
+        from sdpc_b200 import build as b
+        rec = json.load(open(os.path.join(ROOT, "profiles", "conv_traffic.json")))
+        arm = rec["arms"].get(precision)
+        if arm is None:
+            return None, "no ncu capture of this arm"
+        if rec.get("kernel_source_digest") != b.kernel_digest():
+            return None, "the ncu capture in profiles/conv_traffic.json is of an older build of conv_umma.cu"
+        return arm["dram_bytes_per_launch_mean"], rec.get("source", "profiles/conv_traffic.json")
+    except Exception as e:                                  # no capture committed
+        return None, f"no capture ({type(e).__name__})"
+
+
 # ---------------------------------------------------------------------------------------------- CPU arm
 def cpu_view_steps_per_s(steps, warmup, threads=None):
-    """Oracle port on the host cores: one Langevin step (score forward + update + cross-view) of ONE view
-    (A = 1) per step - a bounded sample of the 8-view workload; the cross-view cost per view grows with A,
-    so this flatters the CPU arm."""
-    import numpy as np
+    """Oracle port on the host cores.  One step = ONE view-step of the B = A = 8 workload of the GPU arm: the score
+    forward of one view, its Langevin update, and its share of the cross-view block - all 8 source views of the group
+    un-projected and re-projected into that one target view's z-buffer (targets=(v, 1)) - then the correction.  The
+    view advanced rotates through the group, so 8 steps are exactly one 8-view step of the workload."""
     import torch
     from oracle import crossview_ref as cv
     from oracle import samplers_ref as sr
@@ -149,47 +177,163 @@ def cpu_view_steps_per_s(steps, warmup, threads=None):
     torch.set_num_threads(threads)
     sd = make_state_dict(num_classes=LEVELS)
     sig = sigma_schedule(50, 0.01, LEVELS).numpy()
-    g = synthetic_group(1, 1234)
+    A = VIEWS_PER_GPU
+    g = synthetic_group(A, 1234)
     geo = cv.make_geometry(H, W)
     x = g["x"].clone()
-    labels = torch.full((1,), LEVEL, dtype=torch.long)
-    step_size, noise_scale = sr._step_constants(STEP_LR, sig[LEVEL], sig[-1])
-    eye_to, eye_from = g["toWorld"].reshape(1, 4, 4), g["fromWorld"].reshape(1, 4, 4)
+    label = torch.full((1,), LEVEL, dtype=torch.long)
+    step_size, noise_scale = step_constants(sig)
+    to_w, from_w = g["toWorld"].reshape(A, 4, 4), g["fromWorld"].reshape(A, 4, 4)
 
-    def one(x):
-        grad = torch.nan_to_num(score_forward(sd, x, labels))
-        noise = torch.randn_like(x)
-        x, _ = sr.langevin_update(x, grad, g["refer"], g["mask"], noise, step_size, noise_scale, 1)
-        ni, im, th = cv.shared_images(x, geo, 1, 1, g["exist"], g["sky"], to_world=eye_to, from_world=eye_from,
-                                      min_depth_filter=True, controlled_average=True, allowance=10.0)
-        return cv.apply_correction(x, ni, im, g["sky"], g["mask"], th, 0.01)
+    def one(v):
+        sl = slice(v, v + 1)
+        grad = torch.nan_to_num(score_forward(sd, x[sl], label))
+        noise = torch.randn_like(x[sl])
+        x[sl], _ = sr.langevin_update(x[sl], grad, g["refer"][sl], g["mask"][sl], noise, step_size, noise_scale, 1)
+        ni, im, th = cv.shared_images(x, geo, 1, A, g["exist"], g["sky"], to_world=to_w, from_world=from_w,
+                                      min_depth_filter=True, controlled_average=True, allowance=10.0, targets=(v, 1))
+        x[sl] = cv.apply_correction(x[sl], ni, im, g["sky"][sl], g["mask"][sl], th, 0.01)
 
-    for _ in range(warmup):
-        x = one(x)
+    for i in range(warmup):
+        one(i % A)
     t0 = time.perf_counter()
-    for _ in range(steps):
-        x = one(x)
+    for i in range(steps):
+        one((warmup + i) % A)
     dt = time.perf_counter() - t0
     return steps / dt, dt / steps * 1e3, threads
+
+
+CPU_SAMPLE = ("one step = one view-step of the B=A=8 Line workload: 1 view forward + update + all 8 source views "
+              "re-projected into that view's z-buffer + correction (1/8 of an 8-view step; the view rotates through the group)")
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 8))
-    warm = max(1, min(args.warmup, 2))
+    steps, warm = max(1, args.steps), max(0, args.warmup)
     v, ms, threads = cpu_view_steps_per_s(steps, warm)
     line = {"impl": "reference", "metric": "view-steps/sec", "value": v, "unit": "view-steps/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "views_per_gpu": VIEWS_PER_GPU,
-                       "cpu_sample": "each step = 1 view (A=1) of the workload: the reference's CPU path needs ~1 s per "
-                                     "view-forward, a full 8-view step with its O(A^2) cross-view block ~10 s"},
+            "config": {"workload": workload(), "views_per_gpu": VIEWS_PER_GPU, "group_size": VIEWS_PER_GPU,
+                       "cpu_sample": CPU_SAMPLE},
             "cpu_baseline": {"value": v, "unit": "view-steps/s", "cores": threads, "kind": "port",
-                             "sample": f"{steps} steps x 1 view (A=1), oracle port (torch CPU ops), {threads} threads"},
+                             "sample": f"{steps} steps after {warm} warm-up; {CPU_SAMPLE}; oracle port (torch CPU ops), "
+                                       f"{threads} threads"},
             "e2e": {"value": v, "unit": "view-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------- stock PyTorch on this GPU
+def torch_gpu_baseline(dev, g, B, A, steps, warmup):
+    """The reference's op sequence as stock PyTorch executes it on this GPU (oracle port: same conv2d / instance_norm /
+    pad / max_pool2d / interpolate calls as LiDARGen/models, cross-view block as flat scatter reductions - cheaper than
+    the reference's sort / unique / sparse pipeline, so this baseline is on the fast side).  Three settings:
+    the reference's own (cudnn.benchmark = True as main.py:161 sets it, TF32 convolutions on = torch's default),
+    strict fp32 (TF32 off), and the fastest stock knobs (channels_last + bf16 autocast)."""
+    import torch
+    from oracle import crossview_ref as cv
+    from oracle import samplers_ref as sr
+    from oracle.scorenet_ref import score_forward
+    from oracle.sigmas import sigma_schedule
+    from oracle.weights import make_state_dict
+    sd = {k: v.to(dev) for k, v in make_state_dict(num_classes=LEVELS).items()}
+    sig = sigma_schedule(50, 0.01, LEVELS).numpy()
+    geo = cv.make_geometry(H, W, dev)
+    to = lambda t: t.to(dev)
+    refer, mask, sky, exist = to(g["refer"]), to(g["mask"]), to(g["sky"]), to(g["exist"])
+    to_w, from_w = to(g["toWorld"]).reshape(B, 4, 4), to(g["fromWorld"]).reshape(B, 4, 4)
+    labels = torch.full((B,), LEVEL, device=dev, dtype=torch.long)
+    step_size, noise_scale = step_constants(sig)
+    out = {"what": "oracle port (torch ops of the reference's op sequence) on this GPU, same B=A=8 step, same inputs",
+           "torch": torch.__version__, "cudnn": torch.backends.cudnn.version()}
+    saved = (torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+
+    def measure(name, forward):
+        x = to(g["x"]).clone()
+
+        def full(x):
+            grad = torch.nan_to_num(forward(x))
+            noise = torch.randn_like(x)
+            x, _ = sr.langevin_update(x, grad, refer, mask, noise, step_size, noise_scale, 1)
+            ni, im, th = cv.shared_images(x, geo, 1, A, exist, sky, to_world=to_w, from_world=from_w,
+                                          min_depth_filter=True, controlled_average=True, allowance=10.0)
+            return cv.apply_correction(x, ni, im, sky, mask, th, 0.01)
+
+        def timed(fn, n):
+            torch.cuda.synchronize(dev)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(n):
+                fn()
+            b.record()
+            torch.cuda.synchronize(dev)
+            return a.elapsed_time(b) / n
+
+        for _ in range(max(2, warmup)):
+            full(x)
+        fwd_ms = timed(lambda: forward(x), steps)
+        step_ms = timed(lambda: full(x), steps)
+        out[name] = {"forward_ms": fwd_ms, "step_ms": step_ms, "view_steps_per_s": B / (step_ms / 1e3),
+                     "view_forwards_per_s": B / (fwd_ms / 1e3)}
+
+    try:
+        torch.backends.cudnn.benchmark = True                               # LiDARGen/main.py:161
+        n = max(3, min(steps, 10))
+        torch.backends.cudnn.allow_tf32 = True                              # torch's default: what the reference runs
+        measure("cudnn_tf32", lambda x: score_forward(sd, x, labels))
+        steps = n
+        sd_cl = {k: (v.contiguous(memory_format=torch.channels_last) if v.dim() == 4 else v) for k, v in sd.items()}
+
+        def fwd_autocast(x):
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                return score_forward(sd_cl, x.contiguous(memory_format=torch.channels_last), labels).float()
+        measure("channels_last_bf16_autocast", fwd_autocast)
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+        steps = max(2, min(n, 4))
+        measure("cudnn_fp32", lambda x: score_forward(sd, x, labels))
+    finally:
+        torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = saved
+    del sd
+    torch.cuda.empty_cache()
+    return out
+
+
+def matmul_peak_tflops(dev, dtype_name, seconds=2.0):
+    """Dense matmul throughput of torch/cuBLAS on this GPU, measured the way MEASURED_PEAKS.json's bf16 figures were:
+    8192^3, best of 10 (burst) and back to back for `seconds` (sustained).  Used for the tf32 / fp16 arms' roofline."""
+    import torch
+    n = 8192
+    saved = torch.backends.cuda.matmul.allow_tf32
+    try:
+        if dtype_name == "tf32":
+            torch.backends.cuda.matmul.allow_tf32 = True
+            a, b = torch.randn(n, n, device=dev), torch.randn(n, n, device=dev)
+        else:
+            dt = {"bf16": torch.bfloat16, "fp16": torch.float16}[dtype_name]
+            a, b = torch.randn(n, n, device=dev, dtype=dt), torch.randn(n, n, device=dev, dtype=dt)
+        for _ in range(3):
+            a @ b
+        best = 0.0
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            a @ b
+            e1.record()
+            torch.cuda.synchronize(dev)
+            best = max(best, 2 * n ** 3 / (e0.elapsed_time(e1) / 1e3) / 1e12)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = max(10, int(seconds * best * 1e12 / (2 * n ** 3)))
+        e0.record()
+        for _ in range(reps):
+            a @ b
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return best, 2 * n ** 3 * reps / (e0.elapsed_time(e1) / 1e3) / 1e12
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = saved
 
 
 # ---------------------------------------------------------------------------------------------- GPU arm
@@ -199,8 +343,9 @@ def run_b200(args):
     import torch.distributed as dist
     import sdpc_b200  # noqa: F401
     from sdpc_b200 import cabi
+    from sdpc_b200.dist import ViewShard
     from sdpc_b200.scorenet import NCSN_LiDAR_small
-    from sdpc_b200.step import StepRunner
+    from sdpc_b200.step import StepRunner, translation_origins
     from sdpc_b200.sigmas import get_sigmas
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -216,33 +361,30 @@ def run_b200(args):
     A = min(B, args.group_size)
     if B % A:
         raise SystemExit(f"--views-per-gpu {B} is not a multiple of --group-size {A}")
-    g = synthetic_group(B, 1234 + rank, A)
+    pose = args.variant == "line"
     cfg = config_ns(dev)
     sig = get_sigmas(cfg).cpu().numpy()
-    torch.manual_seed(1234)                                           # random-init weights (nn.Conv2d-style init of the module)
-    net = NCSN_LiDAR_small(cfg, precision=args.precision).to(dev)
-    run = StepRunner((B, 2, H, W), dev, g["refer"], g["mask"], g["sky"], g["exist"], A, cabi.SDPC_VARIANT_POSE,
-                     to_world=g["toWorld"], from_world=g["fromWorld"])
+    step_size, noise_scale = step_constants(sig)
+
+    def make_runner(g, n_views, group, **kw):
+        if pose:
+            return StepRunner((n_views, 2, H, W), dev, g["refer"], g["mask"], g["sky"], g["exist"], group,
+                              cabi.SDPC_VARIANT_POSE, to_world=g["toWorld"], from_world=g["fromWorld"], **kw)
+        return StepRunner((n_views, 2, H, W), dev, g["refer"], g["mask"], g["sky"], g["exist"], group,
+                          cabi.SDPC_VARIANT_TRANSLATION, origins=translation_origins(g["mods"].to(dev)), **kw)
+
+    def make_params(run):
+        if pose:       # Line.yml: setting 5 (min-depth filter), allowance 10, correlation_coefficient 0.01
+            return run.params(step_size, noise_scale, 1, 0.01, 1, True, True, 10, False)
+        # Inpainting.yml / Densification.yml: a-5, setting 7 (controlled average, allowance 10), sky filter on the source
+        return run.params(step_size, noise_scale, 1, 0.01, 1, True, True, 10, True)
+
+    g = synthetic_group(B, 1234 + rank, A, args.variant)
+    run = make_runner(g, B, A)
+    p = make_params(run)
     x = g["x"].to(dev)
     labels = torch.full((B,), LEVEL, device=dev, dtype=torch.long)
-    step_size = STEP_LR * (sig[LEVEL] / sig[-1]) ** 2
-    noise_scale = np.sqrt(step_size * 2)
-    p = run.params(step_size, noise_scale, 1, 0.01, 1, True, True, 10, False)
     new_images = torch.empty_like(x)
-    gmax = torch.zeros(1, device=dev)
-
-    def step(xbuf):
-        grad = net(xbuf, labels)
-        noise = torch.randn_like(xbuf)
-        b = run.buffers(xbuf, grad, noise, new_images=new_images)
-        if world == 1:
-            run.step(p, b)
-        else:                                   # tooHigh is a max over every view of the call
-            run.update_only(p, b)
-            mx = run.local_max()
-            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-            run.merge_max(mx)
-            run.share_only(p, b)
 
     def barrier():
         if world > 1:
@@ -264,109 +406,186 @@ def run_b200(args):
             ms = float(t.item())
         return ms
 
-    # ---- device-resident arm -------------------------------------------------------------------
-    clocks = ClockSampler(local) if rank == 0 else None          # started before the warm-up: nvidia-smi needs a moment to stream
-    for _ in range(max(args.warmup, 3)):
+    peaks = measured_peaks()
+    peak_cache = {}
+
+    def tensor_peak(precision):
+        """(sustained TFLOP/s to divide by, where it comes from) for the operand type the arm's MMAs run in."""
+        if precision in ("bf16", "bf16x3"):
+            if peaks:
+                return peaks["bf16_tflops_sustained"], "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)"
+            return 1400.0, "fallback 1.4 PFLOP/s sustained bf16 (B200_PROFILING.md; of fallback)"
+        kind = "tf32" if precision in ("tf32", "fp32") else "fp16"
+        if kind not in peak_cache:
+            peak_cache[kind] = matmul_peak_tflops(dev, kind)
+        burst, sustained = peak_cache[kind]
+        return sustained, (f"torch.matmul {kind} 8192^3 on this GPU in this run, sustained over 2 s (burst {burst:.0f}); "
+                           "measured like MEASURED_PEAKS.json's bf16 figures")
+
+    def measure_arm(net, steps, warmup, with_clocks=False):
+        """device-resident value + roofline pass + end-to-end pass of one precision arm."""
+        def step(xbuf):
+            grad = net(xbuf, labels)
+            noise = torch.randn_like(xbuf)
+            b = run.buffers(xbuf, grad, noise, new_images=new_images)
+            if world == 1:
+                run.step(p, b)
+            else:                                   # tooHigh is a max over every view of the call
+                run.update_only(p, b)
+                mx = run.local_max()
+                dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+                run.merge_max(mx)
+                run.share_only(p, b)
+
+        clocks = ClockSampler(local) if (with_clocks and rank == 0) else None   # before the warm-up: nvidia-smi needs a moment
+        for _ in range(warmup):
+            step(x)
+        t0 = time.time()
+        ms = timed(lambda: step(x), steps)
+        t1 = time.time()
+        res = {"value": world * B * steps / (ms / 1e3), "ms_per_step": ms / steps, "steps": steps}
+        # roofline pass: the same K steps again with every tensor-core convolution launch bracketed by CUDA events
+        # on the launching stream (this disables the CUDA-graph replay of the forward, the kernels are identical)
+        net.set_profiling(x, True)
         step(x)
-    t0 = time.time()
-    ms = timed(lambda: step(x), args.steps)
-    t1 = time.time()
-    value = world * B * args.steps / (ms / 1e3)
-    # roofline pass: the same K steps again with every tensor-core convolution launch bracketed by CUDA events
-    # on the launching stream (this disables the CUDA-graph replay of the forward, the kernels are identical)
-    net.set_profiling(x, True)
-    step(x)
-    net.profile_collect(x)
-    ms_prof = timed(lambda: step(x), args.steps)
-    conv_ms, conv_flops, conv_launches = net.profile_collect(x)
-    net.set_profiling(x, False)
-    # our kernels per step: the score network's (its launch count includes one memset) + what the step call launches
-    # (update, scatter, resolve, correct; sdpc_step_kernel_launches) [+ the max merge of the sharded flow]
-    step_kernels = run.kernel_launches(p, run.buffers(x, x, x, new_images=new_images)) + (1 if world > 1 else 0)
-    launches_per_step = (net.launch_count(x) - 1) + step_kernels
+        net.profile_collect(x)
+        ms_prof = timed(lambda: step(x), steps)
+        conv_ms, conv_flops, conv_launches = net.profile_collect(x)
+        net.set_profiling(x, False)
+        peak, peak_src = tensor_peak(net.precision)
+        achieved = conv_flops / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
+        traffic, traffic_src = measured_conv_traffic(net.precision)
+        res["roofline"] = {
+            "bound": "tensor", "kernel": "conv_umma_kernel (tcgen05 implicit-GEMM 3x3/1x1 conv)",
+            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
+            "traffic": traffic, "traffic_unit": "dram bytes per conv launch, mean over the captured launches",
+            "traffic_source": traffic_src, "peak_source": peak_src, "launches_timed": conv_launches,
+            "conv_share_of_step": conv_ms / ms_prof if ms_prof else None,
+            "timing": "CUDA events around each conv launch, separate eager pass of the same K steps "
+                      f"({ms_prof / steps:.2f} ms/step without graph replay)",
+            "flops_per_view_forward": net.flops_per_view(x)}
+        if net.precision == "bf16x3":
+            res["roofline"]["note"] = ("algorithmic FLOPs / time against the bf16 peak: the arm executes 3 bf16 MMA passes per "
+                                       "algorithmic FLOP (hi*hi + hi*lo + lo*hi), so frac <= 1/3; executed MMA rate = 3 x achieved")
+            res["roofline"]["executed_frac"] = 3 * achieved / peak if peak else None
+        # our kernels per step: the score network's (its launch count includes one memset) + what the step call launches
+        step_kernels = run.kernel_launches(p, run.buffers(x, x, x, new_images=new_images)) + (1 if world > 1 else 0)
+        res["gpu_launches"] = ((net.launch_count(x) - 1) + step_kernels) * steps
+        # ---- end-to-end: HOST sample buffers through sdpc_langevin_reproject_step_host -----------------------------
+        host = [g["x"].clone().pin_memory(), torch.empty_like(g["x"]).pin_memory()]
+        ni_host = torch.empty_like(g["x"]).pin_memory()
+        xd, gd = torch.empty_like(x), torch.empty_like(x)
+        stream = torch.cuda.current_stream(dev)
 
-    # ---- end-to-end arm: host buffers, copies inside the timed region ------------------------------
-    x_host = g["x"].clone().pin_memory()
-    out_host = torch.empty_like(x_host).pin_memory()
-    ni_host = torch.empty_like(x_host).pin_memory()
-    xd = torch.empty_like(x)
+        def e2e_step():
+            noise = torch.randn_like(xd)
+            b = run.buffers(xd, gd, noise, new_images=new_images)
+            if world == 1:
+                run.step_host(p, b, host[0], ni_host, scorenet=net, labels=labels)
+            else:                                    # the MAX all-reduce sits between update and share
+                xd.copy_(host[0], non_blocking=True)
+                gd.copy_(net(xd, labels))
+                run.update_only(p, b)
+                mx = run.local_max()
+                dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+                run.merge_max(mx)
+                run.share_only(p, b)
+                host[0].copy_(xd, non_blocking=True)
+                ni_host.copy_(new_images, non_blocking=True)
+            stream.synchronize()                     # the caller reads the result before the next step
+            host[1].copy_(host[0])                   # (host-side hand-over: the result is the next step's input)
 
-    host = [x_host, out_host]                           # pinned ping-pong: a step's result is the next step's input
+        for _ in range(2):
+            e2e_step()
+        e2e_steps = max(3, steps // 2)
+        ms_e2e = timed(e2e_step, e2e_steps)
+        nbytes = host[0].numel() * 4
+        res["e2e"] = {"value": world * B * e2e_steps / (ms_e2e / 1e3), "unit": "view-steps/s",
+                      "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": 2 * nbytes, "ms_per_step": ms_e2e / e2e_steps,
+                      "api": "sdpc_langevin_reproject_step_host (pinned host x in, x + newImages out)" if world == 1 else
+                             "pinned host x in / out around update, all-reduce(MAX), share"}
+        if clocks:
+            res["clocks"] = clocks.stop(t0, t1, time.time())
+        return res
 
-    def e2e_step():
-        xd.copy_(host[0], non_blocking=True)
-        step(xd)
-        host[1].copy_(xd, non_blocking=True)
-        ni_host.copy_(new_images, non_blocking=True)
-        torch.cuda.current_stream().synchronize()       # the caller reads the result before the next step
-        host.reverse()
-
-    for _ in range(2):
-        e2e_step()
-    e2e_steps = max(3, args.steps // 2)
-    ms_e2e = timed(e2e_step, e2e_steps)
-    e2e_value = world * B * e2e_steps / (ms_e2e / 1e3)
-    clk = clocks.stop(t0, t1, time.time()) if clocks else None
-    nbytes = x_host.numel() * 4
+    torch.manual_seed(1234)                                           # random-init weights (nn.Conv2d-style init of the module)
+    net = NCSN_LiDAR_small(cfg, precision=args.precision).to(dev)
+    warm = max(args.warmup, 3)
+    head = measure_arm(net, args.steps, warm, with_clocks=True)
 
     # fp32-parity arm on the tensor cores (bf16x3: hi/lo operand split, 2e-4 of the fp32 oracle), same step
     parity = None
     if args.precision == "bf16" and not args.no_parity_arm:
         net3 = NCSN_LiDAR_small(config_ns(dev), precision="bf16x3").to(dev)
         net3.load_state_dict(net.state_dict())
-        fast_net, net = net, net3
-        for _ in range(3):
-            step(x)
-        k3 = max(3, args.steps // 2)
-        ms3 = timed(lambda: step(x), k3)
-        parity = {"dtype": "bf16x3", "value": world * B * k3 / (ms3 / 1e3), "unit": "view-steps/s",
-                  "ms_per_step": ms3 / k3, "tolerance": "score within 1e-3 of the fp32 oracle (measured 2e-4, tests/test_gpu_scorenet.py)"}
-        net = fast_net
+        parity = measure_arm(net3, max(3, args.steps // 2), 3)
+        parity.update({"dtype": "bf16x3", "unit": "view-steps/s",
+                       "tolerance": "score within 1e-3 of the fp32 oracle (measured 2e-4, tests/test_gpu_scorenet.py)"})
         del net3
+        torch.cuda.empty_cache()
+
+    # north_star's sharding: ONE group of 8 views over the N ranks, all-gather of the updated planes every step
+    sharded = None
+    if world > 1 and not args.no_sharded and 8 % world == 0:
+        gs = synthetic_group(8, 1234, 8, args.variant)               # the same group on every rank
+        runs = make_runner(gs, 8, 8)
+        shard = ViewShard(8, 8)
+        shard.attach(runs, None)
+        ps = make_params(runs)
+        xs = gs["x"].to(dev)
+        lab8 = torch.full((8,), LEVEL, device=dev, dtype=torch.long)
+        grad_full = torch.zeros_like(xs)
+        ni8 = torch.empty_like(xs)
+
+        def sharded_step():
+            shard.score(net, xs, lab8, grad_full)
+            noise = torch.randn_like(xs)
+            shard.step(runs, ps, runs.buffers(xs, grad_full, noise, new_images=ni8), xs)
+
+        for _ in range(3):
+            sharded_step()
+        ks = args.steps
+        ms_s = timed(sharded_step, ks)
+        sharded = {"value": 8 * ks / (ms_s / 1e3), "unit": "view-steps/s", "ms_per_step": ms_s / ks, "views": 8,
+                   "views_per_rank": 8 // world, "scaling": "strong (one group of 8 views over the ranks)",
+                   "exchange": shard.exchange_description()}
+
+    tgb = None
+    if world == 1 and pose and not args.no_torch_baseline:
+        tgb = torch_gpu_baseline(dev, g, B, A, min(args.steps, 10), 3)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-    peaks = measured_peaks()
-    if args.precision == "bf16":
-        peak, peak_src = (peaks["bf16_tflops_sustained"], "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)") \
-            if peaks else (1400.0, "fallback 1.4 PFLOP/s sustained (of fallback)")
-    else:
-        peak, peak_src = ((peaks["bf16_tflops_sustained"] / 2, "half of measured bf16 sustained (tf32 nominal ratio)")
-                          if peaks else (700.0, "fallback"))
-    achieved = conv_flops / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
     line = {
-        "metric": "view-steps/sec", "value": value, "unit": "view-steps/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "metric": "view-steps/sec", "value": head["value"], "unit": "view-steps/s", "n_gpus": world, "steps": args.steps,
+        "warmup": warm, "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
-        "config": {"workload": workload(B, A),
+        "config": {"workload": workload(B, A, args.variant), "variant": args.variant,
                    "views_per_gpu": B, "group_size": A, "global_views": world * B,
                    "parallelism": f"views x{world} ({B // A} group{'s' if B // A > 1 else ''} of {A} per rank)",
                    "l2": "per-step working set (activations, >2 GB) exceeds the 126 MB L2; no explicit flush",
-                   "exchange": "1-float all-reduce(MAX) per step (tooHigh gate)" if world > 1 else "none"},
-        "e2e": {"value": e2e_value, "unit": "view-steps/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": 2 * nbytes,
-                "ms_per_step": ms_e2e / e2e_steps},
-        "gpu_launches": launches_per_step * args.steps,
-        "clocks": clk,
-        "roofline": {"bound": "tensor", "kernel": "conv_umma_kernel (tcgen05 implicit-GEMM 3x3/1x1 conv)",
-                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
-                     # dram__bytes_read.sum + dram__bytes_write.sum per launch, mean of the 6 conv launches captured with
-                     # ncu --set full in profiles/r01_ncu_full_conv2.txt (256->256 @32x512x8 views; algorithmic bytes of such
-                     # a launch: 67 MB operand + 134 MB fp32 output [+ 134 MB residual])
-                     "traffic": 2.18e8 if args.precision == "bf16" else None, "traffic_unit": "bytes/launch (ncu, profiles/)",
-                     "peak_source": peak_src, "launches_timed": conv_launches,
-                     "conv_share_of_step": conv_ms / ms_prof if ms_prof else None,
-                     "timing": "CUDA events around each conv launch, separate eager pass of the same K steps "
-                               f"({ms_prof / args.steps:.2f} ms/step without graph replay)",
-                     "flops_per_view_forward": net.flops_per_view(x)},
+                   "exchange": "1-float all-reduce(MAX) per step (tooHigh gate)" if world > 1 else "none",
+                   "tolerance": {"bf16": "bf16 operands: score within 8e-2 of the fp32 oracle (measured 5.6e-2), stated "
+                                         "separately from north_star's 1e-3 fp32 bound - see fp32_parity_arm",
+                                 "bf16x3": "score within 1e-3 of the fp32 oracle (measured 2e-4)",
+                                 "fp16": "fp16 operands (TF32-class mantissa): score within 2e-2 of the fp32 oracle",
+                                 "tf32": "score within 2e-2 of the fp32 oracle (measured 8e-3)",
+                                 "fp32": "score within 1e-4 of the fp32 oracle"}[args.precision]},
+        "e2e": head["e2e"], "gpu_launches": head["gpu_launches"], "clocks": head.get("clocks"), "roofline": head["roofline"],
     }
     if parity:
         line["fp32_parity_arm"] = parity
+    if sharded:
+        line["sharded_group"] = sharded
+    if tgb:
+        line["torch_gpu_baseline"] = tgb
     if world == 1 and not args.no_cpu_baseline:
-        v, cms, threads = cpu_view_steps_per_s(3, 1)
+        v, cms, threads = cpu_view_steps_per_s(8, 1)
         line["cpu_baseline"] = {"value": v, "unit": "view-steps/s", "cores": threads, "kind": "port",
-                                "sample": f"3 steps x 1 view (A=1), oracle port (torch CPU ops), {threads} threads, "
-                                          f"{cms:.0f} ms/step"}
+                                "sample": f"8 steps after 1 warm-up; {CPU_SAMPLE}; oracle port (torch CPU ops), {threads} "
+                                          f"threads, {cms:.0f} ms/step"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SDPC_ABI_VERSION 1
+#define SDPC_ABI_VERSION 2
 
 enum sdpc_status {
   SDPC_OK = 0,
@@ -46,6 +46,9 @@ enum sdpc_precision {
 };
 
 int sdpc_abi_version(void);
+/* sizeof of the ABI structs as this build sees them: 0 sdpc_step_params, 1 sdpc_step_buffers, 2 sdpc_score_config,
+ * 3 sdpc_projection_params; any other index gives 0.  A binding compares them with its own layout at load time. */
+size_t sdpc_abi_struct_bytes(int which);
 const char* sdpc_last_error(void);
 /* Name of the kernels this build contains, e.g. "sm_100a". */
 const char* sdpc_build_arch(void);
@@ -129,11 +132,15 @@ typedef struct sdpc_step_params {
   int32_t tgt_count;     /* number of target views, else n_views */
   int32_t scalar_div_recip; /* 1: tensor/python-scalar divisions as x*(1/s) like torch's CUDA kernels (matches the
                                reference on a GPU bit-for-bit); 0: IEEE division like torch's CPU kernels */
-  int32_t key_shift_override; /* test hook (packed-key winner path): bits of the log-range dropped from the packed
-                                 (depth|source id) key; 0 = auto */
-  int32_t winner_mode;   /* how the z-buffer keeps the nearest candidate: 0 = library default (128-bit CAS on
-                            {log-range, source id}; SDPC_XVIEW_CAS128=0 in the environment selects the packed key),
-                            1 = packed 64-bit key + verification pass, 2 = 128-bit CAS.  Same results bit for bit. */
+  int32_t key_shift_override; /* test hook: bits of the log-range dropped from the packed (depth | source id) key, which
+                                 makes packed winners wrong so that verification and the fix pass are exercised; 0 = auto */
+  int32_t winner_mode;   /* how the nearest candidate of a z-buffer cell is identified.  The scatter keeps min(log-range)
+                            and min(packed log-range | source id) with two fire-and-forget 64-bit reductions; 0 (production):
+                            the packed winner is verified (its exact log-range recomputed) only where its identity matters -
+                            cells the controlled average declares "far", or every filled cell when cell-level debug output
+                            is requested; 1: every filled cell is verified; 2: every filled cell goes through the exact
+                            second traversal (smallest source id at exactly the nearest depth).  A cell whose packed winner
+                            is not confirmed always goes through that traversal, so the three modes agree bit for bit. */
   float step_size;       /* eps: float32 value of step_lr*(sigma/sigmas[-1])**2 (KITTISampling.py:135) */
   float noise_scale;     /* float32 value of np.sqrt(step_size*2) (KITTISampling.py:156) */
   float grad_ref;        /* step_refer */
@@ -173,6 +180,12 @@ typedef struct sdpc_step_buffers {
 } sdpc_step_buffers;
 
 size_t sdpc_step_workspace_bytes(int n_views, int height, int width, int big_rows);
+/* Arms the z-buffers (empty cells) and clears the header.  Call ONCE after allocating a step workspace, before the first
+ * sdpc_crossview_share / sdpc_langevin_reproject_step on it: every share call re-arms the cells it used, so there is no
+ * per-step memset.  A share call on a workspace that was never armed traps (the CUDA error surfaces at the next
+ * synchronisation) instead of returning wrong images. */
+int sdpc_step_workspace_init(void* workspace, size_t workspace_bytes, int n_views, int height, int width, int big_rows,
+                             void* stream);
 
 /* x <- x + eps*nan_to_num(grad) + rho*(-mask*(x-refer)) + noise_scale*noise  (KITTISampling.py:137-156);
  * also leaves max|x[:,0]| of the updated sample in the workspace for the tooHigh gate. */
@@ -185,20 +198,29 @@ int sdpc_step_read_max(void* workspace, float* out_max, void* stream);
  * re-project, z-buffer (count, sums, nearest), fusion, crop/mirror, correction. */
 int sdpc_crossview_share(const sdpc_step_params* p, const sdpc_step_buffers* b,
                          void* workspace, size_t workspace_bytes, void* stream);
-/* Kernels (not memsets) one sdpc_langevin_reproject_step call with these parameters and buffers launches
- * (for bench.py's gpu_launches): update [+ scatter, (verify, exact-winner pass), (cell dump), resolve, correct]. */
+/* Kernels one sdpc_langevin_reproject_step call with these parameters launches (for bench.py's gpu_launches):
+ * update [+ scatter, resolve, fix (exits at once unless resolve flagged a cell), correct]. */
 int sdpc_step_kernel_launches(const sdpc_step_params* p, const sdpc_step_buffers* b);
 /* update followed by share (when p->share != 0) on one stream. */
 int sdpc_langevin_reproject_step(const sdpc_step_params* p, const sdpc_step_buffers* b,
                                  void* workspace, size_t workspace_bytes, void* stream);
 
-/* Same step with HOST buffers (pinned or pageable): copies x, grad/noise in, runs the step,
- * copies x (and new_images when non-NULL) back.  Static inputs (refer, mask, sky, exist, poses,
- * LUTs) stay device pointers in `b`.  Used by bench.py's e2e leg. */
+/* The whole sampling step with HOST sample buffers - the call a host-side caller without device tensors makes, i.e. the
+ * body of the reference's inner loop (KITTISampling.py:137-490: scorenet(x_mod, labels), the update, the cross-view
+ * block) in one entry point, everything enqueued on `stream`:
+ *   x_host -> b->x (H2D);
+ *   b->grad = score(b->x, labels) when `score` is non-NULL (labels: device int64 [B]; score_workspace as for
+ *     sdpc_score_forward), else grad_host -> b->grad when grad_host is non-NULL (else b->grad as it is);
+ *   noise_host -> b->noise when non-NULL (else b->noise as it is: drawn on the device by the caller);
+ *   update (+ share when p->share);
+ *   b->x -> x_host and, when non-NULL and p->share, b->new_images -> new_images_host (D2H).
+ * Host buffers may be pinned or pageable; the static inputs (refer, mask, sky, exist, poses, LUTs) stay device pointers in
+ * `b`.  bench.py's e2e leg and tests/test_gpu_host_step.py call it. */
 int sdpc_langevin_reproject_step_host(const sdpc_step_params* p, const sdpc_step_buffers* b,
-                                      float* x_host, const float* grad_host, const float* noise_host,
-                                      float* new_images_host, void* workspace, size_t workspace_bytes,
-                                      void* stream);
+                                      sdpc_score_t* score, const int64_t* labels, void* score_workspace,
+                                      size_t score_workspace_bytes, float* x_host, const float* grad_host,
+                                      const float* noise_host, float* new_images_host, void* workspace,
+                                      size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Row N1: point cloud -> range image, the projection that renders the sampler's inputs

@@ -73,10 +73,12 @@ def min_depth_threshold(sigma_mod):
 
 
 @torch.no_grad()
-def project_candidates(x, geo, sigma_mod, A, to_world=None, from_world=None, origins=None):
+def project_candidates(x, geo, sigma_mod, A, to_world=None, from_world=None, origins=None, targets=None):
     """Steps 3-4 of SURVEY 8(a).  Returns per (target view t, source point j of t's group):
        nd [B, A*HW] float64, row/col [B, A*HW] int32 (row in the R-row grid),
-       plus is_neg [B,H,W] bool and too_high (0-dim bool)."""
+       plus is_neg [B,H,W] bool and too_high (0-dim bool).
+       `targets` = (first, count) restricts the TARGET views to a range inside one group (the per-rank share of a
+       view-sharded step): the leading dimension of nd/row/col/is_neg is then `count`."""
     B, _, H, W = x.shape
     HW = H * W
     G = B // A
@@ -94,9 +96,14 @@ def project_candidates(x, geo, sigma_mod, A, to_world=None, from_world=None, ori
                          torch.ones(B, HW, dtype=px.dtype, device=x.device)), 1)
         Pw = torch.bmm(to_world, P)                                  # [B,4,HW]
         cloud = Pw.view(G, A, 4, HW).permute(0, 2, 1, 3).reshape(G, 4, A * HW)
-        rel = torch.cat([torch.bmm(from_world[g * A:(g + 1) * A],
-                                   cloud[g].unsqueeze(0).expand(A, 4, A * HW))[:, :3]
-                         for g in range(G)], 0)                      # [B,3,A*HW]
+        if targets is not None:
+            t0, tn = targets
+            assert t0 // A == (t0 + tn - 1) // A, "a target range must stay inside one group"
+            rel = torch.bmm(from_world[t0:t0 + tn], cloud[t0 // A].unsqueeze(0).expand(tn, 4, A * HW))[:, :3]
+        else:
+            rel = torch.cat([torch.bmm(from_world[g * A:(g + 1) * A],
+                                       cloud[g].unsqueeze(0).expand(A, 4, A * HW))[:, :3]
+                             for g in range(G)], 0)                  # [B,3,A*HW]
     else:
         o = origins[:A]                                              # [A,3,1,1] fp32
         rel_groups = []
@@ -108,6 +115,8 @@ def project_candidates(x, geo, sigma_mod, A, to_world=None, from_world=None, ori
             cloud = torch.stack((wx, wy, wz), 1).expand(A, 3, A * HW)
             rel_groups.append(cloud - o[:, :, 0])
         rel = torch.cat(rel_groups, 0)
+        if targets is not None:
+            rel = rel[targets[0]:targets[0] + targets[1]]
     xy = torch.square(rel[:, 0]) + torch.square(rel[:, 1])
     nd = torch.log2(torch.sqrt(xy + torch.square(rel[:, 2])) + 1) / 6 * sigma_mod
     horiz = torch.atan2(rel[:, 1], rel[:, 0])
@@ -116,27 +125,32 @@ def project_candidates(x, geo, sigma_mod, A, to_world=None, from_world=None, ori
     rowr = torch.round((vert - geo.big_row_min) / geo.dv).int()
     col = colr * -1 + W - 1
     row = rowr * -1 + geo.R - 1
+    if targets is not None:
+        is_neg = is_neg[targets[0]:targets[0] + targets[1]]
     return nd, row, col, is_neg, too_high
 
 
 @torch.no_grad()
 def shared_images(x, geo, sigma_mod, A, exist_mask, sky=None, to_world=None, from_world=None,
                   origins=None, min_depth_filter=True, controlled_average=True, allowance=10.0,
-                  sky_filter=False, return_debug=False):
+                  sky_filter=False, return_debug=False, targets=None):
     """Steps 3-7 of SURVEY 8(a): the shared re-projection of every view.
 
     x [B,2,H,W] fp32 (post-Langevin sample); exist_mask bool [>=A,H,W]; sky bool [B,1,H,W].
     Returns new_images [B,2,H,W] fp32, image_mask [B,H,W] bool (already AND existMask[0]),
     too_high; with return_debug also a dict of per-candidate and per-pixel internals.
+    `targets` = (first, count): only these target views (inside one group) are built - every output then has `count`
+    leading entries; the sources are still all A views of that group.
     """
-    B, _, H, W = x.shape
+    Bx, _, H, W = x.shape
     HW, R = H * W, geo.R
     dev = x.device
-    nd, row, col, is_neg, too_high = project_candidates(x, geo, sigma_mod, A, to_world, from_world, origins)
+    nd, row, col, is_neg, too_high = project_candidates(x, geo, sigma_mod, A, to_world, from_world, origins, targets)
+    t0, B = (0, Bx) if targets is None else targets                   # B: number of target views from here on
     valid = (col > -1) & (col < W) & (row > -1) & (row < R)
     if sky_filter:            # a-5 only: source pixel's sky flag (models/__init__.py:352-355)
-        G = B // A
-        valid &= sky.reshape(G, 1, A * HW).expand(G, A, A * HW).reshape(B, A * HW)
+        G = Bx // A
+        valid &= sky.reshape(G, 1, A * HW).expand(G, A, A * HW).reshape(Bx, A * HW)[t0:t0 + B]
     valid &= exist_mask[:A].reshape(1, A * HW)
     if min_depth_filter:
         valid &= nd > min_depth_threshold(sigma_mod).to(dev)
@@ -145,9 +159,9 @@ def shared_images(x, geo, sigma_mod, A, exist_mask, sky=None, to_world=None, fro
     key = ((t_idx * R + row.long()) * W + col.long())[valid]           # flat pixel of target grid
     src = torch.arange(A * HW, device=dev).view(1, A * HW).expand(B, A * HW)[valid]
     tgt = t_idx[valid]
-    inten_all = x[:, 1].reshape(B // A, A * HW)                      # group-major source intensities
+    inten_all = x[:, 1].reshape(Bx // A, A * HW)                     # group-major source intensities
     nd_v = nd[valid]
-    in_v = inten_all[tgt // A, src]
+    in_v = inten_all[(tgt + t0) // A, src]
 
     n_pix = B * R * W
     cnt = torch.zeros(n_pix, dtype=torch.int64, device=dev).index_add_(0, key, torch.ones_like(key))
@@ -162,7 +176,7 @@ def shared_images(x, geo, sigma_mod, A, exist_mask, sky=None, to_world=None, fro
     n_tied = torch.zeros(n_pix, dtype=torch.int64, device=dev).index_add_(0, key[is_win], torch.ones_like(key[is_win]))
     has = cnt > 0
     win_safe = torch.where(has, winner, torch.zeros_like(winner))
-    grp = (torch.arange(n_pix, device=dev) // (R * W)) // A
+    grp = (torch.arange(n_pix, device=dev) // (R * W) + t0) // A
     min_i = torch.where(has, inten_all[grp, win_safe], torch.zeros((), dtype=torch.float32, device=dev))
     min_d = torch.where(has, min_d, torch.zeros((), dtype=torch.float64, device=dev))
 

@@ -9,6 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SDPC_LIB") or os.path.join(_HERE, "libsdpc_b200.so")   # SDPC_LIB: A/B timing of two builds
 
+ABI_VERSION = 2          # SDPC_ABI_VERSION of include/sdpc_b200.h
 SDPC_VARIANT_POSE, SDPC_VARIANT_TRANSLATION = 0, 1
 PREC_FP32, PREC_TF32, PREC_BF16, PREC_BF16X3 = 0, 1, 2, 3
 PRECISIONS = {"fp32": PREC_FP32, "tf32": PREC_TF32, "bf16": PREC_BF16, "bf16x3": PREC_BF16X3}
@@ -52,6 +53,7 @@ class ProjectionParams(C.Structure):
 _P, _I, _SZ = C.c_void_p, C.c_int, C.c_size_t
 SYMBOLS = [
     ("sdpc_abi_version", _I, []),
+    ("sdpc_abi_struct_bytes", _SZ, [_I]),
     ("sdpc_last_error", C.c_char_p, []),
     ("sdpc_build_arch", C.c_char_p, []),
     ("sdpc_score_create", _I, [C.POINTER(ScoreConfig), C.POINTER(_P)]),
@@ -68,6 +70,7 @@ SYMBOLS = [
     ("sdpc_score_set_profiling", _I, [_P, _I]),
     ("sdpc_score_profile_collect", _I, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_I)]),
     ("sdpc_step_workspace_bytes", _SZ, [_I, _I, _I, _I]),
+    ("sdpc_step_workspace_init", _I, [_P, _SZ, _I, _I, _I, _I, _P]),
     ("sdpc_langevin_update", _I, [C.POINTER(StepParams), C.POINTER(StepBuffers), _P, _SZ, _P]),
     ("sdpc_step_merge_max", _I, [_P, _P, _I, _P]),
     ("sdpc_step_read_max", _I, [_P, _P, _P]),
@@ -81,7 +84,8 @@ SYMBOLS = [
     ("sdpc_depth_intensity_errors", _I, [_P, _P, _P, _I, _I, _I, _P, _P]),
     ("sdpc_transform_scan", _I, [_P, _I, C.POINTER(C.c_double), C.POINTER(C.c_double), _P, _P]),
     ("sdpc_range_image_postprocess", _I, [_P, _P, _P, _P, _I, _I, C.c_double, _P, _P, _P, _P]),
-    ("sdpc_langevin_reproject_step_host", _I, [C.POINTER(StepParams), C.POINTER(StepBuffers), _P, _P, _P, _P, _P, _SZ, _P]),
+    ("sdpc_langevin_reproject_step_host", _I, [C.POINTER(StepParams), C.POINTER(StepBuffers), _P, _P, _P, _SZ, _P, _P, _P, _P,
+                                               _P, _SZ, _P]),
 ]
 
 _lib = None
@@ -104,8 +108,13 @@ def load(path=None):
     for name, res, args in SYMBOLS:
         fn = getattr(lib, name)        # AttributeError if the .so does not export a declared symbol
         fn.restype, fn.argtypes = res, args
-    if lib.sdpc_abi_version() != 1:
-        raise SdpcError("ABI version mismatch")
+    if lib.sdpc_abi_version() != ABI_VERSION:
+        raise SdpcError(f"{path}: ABI version {lib.sdpc_abi_version()} != {ABI_VERSION} of this binding (stale build: run "
+                        f"`python -c 'import __graft_entry__ as g; g.build()'`)")
+    for which, st in enumerate((StepParams, StepBuffers, ScoreConfig, ProjectionParams)):
+        if lib.sdpc_abi_struct_bytes(which) != C.sizeof(st):
+            raise SdpcError(f"{path}: sizeof({st.__name__}) is {lib.sdpc_abi_struct_bytes(which)} in the library, "
+                            f"{C.sizeof(st)} in this binding")
     if path == LIB_PATH:
         _lib = lib
     return lib

@@ -21,5 +21,14 @@ bool pdl_enabled() {
 }  // namespace sdpc
 
 extern "C" int sdpc_abi_version(void) { return SDPC_ABI_VERSION; }
+extern "C" size_t sdpc_abi_struct_bytes(int which) {
+  switch (which) {
+    case 0: return sizeof(sdpc_step_params);
+    case 1: return sizeof(sdpc_step_buffers);
+    case 2: return sizeof(sdpc_score_config);
+    case 3: return sizeof(sdpc_projection_params);
+    default: return 0;
+  }
+}
 extern "C" const char* sdpc_last_error(void) { return sdpc::g_err; }
 extern "C" const char* sdpc_build_arch(void) { return "sm_100a"; }

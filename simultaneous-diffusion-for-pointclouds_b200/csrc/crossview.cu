@@ -3,21 +3,25 @@
 // Replaces the per-step ATen pipeline of the reference samplers
 //   a-4 LiDARGen/models/KITTISampling.py:137-490  (pose matrices)
 //   a-5 LiDARGen/models/__init__.py:240-582       (translations)
-// (about 25*B small kernels + 3*B radix sorts + 6*B sparse->dense scatters per step) with four
-// launches: update, scatter (z-buffer build incl. the nearest candidate), resolve, correct.
+// (about 25*B small kernels + 3*B radix sorts + 6*B sparse->dense scatters per step) with five launches and no
+// memset: update, scatter, resolve, fix (exits at once unless resolve flagged a cell), correct.
 //
 //   update  : x <- x + eps*g + rho*(-mask*(x-ref)) + s*z ; block max of |x0| -> atomicMax
-//   scatter : one thread per SOURCE pixel: decode range (fp32), un-project (fp64), to world,
-//             then for every target view of the group: from-world, spherical re-projection,
-//             validity, and order-independent atomics into the target's R x W grid:
-//             atomicAdd count / fixed-point depth sum / fixed-point intensity sum, and the nearest
-//             candidate as {fp64 bits of the log-range, source id}: lexicographic minimum by a
-//             128-bit compare-and-swap (deterministic tie break: smallest source id).
-//   winner  : legacy / cross-check paths only (candidate-level debug output, winner_mode = 1): 64-bit
-//             atomicMin on the key, then the candidate whose log-range equals the grid minimum claims
-//             the pixel, either through a packed key + verification or a second traversal.
-//   resolve : one thread per OUTPUT pixel: average / controlled average, crop + mirror for
-//             negative ranges, existMask, correction, in-place x update, optional newImages.
+//   scatter : warp-vote compaction of the source pixels that may contribute; per compacted pixel: decode range (fp32),
+//             un-project (fp64), to world, then for every target view of the group: from-world, pixel indices
+//             (guarded fp32 estimate, crossview_core.h::pixel_fast), and only for candidates that land in the grid the
+//             exact fp64 log-range and five fire-and-forget reductions (RED, nothing is returned to the SM) into the
+//             target's R x W grid: min of the key, min of the packed (key | source id), fixed-point depth sum,
+//             fixed-point intensity sum, count.  All of them are order independent: two runs are bit-identical.
+//   resolve : one thread per grid CELL: average / controlled average, crop + mirror for negative ranges (a cell
+//             serves the pixel below it and / or the point-mirrored pixel), existMask, optional newImages - and it
+//             re-arms the cell, so the z-buffers are empty again when the call returns.  Where the nearest
+//             candidate's identity matters (a "far" cell takes its intensity; debug output) the packed winner is
+//             verified by recomputing that source's exact log-range; a cell whose packed winner is not confirmed
+//             (needs two candidates within 2e-10 relative, or the test hook) is flagged instead of finished.
+//   fix     : only when a cell was flagged: one more traversal of the candidates gives the flagged cells their exact
+//             (log-range, smallest source id) winner, the last block to finish completes and re-arms them.
+//   correct : x += c * corr with the tooHigh gate.
 //
 // Compiled with -fmad=false: see crossview_core.h.
 #include <cuda_runtime.h>
@@ -26,23 +30,40 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
+
 #include "../../include/sdpc_b200.h"
 #include "common.h"
 #include "crossview_core.h"
 
 namespace sdpc {
 
+// One z-buffer cell, 32 bytes = one L2 sector.  Armed (empty) state: {~0, ~0, 0, 0} and cnt = 0.
+struct __align__(16) CellRec {
+  unsigned long long zmin;      // fp64 bits of the smallest squared range (the log-range is a monotone function of it)
+  unsigned long long zpack;     // (zmin's bits with the low key_shift bits replaced by the source id); while a cell is
+                                // flagged: the smallest source id among the candidates at exactly the nearest range
+  long long sum_d;              // fixed-point 2^-40
+  long long sum_i;              // fixed-point 2^-32
+};
+constexpr unsigned kFlagBit = 0x80000000u;          // in cnt: resolve could not confirm the packed winner of this cell
+constexpr unsigned long long kMagic = 0x5344504362323030ull;
+
+struct StepHeader {             // first 256 bytes of the workspace
+  unsigned int max_bits;        // bit pattern of max |x0| of the last update (sdpc_step_read_max / merge_max use offset 0)
+  unsigned int pad0[3];
+  unsigned int flag_count;      // cells flagged by the resolve pass of the running call
+  unsigned int ticket;          // fix pass: blocks that finished their traversal
+  unsigned int pad1[2];
+  unsigned long long magic;     // kMagic ^ cells once sdpc_step_workspace_init armed the z-buffers
+};
+
 struct StepWorkspace {
-  unsigned int* max_bits;       // [1]   bit pattern of max |x0|
-  unsigned long long* zmin;     // [B*R*W] fp64 bits of the nearest log-range (0xFF.. = empty)
-  unsigned int* winner;         // [B*R*W] source id of the nearest candidate
-  long long* sum_d;             // [B*R*W] fixed-point 2^-40
-  long long* sum_i;             // [B*R*W] fixed-point 2^-32
+  StepHeader* hdr;
+  CellRec* rec;                 // [B*R*W]
   unsigned int* cnt;            // [B*R*W]
-  unsigned long long* zpack;    // [B*R*W] (log-range bits with the low key_shift bits replaced by the source id)
-  unsigned int* flag;           // [1]   set when a packed winner could not be confirmed -> exact winner pass runs
-  ulonglong2* zkey;             // [B*R*W] default winner path: {.x = source id, .y = fp64 bits of its log-range}, the
-                                //         lexicographic minimum over (.y, .x) kept by a 128-bit compare-and-swap
+  unsigned int* work_ctr;       // [2*B] work-item counters of the scatter ([0, n_groups)) and of the fix pass; zero between calls
+  int n_groups;
   float* shared_img;            // [B,2,H,W] newImages when the caller does not ask for them
   uint8_t* shared_mask;         // [B,H,W]   imageMask & existMask[0] & sky
   size_t cells;
@@ -54,31 +75,40 @@ static size_t workspace_layout(int B, int H, int R, int W, char* base, StepWorks
   size_t cells = (size_t)B * R * W;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
-  size_t o_max = take(256);
-  size_t o_zmin = take(cells * 8);
-  size_t o_win = take(cells * 4);
-  size_t o_sd = take(cells * 8);
-  size_t o_si = take(cells * 8);
+  size_t o_hdr = take(256);
+  size_t o_rec = take(cells * sizeof(CellRec));
   size_t o_cnt = take(cells * 4);
-  size_t o_zpack = take(cells * 8);
-  size_t o_zkey = take(cells * 16);
+  size_t o_ctr = take((size_t)B * 2 * 4);
   size_t o_img = take((size_t)B * 2 * H * W * 4);
   size_t o_msk = take((size_t)B * H * W);
   if (ws) {
+    ws->hdr = (StepHeader*)(base + o_hdr);
+    ws->rec = (CellRec*)(base + o_rec);
+    ws->cnt = (unsigned int*)(base + o_cnt);
+    ws->work_ctr = (unsigned int*)(base + o_ctr);
+    ws->n_groups = B;             // set by the caller once the group size is known (<= B)
     ws->shared_img = (float*)(base + o_img);
     ws->shared_mask = (uint8_t*)(base + o_msk);
-    ws->max_bits = (unsigned int*)(base + o_max);
-    ws->zmin = (unsigned long long*)(base + o_zmin);
-    ws->winner = (unsigned int*)(base + o_win);
-    ws->sum_d = (long long*)(base + o_sd);
-    ws->sum_i = (long long*)(base + o_si);
-    ws->cnt = (unsigned int*)(base + o_cnt);
-    ws->zpack = (unsigned long long*)(base + o_zpack);
-    ws->zkey = (ulonglong2*)(base + o_zkey);
-    ws->flag = (unsigned int*)(base + o_max + 64);
     ws->cells = cells;
   }
   return off;
+}
+
+__global__ void __launch_bounds__(256) arm_kernel(StepWorkspace ws) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < ws.cells) {
+    CellRec r;
+    r.zmin = ~0ull; r.zpack = ~0ull; r.sum_d = 0; r.sum_i = 0;
+    ws.rec[i] = r;
+    ws.cnt[i] = 0u;
+  }
+  if (i < 2 * (size_t)ws.n_groups) ws.work_ctr[i] = 0u;
+  if (i == 0) {
+    ws.hdr->max_bits = 0u;
+    ws.hdr->flag_count = 0u;
+    ws.hdr->ticket = 0u;
+    ws.hdr->magic = kMagic ^ (unsigned long long)ws.cells;
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -141,70 +171,133 @@ __global__ void merge_max_kernel(unsigned int* max_bits, const float* other, int
 }
 
 // ------------------------------------------------------------------------------------------
-// scatter / winner
+// scatter / resolve / fix
 // ------------------------------------------------------------------------------------------
 constexpr int kMaxGroup = 32;
+constexpr int kSeg = 128;               // source pixels per work item of the production traversal (one warp, 4 per lane)
+constexpr int kTravThreads = 256;       // 8 warps per persistent block
+constexpr int kTravWarps = kTravThreads / 32;
 
-struct ScatterArgs {
-  const float* x;
+__device__ const double g_log2_tab[SDPC_LOG2_TABLE_DOUBLES] = {SDPC_LOG2_TABLE};
+
+struct StepArgs {
+  float* x;                     // scatter / resolve / fix only read it
+  const int32_t* mask;
   const uint8_t* sky;
   const uint8_t* exist;
   const double* to_world;
   const double* from_world;
   const float* origins;
   const double *cos_az, *sin_az, *cos_el, *sin_el;
-  int32_t* dbg_row;
+  float* img;                   // [B,2,H,W] newImages (caller's buffer or workspace scratch)
+  int32_t* dbg_row;             // candidate-level debug output: selects the full fp64 scatter
   int32_t* dbg_col;
   uint8_t* dbg_valid;
+  int32_t* dbg_cnt;             // cell-level debug output
+  int32_t* dbg_winner;
+  double* dbg_min_d;
   StepWorkspace ws;
   GeoConsts geo;
   int A, variant, sky_filter, tgt_first, tgt_count;
   float sigma_mod, min_depth_thr;
+  double allowance;
   int key_shift;                // low bits of the packed key that hold the source id
+  int want_key;                 // the nearest candidate is needed (controlled average or cell-level debug output)
+  int winner_mode;              // 0: verify the packed winner where it matters; 1: verify every filled cell;
+                                // 2: flag every filled cell (the exact traversal decides every winner)
 };
 
-// Exact (log-range, source id) minimum in ONE 16-byte word per cell (the default winner path): the nearest candidate and,
-// among candidates at exactly the same depth, the smallest source id - the same winner the packed-key path confirms
-// with its verification pass, without that pass and without the second 64-bit atomicMin.  Values only ever decrease,
-// so a stale (even torn) first read can only cost one extra CAS round, never a wrong skip.
-__device__ __forceinline__ ulonglong2 cas128(ulonglong2* p, ulonglong2 cmp, ulonglong2 val) {
-  ulonglong2 old;
-  asm volatile(
-      "{\n\t.reg .b128 c, s, o;\n\t"
-      "mov.b128 c, {%2, %3};\n\t"
-      "mov.b128 s, {%4, %5};\n\t"
-      "atom.relaxed.gpu.global.cas.b128 o, [%6], c, s;\n\t"
-      "mov.b128 {%0, %1}, o;\n\t}"
-      : "=l"(old.x), "=l"(old.y)
-      : "l"(cmp.x), "l"(cmp.y), "l"(val.x), "l"(val.y), "l"(p)
-      : "memory");
-  return old;
+struct SourcePoint {            // a source pixel in world coordinates (pose variant: homogeneous)
+  double wx, wy, wz, ww;
+};
+
+// decode + un-project + to-world of pixel p of source view b (a-th view of its group); to: its 4x4 (pose variant)
+__device__ __forceinline__ SourcePoint source_point(const StepArgs& a, int b, int src_a, int p, const double* to,
+                                                    const float* org) {
+  const int HW = a.geo.H * a.geo.W;
+  const int r = p / a.geo.W, c = p - r * a.geo.W;
+  const float x0 = a.x[((size_t)b * 2) * HW + p];
+  const float dist = decode_range(x0, a.sigma_mod, a.geo.recip);
+  double P[3];
+  unproject(dist, a.cos_az[c], a.sin_az[c], a.cos_el[r], a.sin_el[r], P);
+  SourcePoint s;
+  s.ww = 1.0;
+  if (a.variant == SDPC_VARIANT_POSE) {
+    s.wx = dot4(to + 0, P[0], P[1], P[2], 1.0);
+    s.wy = dot4(to + 4, P[0], P[1], P[2], 1.0);
+    s.wz = dot4(to + 8, P[0], P[1], P[2], 1.0);
+    s.ww = dot4(to + 12, P[0], P[1], P[2], 1.0);
+  } else {
+    s.wx = P[0] + (double)org[src_a * 3 + 0];
+    s.wy = P[1] + (double)org[src_a * 3 + 1];
+    s.wz = P[2] + (double)org[src_a * 3 + 2];
+  }
+  return s;
 }
-__device__ __forceinline__ void zkey_min(ulonglong2* p, unsigned long long key, unsigned src_id) {
-  const ulonglong2 mine = make_ulonglong2((unsigned long long)src_id, key);
-  ulonglong2 cur = *p;
-  while (mine.y < cur.y || (mine.y == cur.y && mine.x < cur.x)) {
-    const ulonglong2 old = cas128(p, cur, mine);
-    if (old.x == cur.x && old.y == cur.y) break;
-    cur = old;
+
+// the point in the frame of target view t (from: rows 0..2 of its 4x4; ta: index of t in its group)
+__device__ __forceinline__ void to_target(const StepArgs& a, const SourcePoint& s, const double* from, const float* org,
+                                          int ta, double* qx, double* qy, double* qz) {
+  if (a.variant == SDPC_VARIANT_POSE) {
+    *qx = dot4(from + 0, s.wx, s.wy, s.wz, s.ww);
+    *qy = dot4(from + 4, s.wx, s.wy, s.wz, s.ww);
+    *qz = dot4(from + 8, s.wx, s.wy, s.wz, s.ww);
+  } else {
+    *qx = s.wx - (double)org[ta * 3 + 0];
+    *qy = s.wy - (double)org[ta * 3 + 1];
+    *qz = s.wz - (double)org[ta * 3 + 2];
   }
 }
 
-template <int PASS>
-__global__ void __launch_bounds__(256) scatter_kernel(ScatterArgs a) {
+// The five reductions of one candidate; none returns a value, so the compiler emits RED and the warp never waits.
+// r2: exact squared range (the z-buffer key); nd: its log-range as the depth sum takes it.
+__device__ __forceinline__ void accumulate(const StepArgs& a, size_t cell, double r2, double nd, unsigned src_id,
+                                           long long inten_fx) {
+  CellRec* rec = a.ws.rec + cell;
+  if (a.want_key) {
+    const unsigned long long key = (unsigned long long)__double_as_longlong(r2);      // r2 >= 0: monotone
+    atomicMin(&rec->zmin, key);
+    atomicMin(&rec->zpack, ((key >> a.key_shift) << a.key_shift) | (unsigned long long)src_id);
+  }
+  atomicAdd((unsigned long long*)&rec->sum_d, (unsigned long long)depth_to_fixed(nd));
+  atomicAdd((unsigned long long*)&rec->sum_i, (unsigned long long)inten_fx);
+  atomicAdd(a.ws.cnt + cell, 1u);
+}
+// fix pass: a candidate of a flagged cell at exactly the nearest range reports its source id
+__device__ __forceinline__ void report_winner(const StepArgs& a, size_t cell, double r2, unsigned src_id) {
+  if (!(__ldcg(a.ws.cnt + cell) & kFlagBit)) return;
+  CellRec* rec = a.ws.rec + cell;
+  if ((unsigned long long)__double_as_longlong(r2) == __ldcg(&rec->zmin)) atomicMin(&rec->zpack, (unsigned long long)src_id);
+}
+
+// The min-depth filter (KITTISampling.py:273-275, nd > threshold in float64) on the table logarithm: decided by the
+// estimate unless it is within 1e-12 of the threshold, where the library expression of the reference decides.
+__device__ __forceinline__ bool passes_min_depth(const StepArgs& a, double r2, double nd_fast) {
+  if (a.min_depth_thr < 0.0f) return true;
+  const double thr = (double)a.min_depth_thr;
+  if (fabs(nd_fast - thr) > 1e-12 * (1.0 + thr)) return nd_fast > thr;
+  return log_range_of_r2(r2, a.sigma_mod, a.geo) > thr;
+}
+
+__device__ __forceinline__ void check_armed(const StepArgs& a) {
+  // a workspace that was never armed (sdpc_step_workspace_init) would give silently wrong z-buffers: fail loudly
+  if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0 &&
+      a.ws.hdr->magic != (kMagic ^ (unsigned long long)a.ws.cells)) {
+    printf("sdpc: step workspace is not armed: call sdpc_step_workspace_init once before the first step\n");
+    __trap();
+  }
+}
+
+// Full fp64 traversal, one thread per source pixel, with the candidate-level debug output: the cross-check of the
+// production traversal below (tests assert that both leave bit-identical cells).  FIX: the second traversal that gives
+// flagged cells their exact winner.
+template <bool FIX>
+__device__ __forceinline__ void traverse_full(const StepArgs& a, double* s_to, double* s_from, float* s_org) {
   const int HW = a.geo.H * a.geo.W;
-  const int src_a = blockIdx.y;              // source view within its group
-  const int g = blockIdx.z;                  // group
-  const int b = g * a.A + src_a;             // global source view
-  // targets of this group that this call resolves
+  const int src_a = blockIdx.y, g = blockIdx.z, b = g * a.A + src_a;
   const int t_lo = max(g * a.A, a.tgt_first);
   const int t_hi = min((g + 1) * a.A, a.tgt_first + a.tgt_count);
   if (t_lo >= t_hi) return;
-  if (PASS == 1 && *a.ws.flag == 0) return;   // every packed winner was confirmed: nothing to do
-
-  __shared__ double s_to[16];
-  __shared__ double s_from[kMaxGroup * 12];
-  __shared__ float s_org[kMaxGroup * 3];
   if (a.variant == SDPC_VARIANT_POSE) {
     if (threadIdx.x < 16) s_to[threadIdx.x] = a.to_world[(size_t)b * 16 + threadIdx.x];
     for (int i = threadIdx.x; i < (t_hi - t_lo) * 12; i += blockDim.x)
@@ -213,277 +306,338 @@ __global__ void __launch_bounds__(256) scatter_kernel(ScatterArgs a) {
     for (int i = threadIdx.x; i < a.A * 3; i += blockDim.x) s_org[i] = a.origins[i];
   }
   __syncthreads();
-
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= HW) return;
-  const bool want_dbg = (PASS == 0) && (a.dbg_row != nullptr);
+  const bool want_dbg = !FIX && a.dbg_row != nullptr;
   bool src_ok = a.exist[(size_t)src_a * HW + p] != 0;
   if (a.sky_filter) src_ok = src_ok && (a.sky[(size_t)b * HW + p] != 0);
   if (!src_ok && !want_dbg) return;
-
-  const int r = p / a.geo.W, c = p - r * a.geo.W;
-  const float x0 = a.x[((size_t)b * 2) * HW + p];
-  const float x1 = a.x[((size_t)b * 2 + 1) * HW + p];
-  const float dist = decode_range(x0, a.sigma_mod, a.geo.recip);
-  double P[3];
-  unproject(dist, a.cos_az[c], a.sin_az[c], a.cos_el[r], a.sin_el[r], P);
-  double wx, wy, wz, ww = 1.0;
-  if (a.variant == SDPC_VARIANT_POSE) {
-    wx = dot4(s_to + 0, P[0], P[1], P[2], 1.0);
-    wy = dot4(s_to + 4, P[0], P[1], P[2], 1.0);
-    wz = dot4(s_to + 8, P[0], P[1], P[2], 1.0);
-    ww = dot4(s_to + 12, P[0], P[1], P[2], 1.0);
-  } else {
-    wx = P[0] + (double)s_org[src_a * 3 + 0];
-    wy = P[1] + (double)s_org[src_a * 3 + 1];
-    wz = P[2] + (double)s_org[src_a * 3 + 2];
-  }
-  const long long inten_fx = inten_to_fixed(x1);
+  const SourcePoint s = source_point(a, b, src_a, p, s_to, s_org);
+  const long long inten_fx = FIX ? 0 : inten_to_fixed(a.x[((size_t)b * 2 + 1) * HW + p]);
   const unsigned src_id = (unsigned)(src_a * HW + p);
   const size_t grid_cells = (size_t)a.geo.R * a.geo.W;
-
   for (int t = t_lo; t < t_hi; ++t) {
     double qx, qy, qz;
-    if (a.variant == SDPC_VARIANT_POSE) {
-      const double* m = s_from + (t - t_lo) * 12;
-      qx = dot4(m + 0, wx, wy, wz, ww);
-      qy = dot4(m + 4, wx, wy, wz, ww);
-      qz = dot4(m + 8, wx, wy, wz, ww);
-    } else {
-      const int ta = t - g * a.A;
-      qx = wx - (double)s_org[ta * 3 + 0];
-      qy = wy - (double)s_org[ta * 3 + 1];
-      qz = wz - (double)s_org[ta * 3 + 2];
-    }
-    Candidate cd = reproject(qx, qy, qz, a.sigma_mod, a.geo);
+    to_target(a, s, s_from + (t - t_lo) * 12, s_org, t - g * a.A, &qx, &qy, &qz);
+    const Candidate cd = reproject(qx, qy, qz, a.sigma_mod, a.geo);
     bool ok = src_ok && in_grid(cd, a.geo);
     if (a.min_depth_thr >= 0.0f) ok = ok && (cd.nd > (double)a.min_depth_thr);
     if (want_dbg) {
-      size_t k = (size_t)t * a.A * HW + src_id;
+      const size_t k = (size_t)t * a.A * HW + src_id;
       a.dbg_row[k] = cd.row;
       a.dbg_col[k] = cd.col;
       a.dbg_valid[k] = ok ? 1 : 0;
     }
     if (!ok) continue;
     const size_t cell = (size_t)t * grid_cells + (size_t)cd.row * a.geo.W + cd.col;
-    const unsigned long long key = (unsigned long long)__double_as_longlong(cd.nd);   // nd >= 0: monotone
-    if (PASS == 0) {
-      atomicMin(a.ws.zmin + cell, key);
-      atomicMin(a.ws.zpack + cell, ((key >> a.key_shift) << a.key_shift) | (unsigned long long)src_id);
-      atomicAdd(a.ws.cnt + cell, 1u);
-      atomicAdd((unsigned long long*)(a.ws.sum_d + cell), (unsigned long long)depth_to_fixed(cd.nd));
-      atomicAdd((unsigned long long*)(a.ws.sum_i + cell), (unsigned long long)inten_fx);
-    } else {
-      if (a.ws.zmin[cell] == key) atomicMin(a.ws.winner + cell, src_id);
-    }
+    const double r2 = range2(qx, qy, qz);
+    if (!FIX) accumulate(a, cell, r2, cd.nd, src_id, inten_fx);
+    else report_winner(a, cell, r2, src_id);
   }
 }
 
-
-// ------------------------------------------------------------------------------------------
-// production scatter: compacted valid source pixels, fp32-guarded re-projection; nearest candidate by a 128-bit CAS on
-// {log-range, source id} (CAS = true, default) or by the packed 64-bit key that verify_winner_kernel confirms (CAS = false)
-// ------------------------------------------------------------------------------------------
-constexpr int kChunk = 1024;      // source pixels per block (4 per thread)
-
-template <bool CAS>
-__global__ void __launch_bounds__(256) scatter_fast_kernel(ScatterArgs a) {
-  const int HW = a.geo.H * a.geo.W;
-  const int src_a = blockIdx.y, g = blockIdx.z, b = g * a.A + src_a;
-  const int t_lo = max(g * a.A, a.tgt_first);
-  const int t_hi = min((g + 1) * a.A, a.tgt_first + a.tgt_count);
-  if (t_lo >= t_hi) return;
+__global__ void __launch_bounds__(256) scatter_full_kernel(StepArgs a) {
   __shared__ double s_to[16];
   __shared__ double s_from[kMaxGroup * 12];
   __shared__ float s_org[kMaxGroup * 3];
-  __shared__ unsigned short s_list[kChunk];
-  __shared__ int s_wsum[8];
+  check_armed(a);
+  traverse_full<false>(a, s_to, s_from, s_org);
+}
+
+// Production traversal.  Persistent blocks (blockIdx.y = group); every WARP draws work items - 128 consecutive pixels of
+// one source view of the group - from the group's counter until none is left, so rows the beam mask empties and
+// regions that project outside the target grids do not leave SMs idle.  Per item: warp-vote / prefix compaction of
+// the pixels that may contribute (up to 4 per lane, kept in registers as world points), then target by target: the
+// target's matrix comes out of shared memory once and serves the lane's pixels.
+template <bool FIX>
+__device__ __forceinline__ void traverse_items(const StepArgs& a, unsigned* counter) {
+  __shared__ double s_to[kMaxGroup * 16];
+  __shared__ double s_from[kMaxGroup * 12];
+  __shared__ float s_org[kMaxGroup * 3];
+  __shared__ double s_tab[SDPC_LOG2_TABLE_DOUBLES];
+  __shared__ unsigned char s_list[kTravWarps][kSeg];
+  const int HW = a.geo.H * a.geo.W;
+  const int g = blockIdx.y;
+  const int t_lo = max(g * a.A, a.tgt_first);
+  const int t_hi = min((g + 1) * a.A, a.tgt_first + a.tgt_count);
+  if (t_lo >= t_hi) return;
   if (a.variant == SDPC_VARIANT_POSE) {
-    if (threadIdx.x < 16) s_to[threadIdx.x] = a.to_world[(size_t)b * 16 + threadIdx.x];
+    for (int i = threadIdx.x; i < a.A * 16; i += blockDim.x) s_to[i] = a.to_world[(size_t)g * a.A * 16 + i];
     for (int i = threadIdx.x; i < (t_hi - t_lo) * 12; i += blockDim.x)
       s_from[i] = a.from_world[(size_t)(t_lo + i / 12) * 16 + (i % 12)];
   } else {
     for (int i = threadIdx.x; i < a.A * 3; i += blockDim.x) s_org[i] = a.origins[i];
   }
-  // ---- phase 1: warp-vote / prefix compaction of the source pixels that may contribute
-  const int base = blockIdx.x * kChunk;
+  for (int i = threadIdx.x; i < SDPC_LOG2_TABLE_DOUBLES; i += blockDim.x) s_tab[i] = g_log2_tab[i];
+  __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uchar4 ex = *reinterpret_cast<const uchar4*>(a.exist + (size_t)src_a * HW + base + threadIdx.x * 4);
-  uchar4 sk = make_uchar4(1, 1, 1, 1);
-  if (a.sky_filter) sk = *reinterpret_cast<const uchar4*>(a.sky + (size_t)b * HW + base + threadIdx.x * 4);
-  const unsigned v = (ex.x && sk.x ? 1u : 0u) | (ex.y && sk.y ? 2u : 0u) | (ex.z && sk.z ? 4u : 0u) | (ex.w && sk.w ? 8u : 0u);
-  const int mine = __popc(v);
-  int incl = mine;
+  const unsigned segs = (unsigned)(HW / kSeg), n_items = segs * (unsigned)a.A;
+  const unsigned grid_cells = (unsigned)(a.geo.R * a.geo.W);
+  unsigned char* list = s_list[warp];
+  for (;;) {
+    unsigned item = 0;
+    if (lane == 0) item = atomicAdd(counter + g, 1u);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if (item >= n_items) break;
+    const int src_a = (int)(item / segs), base = (int)(item % segs) * kSeg, b = g * a.A + src_a;
+    // ---- compaction of the pixels that may contribute
+    const uchar4 ex = *reinterpret_cast<const uchar4*>(a.exist + (size_t)src_a * HW + base + lane * 4);
+    uchar4 sk = make_uchar4(1, 1, 1, 1);
+    if (a.sky_filter) sk = *reinterpret_cast<const uchar4*>(a.sky + (size_t)b * HW + base + lane * 4);
+    const unsigned v = (ex.x && sk.x ? 1u : 0u) | (ex.y && sk.y ? 2u : 0u) | (ex.z && sk.z ? 4u : 0u) | (ex.w && sk.w ? 8u : 0u);
+    const int mine = __popc(v);
+    int incl = mine;
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int n = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += n;
-  }
-  if (lane == 31) s_wsum[warp] = incl;
-  __syncthreads();
-  int off = incl - mine, total = 0;
-#pragma unroll
-  for (int w = 0; w < 8; ++w) {
-    if (w < warp) off += s_wsum[w];
-    total += s_wsum[w];
-  }
-#pragma unroll
-  for (int k = 0; k < 4; ++k)
-    if (v & (1u << k)) s_list[off++] = (unsigned short)(threadIdx.x * 4 + k);
-  __syncthreads();
-  // ---- phase 2: every lane works on a contributing pixel
-  const size_t grid_cells = (size_t)a.geo.R * a.geo.W;
-  for (int i = threadIdx.x; i < total; i += blockDim.x) {
-    const int p = base + s_list[i];
-    const int r = p / a.geo.W, c = p - r * a.geo.W;
-    const float x0 = a.x[((size_t)b * 2) * HW + p];
-    const float x1 = a.x[((size_t)b * 2 + 1) * HW + p];
-    const float dist = decode_range(x0, a.sigma_mod, a.geo.recip);
-    double P[3];
-    unproject(dist, a.cos_az[c], a.sin_az[c], a.cos_el[r], a.sin_el[r], P);
-    double wx, wy, wz, ww = 1.0;
-    if (a.variant == SDPC_VARIANT_POSE) {
-      wx = dot4(s_to + 0, P[0], P[1], P[2], 1.0);
-      wy = dot4(s_to + 4, P[0], P[1], P[2], 1.0);
-      wz = dot4(s_to + 8, P[0], P[1], P[2], 1.0);
-      ww = dot4(s_to + 12, P[0], P[1], P[2], 1.0);
-    } else {
-      wx = P[0] + (double)s_org[src_a * 3 + 0];
-      wy = P[1] + (double)s_org[src_a * 3 + 1];
-      wz = P[2] + (double)s_org[src_a * 3 + 2];
+    for (int o = 1; o < 32; o <<= 1) {
+      const int n = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += n;
     }
-    const long long inten_fx = inten_to_fixed(x1);
-    const unsigned src_id = (unsigned)(src_a * HW + p);
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total == 0) continue;
+    int off = incl - mine;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (v & (1u << k)) list[off++] = (unsigned char)(lane * 4 + k);
+    __syncwarp();
+    // ---- the lane's pixels as world points
+    SourcePoint sp[4];
+    long long ifx[4];
+    int pix[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int idx = lane + 32 * j;
+      pix[j] = -1;
+      ifx[j] = 0;
+      sp[j].wx = sp[j].wy = sp[j].wz = 0.0; sp[j].ww = 1.0;
+      if (idx < total) {
+        const int p = base + list[idx];
+        pix[j] = p;
+        sp[j] = source_point(a, b, src_a, p, s_to + src_a * 16, s_org);
+        if (!FIX) ifx[j] = inten_to_fixed(a.x[((size_t)b * 2 + 1) * HW + p]);
+      }
+    }
+    __syncwarp();                      // the list may be overwritten by the next item from here on
+    // ---- target by target
     for (int t = t_lo; t < t_hi; ++t) {
-      double qx, qy, qz;
+      double m[12];
       if (a.variant == SDPC_VARIANT_POSE) {
-        const double* m = s_from + (t - t_lo) * 12;
-        qx = dot4(m + 0, wx, wy, wz, ww);
-        qy = dot4(m + 4, wx, wy, wz, ww);
-        qz = dot4(m + 8, wx, wy, wz, ww);
+#pragma unroll
+        for (int k = 0; k < 12; ++k) m[k] = s_from[(t - t_lo) * 12 + k];
       } else {
-        const int ta = t - g * a.A;
-        qx = wx - (double)s_org[ta * 3 + 0];
-        qy = wy - (double)s_org[ta * 3 + 1];
-        qz = wz - (double)s_org[ta * 3 + 2];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) m[k] = (double)s_org[(t - g * a.A) * 3 + k];
       }
-      const Candidate cd = reproject_fast(qx, qy, qz, a.sigma_mod, a.geo);
-      bool ok = in_grid(cd, a.geo);
-      if (a.min_depth_thr >= 0.0f) ok = ok && (cd.nd > (double)a.min_depth_thr);
-      if (!ok) continue;
-      const size_t cell = (size_t)t * grid_cells + (size_t)cd.row * a.geo.W + cd.col;
-      const unsigned long long key = (unsigned long long)__double_as_longlong(cd.nd);
-      if constexpr (CAS) {
-        zkey_min(a.ws.zkey + cell, key, src_id);
-      } else {
-        atomicMin(a.ws.zmin + cell, key);
-        atomicMin(a.ws.zpack + cell, ((key >> a.key_shift) << a.key_shift) | (unsigned long long)src_id);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (pix[j] < 0) continue;
+        double qx, qy, qz;
+        if (a.variant == SDPC_VARIANT_POSE) {
+          qx = dot4(m + 0, sp[j].wx, sp[j].wy, sp[j].wz, sp[j].ww);
+          qy = dot4(m + 4, sp[j].wx, sp[j].wy, sp[j].wz, sp[j].ww);
+          qz = dot4(m + 8, sp[j].wx, sp[j].wy, sp[j].wz, sp[j].ww);
+        } else {
+          qx = sp[j].wx - m[0];
+          qy = sp[j].wy - m[1];
+          qz = sp[j].wz - m[2];
+        }
+        int row, col;
+        if (!pixel_fast(qx, qy, qz, a.geo, &row, &col)) continue;
+        const size_t cell = (size_t)((unsigned)t * grid_cells + (unsigned)(row * a.geo.W + col));
+        const double r2 = range2(qx, qy, qz);
+        const unsigned src_id = (unsigned)(src_a * HW + pix[j]);
+        if (FIX) {
+          if (!(__ldcg(a.ws.cnt + cell) & kFlagBit)) continue;
+        }
+        const double nd = fast_log_range_of_r2(r2, a.sigma_mod, a.geo, s_tab);
+        if (!passes_min_depth(a, r2, nd)) continue;
+        if (!FIX) accumulate(a, cell, r2, nd, src_id, ifx[j]);
+        else report_winner(a, cell, r2, src_id);
       }
-      atomicAdd(a.ws.cnt + cell, 1u);
-      atomicAdd((unsigned long long*)(a.ws.sum_d + cell), (unsigned long long)depth_to_fixed(cd.nd));
-      atomicAdd((unsigned long long*)(a.ws.sum_i + cell), (unsigned long long)inten_fx);
     }
   }
 }
 
-// Confirm the packed winners: for every filled cell recompute the exact log-range of the source the packed key
-// names; if it is the cell minimum that source is the (smallest-id) nearest candidate, otherwise raise the flag
-// that makes the exact winner pass run.
-__global__ void __launch_bounds__(256) verify_winner_kernel(ScatterArgs a) {
+__global__ void __launch_bounds__(kTravThreads) scatter_fast_kernel(StepArgs a) {
+  check_armed(a);
+  traverse_items<false>(a, a.ws.work_ctr);
+}
+
+// Exact squared range of source id `id` of the group of target t, seen from t: the expression the scatter evaluated
+__device__ __forceinline__ unsigned long long exact_key_of(const StepArgs& a, int t, unsigned id) {
   const int HW = a.geo.H * a.geo.W;
-  const size_t grid_cells = (size_t)a.geo.R * a.geo.W;
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (size_t)a.tgt_count * grid_cells) return;
-  const int t = a.tgt_first + (int)(i / grid_cells);
-  const size_t cell = (size_t)a.tgt_first * grid_cells + i;
-  if (a.ws.cnt[cell] == 0) return;
-  const unsigned id = (unsigned)(a.ws.zpack[cell] & ((1ull << a.key_shift) - 1ull));
   const int g = t / a.A, src_a = id / HW, p = id - src_a * HW, b = g * a.A + src_a;
-  const int r = p / a.geo.W, c = p - r * a.geo.W;
-  const float dist = decode_range(a.x[((size_t)b * 2) * HW + p], a.sigma_mod, a.geo.recip);
-  double P[3], qx, qy, qz;
-  unproject(dist, a.cos_az[c], a.sin_az[c], a.cos_el[r], a.sin_el[r], P);
-  if (a.variant == SDPC_VARIANT_POSE) {
-    const double* tw = a.to_world + (size_t)b * 16;
-    const double wx = dot4(tw + 0, P[0], P[1], P[2], 1.0), wy = dot4(tw + 4, P[0], P[1], P[2], 1.0);
-    const double wz = dot4(tw + 8, P[0], P[1], P[2], 1.0), ww = dot4(tw + 12, P[0], P[1], P[2], 1.0);
-    const double* m = a.from_world + (size_t)t * 16;
-    qx = dot4(m + 0, wx, wy, wz, ww);
-    qy = dot4(m + 4, wx, wy, wz, ww);
-    qz = dot4(m + 8, wx, wy, wz, ww);
-  } else {
-    const int ta = t - g * a.A;
-    qx = (P[0] + (double)a.origins[src_a * 3 + 0]) - (double)a.origins[ta * 3 + 0];
-    qy = (P[1] + (double)a.origins[src_a * 3 + 1]) - (double)a.origins[ta * 3 + 1];
-    qz = (P[2] + (double)a.origins[src_a * 3 + 2]) - (double)a.origins[ta * 3 + 2];
-  }
-  const double xy = qx * qx + qy * qy;
-  double nd = log2(sqrt(xy + qz * qz) + 1.0);
-  nd = sdiv(nd, 6.0, a.geo.recip) * (double)a.sigma_mod;
-  if ((unsigned long long)__double_as_longlong(nd) == a.ws.zmin[cell]) a.ws.winner[cell] = id;
-  else atomicOr(a.ws.flag, 1u);
+  const SourcePoint s = source_point(a, b, src_a, p, a.to_world + (size_t)b * 16, a.origins);
+  double qx, qy, qz;
+  to_target(a, s, a.from_world + (size_t)t * 16, a.origins, t - g * a.A, &qx, &qy, &qz);
+  return (unsigned long long)__double_as_longlong(range2(qx, qy, qz));
 }
 
-// ------------------------------------------------------------------------------------------
-// resolve
-// ------------------------------------------------------------------------------------------
-struct ResolveArgs {
-  const float* x;
-  float* img;                   // [B,2,H,W] newImages (caller's buffer or workspace scratch)
-  const int32_t* mask;
-  const uint8_t* sky;
-  const uint8_t* exist;
-  float* new_images;
-  int32_t* too_high_out;
-  int32_t* dbg_cnt;
-  int32_t* dbg_winner;
-  double* dbg_min_d;
-  StepWorkspace ws;
-  GeoConsts geo;
-  int A, tgt_first, tgt_count;
-  int cas;                      // nearest depth and winner come from ws.zkey (128-bit CAS winner path)
-  float sigma_mod, corr_coef;
-  double allowance;
-};
-
-__global__ void __launch_bounds__(256) resolve_kernel(ResolveArgs a) {
-  const int HW = a.geo.H * a.geo.W;
-  const int W = a.geo.W, H = a.geo.H, R = a.geo.R;
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  const int t = a.tgt_first + blockIdx.y;
-  if (p >= HW) return;
-  const int r = p / W, c = p - r * W;
-  const size_t i0 = ((size_t)t * 2) * HW + p;
-  const size_t i1 = i0 + HW;
-  const float x0 = a.x[i0];
-  const bool neg = x0 < 0.0f;
-  // crop rows [R-H, R); negative ranges read the point-mirrored cell (KITTISampling.py:401-403)
-  int gr = neg ? (H - 1 - r) : (r + R - H);
-  int gc = neg ? ((c - W / 2 + W) % W) : c;
-  const size_t cell = (size_t)t * R * W + (size_t)gr * W + gc;
-  const unsigned cnt = a.ws.cnt[cell];
-  double min_d = 0.0;
-  float min_i = 0.0f;
-  if (cnt > 0) {
-    unsigned w;
-    if (a.cas) {
-      const ulonglong2 kv = a.ws.zkey[cell];
-      min_d = __longlong_as_double((long long)kv.y);
-      w = (unsigned)kv.x;
-    } else {
-      min_d = __longlong_as_double((long long)a.ws.zmin[cell]);
-      w = a.ws.winner[cell];
-    }
-    const int g = t / a.A;
-    const int wa = w / HW, wp = w - wa * HW;
-    min_i = a.x[((size_t)(g * a.A + wa) * 2 + 1) * HW + wp];
+// outputs of one cell to the pixel(s) it serves
+__device__ __forceinline__ void write_consumers(const StepArgs& a, int t, int gr, int gc, bool use_d, bool use_m,
+                                                double depth, float inten, bool filled) {
+  const int HW = a.geo.H * a.geo.W, W = a.geo.W, H = a.geo.H, R = a.geo.R;
+  if (use_d) {                                                    // the pixel below the crop offset, non-negative range
+    const int p = (gr - (R - H)) * W + gc;
+    const size_t i0 = ((size_t)t * 2) * HW + p;
+    a.img[i0] = (float)depth;
+    a.img[i0 + HW] = inten;
+    a.ws.shared_mask[(size_t)t * HW + p] = (filled && (a.exist[p] != 0) && (a.sky[(size_t)t * HW + p] != 0)) ? 1 : 0;
   }
-  Fused f = fuse_cell(cnt, a.ws.sum_d[cell], a.ws.sum_i[cell], min_d, min_i, a.sigma_mod, a.allowance, a.geo.recip);
-  float nd = (float)(neg ? f.depth * -1.0 : f.depth);
-  float ni = f.inten;
-  a.img[i0] = nd;
-  a.img[i1] = ni;
-  a.ws.shared_mask[(size_t)t * HW + p] = (f.filled && (a.exist[p] != 0) && (a.sky[(size_t)t * HW + p] != 0)) ? 1 : 0;
+  if (use_m) {                                                    // the point-mirrored pixel, negative range
+    const int p = (H - 1 - gr) * W + ((gc + W / 2) % W);
+    const size_t i0 = ((size_t)t * 2) * HW + p;
+    a.img[i0] = (float)(depth * -1.0);
+    a.img[i0 + HW] = inten;
+    a.ws.shared_mask[(size_t)t * HW + p] = (filled && (a.exist[p] != 0) && (a.sky[(size_t)t * HW + p] != 0)) ? 1 : 0;
+  }
+}
+
+__device__ __forceinline__ void consumers_of(const StepArgs& a, int t, int gr, int gc, bool* use_d, bool* use_m) {
+  // crop rows [R-H, R); negative ranges read the point-mirrored cell (KITTISampling.py:401-403): pixel (r, c) reads
+  // cell (r + R - H, c) when x0 >= 0 and cell (H - 1 - r, (c - W/2) mod W) when x0 < 0
+  const int HW = a.geo.H * a.geo.W, W = a.geo.W, H = a.geo.H, R = a.geo.R;
+  const float* x0 = a.x + ((size_t)t * 2) * HW;
+  *use_d = (gr >= R - H) && !(x0[(gr - (R - H)) * W + gc] < 0.0f);
+  *use_m = (gr < H) && (x0[(H - 1 - gr) * W + ((gc + W / 2) % W)] < 0.0f);
+}
+
+__device__ __forceinline__ void rearm(const StepArgs& a, size_t cell) {
+  CellRec r;
+  r.zmin = ~0ull; r.zpack = ~0ull; r.sum_d = 0; r.sum_i = 0;
+  a.ws.rec[cell] = r;
+  a.ws.cnt[cell] = 0u;
+}
+
+// Finish one filled cell whose winner (if anybody needs it) is confirmed: outputs, debug output, re-arm.
+__device__ __forceinline__ void finish_cell(const StepArgs& a, int t, int gr, int gc, size_t cell, unsigned cn,
+                                            const CellRec& rec, FusedFast f, long long winner) {
+  const int HW = a.geo.H * a.geo.W;
+  const double min_d = a.want_key ? log_range_of_r2(__longlong_as_double((long long)rec.zmin), a.sigma_mod, a.geo) : 0.0;
+  if (f.far) {
+    const int g = t / a.A, wa = (int)winner / HW, wp = (int)winner - wa * HW;
+    fuse_far(&f, min_d, a.x[((size_t)(g * a.A + wa) * 2 + 1) * HW + wp], a.sigma_mod, a.allowance, a.geo.recip);
+  }
+  bool use_d, use_m;
+  consumers_of(a, t, gr, gc, &use_d, &use_m);
+  write_consumers(a, t, gr, gc, use_d, use_m, f.depth, f.inten, true);
+  if (a.dbg_cnt) a.dbg_cnt[cell] = (int32_t)cn;
+  if (a.dbg_winner) a.dbg_winner[cell] = (int32_t)winner;
+  if (a.dbg_min_d) a.dbg_min_d[cell] = min_d;
+  rearm(a, cell);
+}
+
+// One thread per grid cell.  Pass 1 finishes what needs no winner (empty cells, plain averages) on the spot; cells whose
+// nearest candidate matters (far cells, or every filled cell in the verifying modes) are queued in shared memory and
+// pass 2 works the queue off with every lane busy: verification of the packed winner (one exact projection), the
+// reference's float64 pow / log2 for the far depth.
+__global__ void __launch_bounds__(256) resolve_kernel(StepArgs a) {
+  __shared__ unsigned short s_queue[256];
+  __shared__ unsigned s_n;
+  const int W = a.geo.W, R = a.geo.R;
+  const int t = a.tgt_first + blockIdx.y;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;          // cell of target t
+  if (threadIdx.x == 0) s_n = 0;
+  __syncthreads();
+  if (k < R * W) {
+    const int gr = k / W, gc = k - gr * W;
+    const size_t cell = (size_t)t * R * W + k;
+    const unsigned cn = a.ws.cnt[cell];
+    if (cn == 0) {                                                // empty: the cell is still armed
+      bool use_d, use_m;
+      consumers_of(a, t, gr, gc, &use_d, &use_m);
+      // the reference's arithmetic on an empty cell ends in +0 (-0 after the mirror's sign flip) and intensity 0
+      write_consumers(a, t, gr, gc, use_d, use_m, 0.0, 0.0f, false);
+      if (a.dbg_cnt) a.dbg_cnt[cell] = 0;
+      if (a.dbg_winner) a.dbg_winner[cell] = -1;
+      if (a.dbg_min_d) a.dbg_min_d[cell] = 0.0;
+    } else {
+      const CellRec rec = a.ws.rec[cell];
+      const FusedFast f = fuse_cell_fast(cn, rec.sum_d, rec.sum_i, __longlong_as_double((long long)rec.zmin), a.sigma_mod,
+                                         a.allowance, a.geo);
+      if (a.want_key && (f.far || a.winner_mode >= 1)) s_queue[atomicAdd(&s_n, 1u)] = (unsigned short)threadIdx.x;
+      else finish_cell(a, t, gr, gc, cell, cn, rec, f, -1);
+    }
+  }
+  __syncthreads();
+  const unsigned n = s_n;
+  for (unsigned i = threadIdx.x; i < n; i += blockDim.x) {
+    const int kk = blockIdx.x * blockDim.x + s_queue[i];
+    const int gr = kk / W, gc = kk - gr * W;
+    const size_t cell = (size_t)t * R * W + kk;
+    const unsigned cn = a.ws.cnt[cell];
+    const CellRec rec = a.ws.rec[cell];
+    const FusedFast f = fuse_cell_fast(cn, rec.sum_d, rec.sum_i, __longlong_as_double((long long)rec.zmin), a.sigma_mod,
+                                       a.allowance, a.geo);
+    const unsigned id = (unsigned)(rec.zpack & ((1ull << a.key_shift) - 1ull));
+    const bool confirmed = a.winner_mode != 2 && exact_key_of(a, t, id) == rec.zmin;
+    if (!confirmed) {                                             // leave the cell to the fix pass
+      a.ws.rec[cell].zpack = ~0ull;
+      a.ws.cnt[cell] = cn | kFlagBit;
+      atomicAdd(&a.ws.hdr->flag_count, 1u);
+      continue;
+    }
+    finish_cell(a, t, gr, gc, cell, cn, rec, f, (long long)id);
+  }
+  // the scatter's work counters are free again
+  if (blockIdx.x == 0 && blockIdx.y == 0)
+    for (int i = threadIdx.x; i < a.ws.n_groups; i += blockDim.x) a.ws.work_ctr[i] = 0u;
+}
+
+// After a fix traversal: the last block to finish completes the flagged cells of this call's target range.
+__device__ __forceinline__ void fix_epilogue(const StepArgs& a) {
+  __shared__ unsigned s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned total = gridDim.x * gridDim.y * gridDim.z;
+    s_last = (atomicAdd(&a.ws.hdr->ticket, 1u) == total - 1u) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const size_t grid_cells = (size_t)a.geo.R * a.geo.W;
+  const size_t first = (size_t)a.tgt_first * grid_cells, n = (size_t)a.tgt_count * grid_cells;
+  for (size_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const size_t cell = first + i;
+    const unsigned c = __ldcg(a.ws.cnt + cell);
+    if (!(c & kFlagBit)) continue;
+    const unsigned cn = c & ~kFlagBit;
+    CellRec rec;
+    rec.zmin = __ldcg(&a.ws.rec[cell].zmin);
+    rec.zpack = __ldcg(&a.ws.rec[cell].zpack);
+    rec.sum_d = __ldcg(&a.ws.rec[cell].sum_d);
+    rec.sum_i = __ldcg(&a.ws.rec[cell].sum_i);
+    const int t = (int)(cell / grid_cells), k = (int)(cell - (size_t)t * grid_cells);
+    const FusedFast f = fuse_cell_fast(cn, rec.sum_d, rec.sum_i, __longlong_as_double((long long)rec.zmin), a.sigma_mod,
+                                       a.allowance, a.geo);
+    long long winner = (long long)rec.zpack;
+    if ((unsigned long long)winner >= (unsigned long long)a.A * a.geo.H * a.geo.W) {   // cannot happen: the traversal is
+      printf("sdpc: flagged cell %llu found no candidate at its nearest depth\n", (unsigned long long)cell);  // deterministic
+      winner = 0;
+    }
+    finish_cell(a, t, k / a.geo.W, k % a.geo.W, cell, cn, rec, f, winner);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    a.ws.hdr->flag_count = 0u;
+    a.ws.hdr->ticket = 0u;
+  }
+  for (int i = threadIdx.x; i < a.ws.n_groups; i += blockDim.x) a.ws.work_ctr[a.ws.n_groups + i] = 0u;
+}
+
+__global__ void __launch_bounds__(kTravThreads) fix_winners_kernel(StepArgs a) {
+  if (__ldcg(&a.ws.hdr->flag_count) == 0u) return;                // the usual case: every packed winner was confirmed
+  traverse_items<true>(a, a.ws.work_ctr + a.ws.n_groups);
+  fix_epilogue(a);
+}
+
+__global__ void __launch_bounds__(256) fix_winners_full_kernel(StepArgs a) {
+  __shared__ double s_to[16];
+  __shared__ double s_from[kMaxGroup * 12];
+  __shared__ float s_org[kMaxGroup * 3];
+  if (__ldcg(&a.ws.hdr->flag_count) == 0u) return;
+  traverse_full<true>(a, s_to, s_from, s_org);
+  fix_epilogue(a);
 }
 
 // correction (KITTISampling.py:427-430,490): corr = -(imageMask&sky) * (1-mask) * (x - new);
@@ -518,33 +672,12 @@ correct_kernel(float* __restrict__ x, const float* __restrict__ img, const uint8
   *reinterpret_cast<float4*>(x + e) = o;
 }
 
-// debug dump of the per-cell state (runs before resolve mutates x)
-__global__ void dump_cells_kernel(StepWorkspace ws, int32_t* cnt, int32_t* winner, double* min_d, size_t first, size_t n,
-                                  int cas) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  size_t k = first + i;
-  unsigned cn = ws.cnt[k];
-  if (cnt) cnt[k] = (int32_t)cn;
-  const ulonglong2 kv = (cas && cn) ? ws.zkey[k] : make_ulonglong2(0ull, 0ull);
-  if (winner) winner[k] = cn ? (int32_t)(cas ? (unsigned)kv.x : ws.winner[k]) : -1;
-  if (min_d) min_d[k] = cn ? __longlong_as_double((long long)(cas ? kv.y : ws.zmin[k])) : 0.0;
-}
-
 }  // namespace sdpc
 
 // ------------------------------------------------------------------------------------------
 // C ABI
 // ------------------------------------------------------------------------------------------
 using namespace sdpc;
-
-// The production scatter keeps the exact (depth, source id) minimum with a 128-bit CAS instead of two 64-bit atomicMins
-// + verification pass (measured 152.9 -> 131.3 us per 8-view step, same results bit for bit) unless
-// SDPC_XVIEW_CAS128=0 (read once) or sdpc_step_params.winner_mode = 1 asks for the packed key.
-static bool xview_cas128() {
-  static const bool on = [] { const char* v = getenv("SDPC_XVIEW_CAS128"); return !(v && v[0] == '0'); }();
-  return on;
-}
 
 static int check_params(const sdpc_step_params* p, const sdpc_step_buffers* b) {
   if (!p || !b) return set_error(SDPC_ERR_ARG, "null params/buffers");
@@ -553,32 +686,38 @@ static int check_params(const sdpc_step_params* p, const sdpc_step_buffers* b) {
   if (p->group_size > kMaxGroup) return set_error(SDPC_ERR_ARG, "group_size > 32 not supported");
   if (p->height <= 0 || p->width <= 0 || (p->height * p->width) % 4 != 0)
     return set_error(SDPC_ERR_ARG, "H*W must be a positive multiple of 4");
+  if ((long long)p->group_size * p->height * p->width > (1ll << 30))
+    return set_error(SDPC_ERR_ARG, "group_size*H*W must stay below 2^30 (source ids are packed into the z-buffer key)");
   if (p->tgt_first < 0 || p->tgt_count < 0 || p->tgt_first + p->tgt_count > p->n_views)
     return set_error(SDPC_ERR_ARG, "target range outside [0, n_views)");
   if (!b->x || !b->refer || !b->mask) return set_error(SDPC_ERR_ARG, "x/refer/mask must be non-null");
   return SDPC_OK;
 }
 
-// the 128-bit CAS winner path serves the production scatter (no candidate-level debug output, H*W a multiple of the chunk)
-static bool use_cas128(const sdpc_step_params* p, const sdpc_step_buffers* b) {
+// candidate-level debug output selects the full fp64 scatter; so does an image whose H*W is not a multiple of a work item
+static bool use_full_scatter(const sdpc_step_params* p, const sdpc_step_buffers* b) {
   const bool dbg_candidates = b->dbg_row && b->dbg_col && b->dbg_valid;
-  const bool fast = !dbg_candidates && (p->height * p->width) % kChunk == 0;
-  return fast && (p->winner_mode == 2 || (p->winner_mode == 0 && xview_cas128()));
+  return dbg_candidates || (p->height * p->width) % kSeg != 0;
 }
 
 extern "C" int sdpc_step_kernel_launches(const sdpc_step_params* p, const sdpc_step_buffers* b) {
   if (!p || !b) return set_error(SDPC_ERR_ARG, "null params/buffers");
-  int n = 1;                                                   // update
-  if (p->share) {
-    n += 3;                                                    // scatter, resolve, correct
-    if (!use_cas128(p, b)) n += 2;                             // verification + exact-winner pass (launched, exits at once)
-    if (b->dbg_cnt || b->dbg_winner || b->dbg_min_d) n += 1;   // cell dump
-  }
-  return n;
+  return p->share ? 5 : 1;          // update [+ scatter, resolve, fix (exits at once unless a cell was flagged), correct]
 }
 
 extern "C" size_t sdpc_step_workspace_bytes(int n_views, int height, int width, int big_rows) {
   return workspace_layout(n_views, height, big_rows, width, nullptr, nullptr);
+}
+
+extern "C" int sdpc_step_workspace_init(void* workspace, size_t workspace_bytes, int n_views, int height, int width,
+                                        int big_rows, void* stream) {
+  if (n_views <= 0 || height <= 0 || width <= 0 || big_rows <= 0) return set_error(SDPC_ERR_ARG, "workspace_init: bad shape");
+  StepWorkspace ws;
+  size_t need = workspace_layout(n_views, height, big_rows, width, (char*)workspace, &ws);
+  if (!workspace || workspace_bytes < need) return set_error(SDPC_ERR_WORKSPACE, "step workspace too small");
+  arm_kernel<<<(unsigned)((ws.cells + 255) / 256), 256, 0, (cudaStream_t)stream>>>(ws);
+  SDPC_CUDA(cudaGetLastError());
+  return SDPC_OK;
 }
 
 extern "C" int sdpc_langevin_update(const sdpc_step_params* p, const sdpc_step_buffers* b, void* workspace,
@@ -588,13 +727,13 @@ extern "C" int sdpc_langevin_update(const sdpc_step_params* p, const sdpc_step_b
   StepWorkspace ws;
   size_t need = workspace_layout(p->n_views, p->height, p->big_rows, p->width, (char*)workspace, &ws);
   if (!workspace || workspace_bytes < need) return set_error(SDPC_ERR_WORKSPACE, "step workspace too small");
-  SDPC_CUDA(cudaMemsetAsync(ws.max_bits, 0, sizeof(unsigned), stream));
+  SDPC_CUDA(cudaMemsetAsync(&ws.hdr->max_bits, 0, sizeof(unsigned), stream));
   const int HW = p->height * p->width;
   const int tcount = p->tgt_count ? p->tgt_count : p->n_views;
   long long n_vec = (long long)tcount * 2 * HW / 4;
   int blocks = (int)((n_vec + 255) / 256);
   langevin_update_kernel<<<blocks, 256, 0, stream>>>(b->x, b->grad, b->noise, b->refer, b->mask, b->grad_likelihood,
-                                                     ws.max_bits, HW, p->tgt_first, n_vec, p->step_size, p->grad_ref,
+                                                     &ws.hdr->max_bits, HW, p->tgt_first, n_vec, p->step_size, p->grad_ref,
                                                      p->noise_scale, p->nan_to_num);
   SDPC_CUDA(cudaGetLastError());
   return SDPC_OK;
@@ -622,81 +761,66 @@ extern "C" int sdpc_crossview_share(const sdpc_step_params* p, const sdpc_step_b
     return set_error(SDPC_ERR_ARG, "share: pose variant needs to_world/from_world");
   if (p->variant == SDPC_VARIANT_TRANSLATION && !b->origins)
     return set_error(SDPC_ERR_ARG, "share: translation variant needs origins");
+  if (p->winner_mode < 0 || p->winner_mode > 2) return set_error(SDPC_ERR_ARG, "winner_mode must be 0, 1 or 2");
   cudaStream_t stream = (cudaStream_t)stream_;
   StepWorkspace ws;
   size_t need = workspace_layout(p->n_views, p->height, p->big_rows, p->width, (char*)workspace, &ws);
   if (!workspace || workspace_bytes < need) return set_error(SDPC_ERR_WORKSPACE, "step workspace too small");
   const int HW = p->height * p->width;
   const int tcount = p->tgt_count ? p->tgt_count : p->n_views;
-  const size_t grid_cells = (size_t)p->big_rows * p->width;
-  const size_t first = (size_t)p->tgt_first * grid_cells, n = (size_t)tcount * grid_cells;
-  const bool dbg_candidates = b->dbg_row && b->dbg_col && b->dbg_valid;
-  const bool fast = !dbg_candidates && HW % kChunk == 0;     // candidate-level debug output: legacy full kernel
-  const bool cas = use_cas128(p, b);
-  // empty z-buffer: 0xFF.. keys / winners, zero sums and counts (only the target views' grids)
-  if (cas) {
-    SDPC_CUDA(cudaMemsetAsync(ws.zkey + first, 0xFF, n * 16, stream));
-  } else {
-    SDPC_CUDA(cudaMemsetAsync(ws.zmin + first, 0xFF, n * 8, stream));
-    SDPC_CUDA(cudaMemsetAsync(ws.winner + first, 0xFF, n * 4, stream));
-    SDPC_CUDA(cudaMemsetAsync(ws.zpack + first, 0xFF, n * 8, stream));
-    SDPC_CUDA(cudaMemsetAsync(ws.flag, 0, sizeof(unsigned), stream));
-  }
-  SDPC_CUDA(cudaMemsetAsync(ws.sum_d + first, 0, n * 8, stream));
-  SDPC_CUDA(cudaMemsetAsync(ws.sum_i + first, 0, n * 8, stream));
-  SDPC_CUDA(cudaMemsetAsync(ws.cnt + first, 0, n * 4, stream));
+  const bool dbg_cells = b->dbg_cnt || b->dbg_winner || b->dbg_min_d;
 
-  ScatterArgs sa;
-  sa.x = b->x; sa.sky = b->sky; sa.exist = b->exist;
-  sa.to_world = b->to_world; sa.from_world = b->from_world; sa.origins = b->origins;
-  sa.cos_az = b->cos_az; sa.sin_az = b->sin_az; sa.cos_el = b->cos_el; sa.sin_el = b->sin_el;
-  sa.dbg_row = dbg_candidates ? b->dbg_row : nullptr;
-  sa.dbg_col = b->dbg_col; sa.dbg_valid = b->dbg_valid;
-  sa.ws = ws;
-  sa.geo.h_min = p->h_min; sa.geo.dh = p->dh; sa.geo.big_row_min = p->big_row_min; sa.geo.dv = p->dv;
-  sa.geo.H = p->height; sa.geo.W = p->width; sa.geo.R = p->big_rows;
-  sa.geo.recip = p->scalar_div_recip ? 1 : 0;
-  sa.A = p->group_size; sa.variant = p->variant; sa.sky_filter = p->sky_filter;
-  sa.tgt_first = p->tgt_first; sa.tgt_count = tcount;
-  sa.sigma_mod = p->sigma_mod; sa.min_depth_thr = p->min_depth_thr;
-  sa.key_shift = 1;
-  while ((1 << sa.key_shift) < p->group_size * HW) ++sa.key_shift;
-  if (p->key_shift_override > sa.key_shift && p->key_shift_override < 52) sa.key_shift = p->key_shift_override;
-  dim3 grid((HW + 255) / 256, p->group_size, p->n_views / p->group_size);
-  if (fast) {
-    dim3 fgrid(HW / kChunk, p->group_size, p->n_views / p->group_size);
-    if (cas) scatter_fast_kernel<true><<<fgrid, 256, 0, stream>>>(sa);
-    else scatter_fast_kernel<false><<<fgrid, 256, 0, stream>>>(sa);
+  StepArgs a;
+  a.x = b->x; a.mask = b->mask; a.sky = b->sky; a.exist = b->exist;
+  a.to_world = b->to_world; a.from_world = b->from_world; a.origins = b->origins;
+  a.cos_az = b->cos_az; a.sin_az = b->sin_az; a.cos_el = b->cos_el; a.sin_el = b->sin_el;
+  a.img = b->new_images ? b->new_images : ws.shared_img;
+  const bool full = use_full_scatter(p, b);
+  a.dbg_row = (b->dbg_row && b->dbg_col && b->dbg_valid) ? b->dbg_row : nullptr;
+  a.dbg_col = b->dbg_col; a.dbg_valid = b->dbg_valid;
+  a.dbg_cnt = b->dbg_cnt; a.dbg_winner = b->dbg_winner; a.dbg_min_d = b->dbg_min_d;
+  a.ws = ws;
+  a.geo = make_geo(p->h_min, p->dh, p->big_row_min, p->dv, p->height, p->width, p->big_rows, p->scalar_div_recip);
+  a.A = p->group_size; a.variant = p->variant; a.sky_filter = p->sky_filter;
+  a.tgt_first = p->tgt_first; a.tgt_count = tcount;
+  a.sigma_mod = p->sigma_mod; a.min_depth_thr = p->min_depth_thr; a.allowance = p->allowance;
+  a.key_shift = 1;
+  while ((1 << a.key_shift) < p->group_size * HW) ++a.key_shift;
+  if (p->key_shift_override > a.key_shift && p->key_shift_override < 52) a.key_shift = p->key_shift_override;
+  a.want_key = (p->allowance >= 0.0 || dbg_cells) ? 1 : 0;
+  a.winner_mode = p->winner_mode;
+  if (dbg_cells && a.winner_mode == 0) a.winner_mode = 1;        // the debug output names every cell's winner
+  a.ws.n_groups = p->n_views / p->group_size;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  // persistent traversal: blocks per group so that the whole grid is about two blocks per SM
+  const int per_group = std::max(1, std::min((HW / kSeg * p->group_size + kTravWarps - 1) / kTravWarps,
+                                             (2 * sms + a.ws.n_groups - 1) / a.ws.n_groups));
+  const dim3 sgrid(per_group, a.ws.n_groups);
+  if (full) {
+    const dim3 grid((HW + 255) / 256, p->group_size, p->n_views / p->group_size);
+    scatter_full_kernel<<<grid, 256, 0, stream>>>(a);
   } else {
-    scatter_kernel<0><<<grid, 256, 0, stream>>>(sa);
+    scatter_fast_kernel<<<sgrid, kTravThreads, 0, stream>>>(a);
   }
   SDPC_CUDA(cudaGetLastError());
-  if (!cas) {
-    verify_winner_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(sa);
-    SDPC_CUDA(cudaGetLastError());
-    scatter_kernel<1><<<grid, 256, 0, stream>>>(sa);            // exits immediately unless a winner was unconfirmed
-    SDPC_CUDA(cudaGetLastError());
-  }
-  if (b->dbg_cnt || b->dbg_winner || b->dbg_min_d) {
-    dump_cells_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(ws, b->dbg_cnt, b->dbg_winner, b->dbg_min_d, first, n,
-                                                                      cas ? 1 : 0);
-    SDPC_CUDA(cudaGetLastError());
-  }
-  ResolveArgs ra;
-  ra.x = b->x; ra.mask = b->mask; ra.sky = b->sky; ra.exist = b->exist;
-  ra.img = b->new_images ? b->new_images : ws.shared_img;
-  ra.new_images = b->new_images; ra.too_high_out = b->too_high;
-  ra.dbg_cnt = b->dbg_cnt; ra.dbg_winner = b->dbg_winner; ra.dbg_min_d = b->dbg_min_d;
-  ra.ws = ws; ra.geo = sa.geo; ra.A = p->group_size; ra.tgt_first = p->tgt_first; ra.tgt_count = tcount;
-  ra.cas = cas ? 1 : 0;
-  ra.sigma_mod = p->sigma_mod; ra.corr_coef = p->corr_coef; ra.allowance = p->allowance;
-  dim3 rgrid((HW + 255) / 256, tcount);
-  resolve_kernel<<<rgrid, 256, 0, stream>>>(ra);
+  const dim3 rgrid((unsigned)((p->big_rows * p->width + 255) / 256), tcount);
+  resolve_kernel<<<rgrid, 256, 0, stream>>>(a);
   SDPC_CUDA(cudaGetLastError());
+  if (a.want_key) {
+    if (HW % kSeg == 0) {
+      fix_winners_kernel<<<sgrid, kTravThreads, 0, stream>>>(a);
+    } else {
+      const dim3 grid((HW + 255) / 256, p->group_size, p->n_views / p->group_size);
+      fix_winners_full_kernel<<<grid, 256, 0, stream>>>(a);
+    }
+    SDPC_CUDA(cudaGetLastError());
+  }
   long long n_vec = (long long)tcount * 2 * HW / 4;
-  correct_kernel<<<(unsigned)((n_vec + 255) / 256), 256, 0, stream>>>(b->x, ra.img, ws.shared_mask, b->mask, ws.max_bits,
+  correct_kernel<<<(unsigned)((n_vec + 255) / 256), 256, 0, stream>>>(b->x, a.img, ws.shared_mask, b->mask, &ws.hdr->max_bits,
                                                                      b->too_high, HW, p->tgt_first, n_vec,
-                                                                     p->sigma_mod, p->corr_coef, sa.geo.recip);
+                                                                     p->sigma_mod, p->corr_coef, a.geo.recip);
   SDPC_CUDA(cudaGetLastError());
   return SDPC_OK;
 }
@@ -708,16 +832,23 @@ extern "C" int sdpc_langevin_reproject_step(const sdpc_step_params* p, const sdp
   return SDPC_OK;
 }
 
-extern "C" int sdpc_langevin_reproject_step_host(const sdpc_step_params* p, const sdpc_step_buffers* b, float* x_host,
-                                                 const float* grad_host, const float* noise_host,
-                                                 float* new_images_host, void* workspace, size_t workspace_bytes,
-                                                 void* stream_) {
+extern "C" int sdpc_langevin_reproject_step_host(const sdpc_step_params* p, const sdpc_step_buffers* b,
+                                                 sdpc_score_t* score, const int64_t* labels, void* score_workspace,
+                                                 size_t score_workspace_bytes, float* x_host, const float* grad_host,
+                                                 const float* noise_host, float* new_images_host, void* workspace,
+                                                 size_t workspace_bytes, void* stream_) {
   if (int e = check_params(p, b)) return e;
   if (!x_host) return set_error(SDPC_ERR_ARG, "x_host is null");
+  if (score && (!labels || !b->grad)) return set_error(SDPC_ERR_ARG, "score given: labels and b->grad (device) must be non-null");
+  if (score && grad_host) return set_error(SDPC_ERR_ARG, "pass either a score handle or grad_host, not both");
   cudaStream_t stream = (cudaStream_t)stream_;
   const size_t bytes = (size_t)p->n_views * 2 * p->height * p->width * sizeof(float);
   SDPC_CUDA(cudaMemcpyAsync(b->x, x_host, bytes, cudaMemcpyHostToDevice, stream));
-  if (grad_host) {
+  if (score) {
+    if (int e = sdpc_score_forward(score, b->x, labels, (float*)b->grad, p->n_views, score_workspace, score_workspace_bytes,
+                                   stream_))
+      return e;
+  } else if (grad_host) {
     if (!b->grad) return set_error(SDPC_ERR_ARG, "grad_host given but b->grad (device staging) is null");
     SDPC_CUDA(cudaMemcpyAsync((void*)b->grad, grad_host, bytes, cudaMemcpyHostToDevice, stream));
   }

@@ -177,6 +177,18 @@ class NCSN_LiDAR_small(nn.Module):
                                                    st["ws"].numel(), stream), "sdpc_score_forward")
         return out
 
+    def handle_and_workspace(self, B, H, W, device):
+        """(handle, workspace pointer, workspace bytes) for a forward of B views on `device`: what a C-ABI caller hands
+        to sdpc_score_forward / sdpc_langevin_reproject_step_host.  Uploads the weights if they changed."""
+        probe = torch.empty(B, self.channels, H, W, device=device)
+        with torch.cuda.device(probe.device):
+            lib, st = self._state(probe)
+            if st["ws"] is None or st["ws_views"] != B:
+                nbytes = lib.sdpc_score_workspace_bytes(st["handle"], B)
+                st["ws"] = torch.empty(int(nbytes), dtype=torch.uint8, device=probe.device)
+                st["ws_views"] = B
+        return st["handle"], C.c_void_p(st["ws"].data_ptr()), st["ws"].numel()
+
     # ------------------------------------------------------------------------------ introspection
     def read_tap(self, name, x):
         """Test hook (needs SDPC_KEEP_TAPS=1 at handle creation): named intermediate as NCHW fp32."""

@@ -45,10 +45,22 @@ class StepRunner:
         self.geo = sensor_geometry(H, W, device)
         self.variant = variant
         f32 = dict(device=device, dtype=torch.float32)
-        self.refer = refer.to(**f32).contiguous()
-        self.mask = mask.to(device=device, dtype=torch.int32).contiguous()
+        # The kernels index refer / mask as dense [B,2,H,W] buffers (float4 / int4 loads) and sky / exist as dense byte
+        # planes: broadcastable inputs (the reference's `-mask*(x-refer)` accepts e.g. a [B,1,H,W] mask) are expanded
+        # here, anything that cannot broadcast to the sample's shape is rejected before a device pointer is formed.
+        self.refer = self._expand(refer, x_shape, "refer_image").to(**f32).contiguous()
+        self.mask = self._expand(mask, x_shape, "refer_mask").to(device=device, dtype=torch.int32).contiguous()
+        if sky is not None and sky.numel() != B * H * W:
+            raise ValueError(f"sky has {sky.numel()} elements, expected B*H*W = {B * H * W} ([B,1,H,W])")
+        if exist is not None and tuple(exist.shape[1:]) != (H, W):
+            raise ValueError(f"existMask is {tuple(exist.shape)}, expected [>={group_size},{H},{W}]")
         self.sky = sky.to(device=device).reshape(B, H, W).to(torch.uint8).contiguous() if sky is not None else None
         self.exist = exist[:group_size].to(device=device).to(torch.uint8).contiguous() if exist is not None else None
+        for name, t in (("toWorld", to_world), ("fromWorld", from_world)):
+            if t is not None and t.numel() != B * 16:
+                raise ValueError(f"{name} has {t.numel()} elements, expected B*16 = {B * 16} ([B,1,4,4])")
+        if origins is not None and (origins.dim() != 4 or origins.shape[0] < group_size or origins.shape[1] != 3):
+            raise ValueError(f"originList is {tuple(origins.shape)}, expected [>={group_size},3,1,1]")
         self.to_world = to_world.to(device=device, dtype=torch.float64).reshape(B, 16).contiguous() if to_world is not None else None
         self.from_world = from_world.to(device=device, dtype=torch.float64).reshape(B, 16).contiguous() if from_world is not None else None
         self.origins = origins[:group_size, :, 0, 0].to(**f32).contiguous() if origins is not None else None
@@ -58,12 +70,16 @@ class StepRunner:
         self.scalar_div_recip = (torch.device(device).type == "cuda") if scalar_div_recip is None else bool(scalar_div_recip)
         nbytes = 256 if self.lib is None else self._ws_bytes()
         self.workspace = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        init = getattr(self.lib, "sdpc_step_workspace_init", None)
+        if init is not None:                # arm the z-buffers once: every share call re-arms what it used (no per-step memset)
+            cabi.check(self.lib, init(_ptr(self.workspace), nbytes, B, H, W, self.geo.R, self._stream()),
+                       "sdpc_step_workspace_init")
         self.too_high = torch.zeros(1, dtype=torch.int32, device=device)
         # debug=True: candidate-level (row/col/valid, selects the legacy full scatter kernel) + cell-level dumps;
         # debug="cells": only the per-cell dumps, so the production (compacted, fp32-guarded) scatter runs
         self.debug = None
         self.key_shift_override = 0
-        self.winner_mode = 0          # sdpc_step_params.winner_mode: 0 library default, 1 packed key + verify, 2 128-bit CAS
+        self.winner_mode = 0          # sdpc_step_params.winner_mode: 0 verify where it matters, 1 verify all, 2 exact traversal
         if debug:
             R = self.geo.R
             i32 = dict(device=device, dtype=torch.int32)
@@ -72,6 +88,13 @@ class StepRunner:
             if debug != "cells":
                 self.debug.update(row=torch.zeros(B, group_size * H * W, **i32), col=torch.zeros(B, group_size * H * W, **i32),
                                   valid=torch.zeros(B, group_size * H * W, device=device, dtype=torch.uint8))
+
+    @staticmethod
+    def _expand(t, shape, name):
+        try:
+            return t.expand(shape)
+        except RuntimeError:
+            raise ValueError(f"{name} of shape {tuple(t.shape)} does not broadcast to the sample's {tuple(shape)}") from None
 
     def _ws_bytes(self):
         fn = getattr(self.lib, "sdpc_step_workspace_bytes", None)
@@ -119,6 +142,19 @@ class StepRunner:
         st = self.lib.sdpc_langevin_reproject_step(C.byref(p), C.byref(b), _ptr(self.workspace),
                                                    self.workspace.numel(), self._stream())
         cabi.check(self.lib, st, "sdpc_langevin_reproject_step")
+
+    def step_host(self, p, b, x_host, new_images_host=None, scorenet=None, labels=None, grad_host=None, noise_host=None):
+        """The whole step on HOST sample buffers (sdpc_langevin_reproject_step_host): x_host -> b.x, score forward of
+        `scorenet` (an sdpc_b200 NCSN_LiDAR_small) into b.grad, update (+ share), b.x -> x_host, newImages -> host.
+        Everything is enqueued on the current stream; the caller synchronises before reading the host buffers."""
+        handle = ws = None
+        ws_bytes = 0
+        if scorenet is not None:
+            handle, ws, ws_bytes = scorenet.handle_and_workspace(self.B, self.H, self.W, self.device)
+        st = self.lib.sdpc_langevin_reproject_step_host(
+            C.byref(p), C.byref(b), handle, _ptr(labels), ws, ws_bytes, _ptr(x_host), _ptr(grad_host), _ptr(noise_host),
+            _ptr(new_images_host), _ptr(self.workspace), self.workspace.numel(), self._stream())
+        cabi.check(self.lib, st, "sdpc_langevin_reproject_step_host")
 
     def kernel_launches(self, p, b):
         """kernels one step() call with these parameters launches (bench.py's gpu_launches)."""

@@ -14,6 +14,7 @@ using namespace sdpc;
 // The emulation exports the product library's entry-point names (host pointers instead of device
 // pointers, `stream` ignored) so that StepRunner / ViewShard can be driven unchanged in CPU tests.
 extern "C" size_t sdpc_step_workspace_bytes(int, int, int, int) { return 256; }
+extern "C" int sdpc_step_workspace_init(void*, size_t, int, int, int, int, void*) { return 0; }
 extern "C" const char* sdpc_last_error(void) { return "host emulation"; }
 
 extern "C" int sdpc_langevin_update(const sdpc_step_params* p, const sdpc_step_buffers* b, void* workspace, size_t,
@@ -55,11 +56,13 @@ extern "C" int sdpc_crossview_share(const sdpc_step_params* p, const sdpc_step_b
   const int HW = H * W;
   const int t0 = p->tgt_first, tn = p->tgt_count ? p->tgt_count : B;
   const float mx = *(float*)workspace;
-  GeoConsts geo{p->h_min, p->dh, p->big_row_min, p->dv, H, W, R, p->scalar_div_recip ? 1 : 0};
+  const GeoConsts geo = make_geo(p->h_min, p->dh, p->big_row_min, p->dv, H, W, R, p->scalar_div_recip ? 1 : 0);
   const size_t cells = (size_t)B * R * W;
   std::vector<unsigned long long> zmin(cells, ~0ull);
   std::vector<unsigned> winner(cells, ~0u), cnt(cells, 0u);
   std::vector<long long> sum_d(cells, 0), sum_i(cells, 0);
+  std::vector<double> r2min(cells, std::numeric_limits<double>::infinity());
+  static const double log2_tab[SDPC_LOG2_TABLE_DOUBLES] = {SDPC_LOG2_TABLE};
   long long fast_mismatch = 0;
   for (int pass = 0; pass < 2; ++pass)
     for (int g = 0; g < B / A; ++g)
@@ -95,9 +98,15 @@ extern "C" int sdpc_crossview_share(const sdpc_step_params* p, const sdpc_step_b
               qz = wz - (double)b->origins[ta * 3 + 2];
             }
             Candidate cd = reproject(qx, qy, qz, p->sigma_mod, geo);
-            {   // the guarded fp32 fast path of the production kernel must give the identical candidate
-              Candidate cf = reproject_fast(qx, qy, qz, p->sigma_mod, geo);
-              if (cf.row != cd.row || cf.col != cd.col || memcmp(&cf.nd, &cd.nd, 8) != 0) ++fast_mismatch;
+            {   // the guarded fp32 estimates of the production kernel must give the identical candidate
+              int frow, fcol;
+              const bool fok = pixel_fast(qx, qy, qz, geo, &frow, &fcol);
+              const double r2 = range2(qx, qy, qz);
+              const double fnd = log_range_of_r2(r2, p->sigma_mod, geo);            // what resolve evaluates per cell
+              const double tnd = fast_log_range_of_r2(r2, p->sigma_mod, geo, log2_tab);   // what the depth sum takes
+              if (fok != in_grid(cd, geo) || (fok && (frow != cd.row || fcol != cd.col)) || memcmp(&fnd, &cd.nd, 8) != 0 ||
+                  !(fabs(tnd - cd.nd) <= 8e-15 * (1.0 + cd.nd)))
+                ++fast_mismatch;
             }
             bool ok = src_ok && in_grid(cd, geo);
             if (p->min_depth_thr >= 0.0f) ok = ok && cd.nd > (double)p->min_depth_thr;
@@ -111,6 +120,7 @@ extern "C" int sdpc_crossview_share(const sdpc_step_params* p, const sdpc_step_b
             memcpy(&key, &cd.nd, 8);
             if (pass == 0) {
               zmin[cell] = std::min(zmin[cell], key);
+              r2min[cell] = std::min(r2min[cell], range2(qx, qy, qz));
               cnt[cell]++;
               sum_d[cell] += depth_to_fixed(cd.nd);
               sum_i[cell] += inten_to_fixed(x1);
@@ -144,6 +154,17 @@ extern "C" int sdpc_crossview_share(const sdpc_step_params* p, const sdpc_step_b
         min_i = b->x[((size_t)((t / A) * A + wa) * 2 + 1) * HW + wp];
       }
       Fused f = fuse_cell(cnt[cell], sum_d[cell], sum_i[cell], min_d, min_i, p->sigma_mod, p->allowance, geo.recip);
+      {   // the production fusion (guarded float32 far test, no pow/log2 round trip) must take the same decision and
+          // land within one float32 ulp of the reference arithmetic
+        FusedFast ff = fuse_cell_fast(cnt[cell], sum_d[cell], sum_i[cell], cnt[cell] ? r2min[cell] : 0.0, p->sigma_mod,
+                                      p->allowance, geo);
+        // the nearest log-range is a function of the smallest squared range, bit for bit
+        if (cnt[cell]) { const double md = log_range_of_r2(r2min[cell], p->sigma_mod, geo); if (memcmp(&md, &min_d, 8) != 0) ++fast_mismatch; }
+        if (ff.far) fuse_far(&ff, min_d, min_i, p->sigma_mod, p->allowance, geo.recip);
+        const float a32 = (float)ff.depth, b32 = (float)f.depth;
+        const float tol = fabsf(b32) * 1.2e-7f;
+        if (fabsf(a32 - b32) > tol || ff.inten != f.inten) ++fast_mismatch;
+      }
       img[i0] = (float)(neg ? f.depth * -1.0 : f.depth);
       img[i1] = f.inten;
       sm[(size_t)t * HW + q] = f.filled && b->exist[q] && b->sky[(size_t)t * HW + q];

@@ -49,7 +49,7 @@ def _oracle(kind, case, sigma, setting, dev):
 def _cuda_step(kind, case, sigma, setting, recip=None, debug=True, key_shift=0, winner_mode=0):
     run = _runner(kind, case, scalar_div_recip=recip, debug=debug)
     run.key_shift_override = key_shift
-    run.winner_mode = winner_mode          # 0 library default (128-bit CAS), 1 packed key + verification, 2 128-bit CAS
+    run.winner_mode = winner_mode          # 0 verify the packed winner where it matters, 1 verify all, 2 exact traversal
     sm = sigma if sigma > 1 else 1
     if kind == "pose":
         p = run.params(0.0, 0.0, 0.0, case["coef"], sm, True, setting == 5, 10.0, False)
@@ -234,9 +234,10 @@ def test_samplers_vs_reference_goldens():
 
 @pytest.mark.parametrize("kind,sigma,setting", CASES)
 def test_production_scatter_equals_full_kernel(kind, sigma, setting):
-    """the compacted / fp32-guarded scatter (production path) with either winner mechanism - the 128-bit CAS on
-    {log-range, source id} (default) and the packed 64-bit key + verification pass - against the full fp64 two-pass
-    kernels (selected by candidate-level debug output): every per-cell result must be bit-identical."""
+    """the compacted scatter with guarded fp32 pixel estimates (production path) in each winner mode - packed winners
+    verified where they matter / everywhere / every winner from the exact second traversal - against the full fp64
+    scatter (selected by candidate-level debug output): every per-cell result must be bit-identical; so must the run
+    without any debug output (winner mode 0 proper: only "far" cells are verified)."""
     case = cases.small_multiview(kind)
     x_a, ni_a, run_a = _cuda_step(kind, case, sigma, setting, debug=True)
     for mode in (0, 1, 2):
@@ -244,12 +245,35 @@ def test_production_scatter_equals_full_kernel(kind, sigma, setting):
         for k in ("cnt", "winner", "min_d"):
             assert torch.equal(run_a.debug[k], run_b.debug[k]), (k, mode)
         assert torch.equal(ni_a, ni_b) and torch.equal(x_a, x_b), mode
+    x_p, ni_p, _ = _cuda_step(kind, case, sigma, setting, debug=False)
+    assert torch.equal(ni_a, ni_p) and torch.equal(x_a, x_p)
     # truncating 44 more bits of the log-range in the packed key makes most packed winners wrong: the verification
-    # must catch them and the exact winner pass must restore the same result
-    x_c, ni_c, run_c = _cuda_step(kind, case, sigma, setting, debug="cells", key_shift=50, winner_mode=1)
-    for k in ("cnt", "winner", "min_d"):
-        assert torch.equal(run_a.debug[k], run_c.debug[k]), k
-    assert torch.equal(ni_a, ni_c) and torch.equal(x_a, x_c)
+    # must catch them and the fix pass (exact traversal for the flagged cells) must restore the same result
+    for dbg in ("cells", False):
+        x_c, ni_c, run_c = _cuda_step(kind, case, sigma, setting, debug=dbg, key_shift=50, winner_mode=0 if dbg is False else 1)
+        if dbg:
+            for k in ("cnt", "winner", "min_d"):
+                assert torch.equal(run_a.debug[k], run_c.debug[k]), k
+        assert torch.equal(ni_a, ni_c) and torch.equal(x_a, x_c)
+
+
+def test_z_buffers_are_rearmed_by_every_call():
+    """no per-step memset: resolve (and the fix pass) leave every cell empty again - many steps on ONE workspace, with
+    changing inputs and with flagged cells, must equal fresh-workspace runs; an un-armed workspace is rejected loudly"""
+    case = cases.small_multiview("pose")
+    run = _runner("pose", case, debug=False)
+    p = run.params(0.0, 0.0, 0.0, case["coef"], 1, True, True, 10.0, False)
+    g = torch.Generator().manual_seed(5)
+    for i in range(6):
+        c2 = dict(case)
+        c2["x"] = case["x"] + 0.02 * i * torch.randn(case["x"].shape, generator=g)
+        run.key_shift_override = 50 if i % 2 else 0
+        p = run.params(0.0, 0.0, 0.0, case["coef"], 1, True, True, 10.0, False)
+        x = c2["x"].to(DEV).clone()
+        ni = torch.zeros_like(x)
+        run.step(p, run.buffers(x, None, None, new_images=ni))
+        x_f, ni_f, _ = _cuda_step("pose", c2, 0.3, 5, debug=False)
+        assert torch.equal(ni, ni_f) and torch.equal(x, x_f), i
 
 
 def test_production_scatter_full_size():
@@ -260,3 +284,5 @@ def test_production_scatter_full_size():
         for k in ("cnt", "winner", "min_d"):
             assert torch.equal(run_a.debug[k], run_b.debug[k]), (k, mode)
         assert torch.equal(ni_a, ni_b) and torch.equal(x_a, x_b), mode
+    x_p, ni_p, _ = _cuda_step("pose", case, 0.3, 5, debug=False)
+    assert torch.equal(ni_a, ni_p) and torch.equal(x_a, x_p)
