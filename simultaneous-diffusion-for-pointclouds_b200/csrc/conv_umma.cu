@@ -45,9 +45,14 @@ template <int N_TILE, int CG = 1>
 struct UmmaCfg {
   static constexpr int kBBytes = N_TILE / CG * kRowBytes;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = kSmemBudget / kStageBytes;          // 4 (N=256) / 6 (N=128, or N=256 split over a CTA pair)
+  // CTA pairs are swapped-operand kernels: their epilogue never touches the transposing staging area, so its 32 KB hold a
+  // seventh 32 KB stage instead (7 x 32 KB + 1 KB + 256 B = 225.25 KB, the size the other variants already use)
+  static constexpr int kStages = CG == 2 ? 7 : kSmemBudget / kStageBytes;   // 4 (N=256) / 6 (N=128) / 7 (N=256 split over a CTA pair)
   static constexpr int kTmemCols = 2 * N_TILE;                       // 512 / 256
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + kBarrierBytes + kEpiWarps * kStgFloats * 4;
+  static constexpr int kStgBytes = CG == 2 ? 0 : kEpiWarps * kStgFloats * 4;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + kBarrierBytes + kStgBytes;
+  static_assert(kSmemBytes <= 227 * 1024, "dynamic shared memory of one CTA");
+  static_assert((2 * kStages + 4) * 8 + 4 <= kBarrierBytes, "barrier block");
 };
 
 // SWAP = false: D[pixel (M=128), cout (N=Cout)]      = X_tile . W^T      (Cout = 256 layers)
@@ -73,7 +78,8 @@ template <typename T, int N_TILE, bool SWAP, int COUT, bool CL, int CG = 1>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_a_lo, const __grid_constant__ CUtensorMap tmap_b_lo,
-                 const __grid_constant__ CUtensorMap tmap_half, const ConvGeom g, const EpiParams e) {
+                 const __grid_constant__ CUtensorMap tmap_half, const __grid_constant__ CUtensorMap tmap_half_lo,
+                 const ConvGeom g, const EpiParams e) {
   static_assert(!CL || SWAP, "clusters are implemented for the swapped-operand variant");
   static_assert(CG == 1 || (CG == 2 && CL && COUT == 2 * kTileM), "CTA pairs: the two 128-channel halves of a Cout = 256 layer");
   using Cfg = UmmaCfg<N_TILE, CG>;
@@ -100,6 +106,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     prefetch_tmap(&tmap_b);
     if (g.passes > 1) { prefetch_tmap(&tmap_a_lo); prefetch_tmap(&tmap_b_lo); }
     if (CL) prefetch_tmap(&tmap_half);
+    if (CL && g.passes > 1) prefetch_tmap(&tmap_half_lo);
     for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, (CL && CG == 1) ? 2 : 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, CG * kEpiWarps); }
     fence_barrier_init();
@@ -139,6 +146,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         for (int pass = 0; pass < g.passes; ++pass) {
           const CUtensorMap* ma = pass == 2 ? &tmap_a_lo : &tmap_a;
           const CUtensorMap* mb = pass == 1 ? &tmap_b_lo : &tmap_b;
+          // half box of the operand the pair shares: the activations (lo plane in pass 2) for the two channel halves of
+          // a Cout = 256 layer, the weights (lo plane in pass 1) for two pixel tiles of a Cout = 128 layer
+          const CUtensorMap* mhalf = (pass == (kMH == 2 ? 2 : 1)) ? &tmap_half_lo : &tmap_half;
           for (int tap = 0; tap < g.taps; ++tap) {
             const int dy = (g.taps == 9) ? (tap / 3 - 1) * g.dil : 0;
             const int dx = (g.taps == 9) ? (tap % 3 - 1) * g.dil : 0;
@@ -152,7 +162,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 const uint32_t lead_full = mapa_u32(full_bar + stage, 0);
                 tma_load_3d_cg2(sa, mb, lead_full, kc * kBK, mh * kTileM, tap);
                 const int hw = g.BH >= 2 ? 0 : (int)crank * (g.BW / 2), hh = g.BH >= 2 ? (int)crank * (g.BH / 2) : 0;
-                tma_load_4d_cg2(sb, &tmap_half, lead_full, kc * kBK, w0 + hw + g.in_pad + dx, h0 + hh + g.in_pad + dy, n);
+                tma_load_4d_cg2(sb, mhalf, lead_full, kc * kBK, w0 + hw + g.in_pad + dx, h0 + hh + g.in_pad + dy, n);
               } else if constexpr (!CL) {
                 // activations and weights land in the M-side (128 rows) or N-side (N_TILE rows) slot
                 mbar_arrive_expect_tx(full_bar + stage, Cfg::kStageBytes);
@@ -163,13 +173,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 mbar_arrive_expect_tx(full_bar + stage, Cfg::kStageBytes);
                 tma_load_3d(sa, mb, full_bar + stage, kc * kBK, mh * kTileM, tap);
                 const int hw = g.BH >= 2 ? 0 : (int)crank * (g.BW / 2), hh = g.BH >= 2 ? (int)crank * (g.BH / 2) : 0;
-                tma_load_4d_mc(sb + crank * (N_TILE / 2) * kRowBytes, &tmap_half, full_bar + stage, kc * kBK,
+                tma_load_4d_mc(sb + crank * (N_TILE / 2) * kRowBytes, mhalf, full_bar + stage, kc * kBK,
                                w0 + hw + g.in_pad + dx, h0 + hh + g.in_pad + dy, n, (uint16_t)3);
               } else {
                 // own activation tile; rows [64 r, 64 r + 64) of the shared weights, multicast to both CTAs
                 mbar_arrive_expect_tx(full_bar + stage, Cfg::kStageBytes);
                 tma_load_4d(sb, ma, full_bar + stage, kc * kBK, w0 + g.in_pad + dx, h0 + g.in_pad + dy, n);
-                tma_load_3d_mc(sa + crank * (kTileM / 2) * kRowBytes, &tmap_half, full_bar + stage, kc * kBK,
+                tma_load_3d_mc(sa + crank * (kTileM / 2) * kRowBytes, mhalf, full_bar + stage, kc * kBK,
                                (int)crank * (kTileM / 2), tap, (uint16_t)3);
               }
               if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
@@ -574,7 +584,7 @@ static int launch_t(const UmmaConvLaunch& L, cudaStream_t stream) {
   }
   if (!CL) {
     int grid = L.geom.num_tiles < L.num_sms ? L.geom.num_tiles : L.num_sms;
-    SDPC_CUDA(launch_k(kernel, dim3(grid), dim3(kThreads), Cfg::kSmemBytes, stream, L.tmap_a, L.tmap_b, L.tmap_a_lo, L.tmap_b_lo, L.tmap_half, L.geom, L.epi));
+    SDPC_CUDA(launch_k(kernel, dim3(grid), dim3(kThreads), Cfg::kSmemBytes, stream, L.tmap_a, L.tmap_b, L.tmap_a_lo, L.tmap_b_lo, L.tmap_half, L.tmap_half_lo, L.geom, L.epi));
   } else {
     int clusters = L.geom.num_tiles / 2 < max_clusters ? L.geom.num_tiles / 2 : max_clusters;
     if (clusters > L.num_sms / 2) clusters = L.num_sms / 2;
@@ -588,7 +598,7 @@ static int launch_t(const UmmaConvLaunch& L, cudaStream_t stream) {
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    SDPC_CUDA(cudaLaunchKernelEx(&cfg, kernel, L.tmap_a, L.tmap_b, L.tmap_a_lo, L.tmap_b_lo, L.tmap_half, L.geom, L.epi));
+    SDPC_CUDA(cudaLaunchKernelEx(&cfg, kernel, L.tmap_a, L.tmap_b, L.tmap_a_lo, L.tmap_b_lo, L.tmap_half, L.tmap_half_lo, L.geom, L.epi));
   }
   SDPC_CUDA(cudaGetLastError());
   return SDPC_OK;
@@ -597,6 +607,12 @@ static int launch_t(const UmmaConvLaunch& L, cudaStream_t stream) {
 // swapped layers run as 2-CTA clusters with operand multicast unless SDPC_CLUSTER=0 (A/B switch, read once)
 bool conv_umma_cluster() {
   static const bool on = [] { const char* v = getenv("SDPC_CLUSTER"); return !(v && v[0] == '0'); }();
+  return on;
+}
+// the bf16x3 arm (three passes over K with hi / lo operand planes) runs in clusters / CTA pairs like the bf16 arm (measured
+// on a B200: outputs bit-identical to single CTAs, 8-view forward 27.4 -> 26.5 ms); SDPC_X3_CLUSTER=0 = single CTAs
+bool conv_umma_x3_cluster() {
+  static const bool on = [] { const char* v = getenv("SDPC_X3_CLUSTER"); return !(v && v[0] == '0'); }();
   return on;
 }
 // Cout = 256 layers run swapped as two 128-channel halves unless SDPC_SWAP256=0 (A/B switch, read once)
@@ -626,7 +642,7 @@ int conv_umma_launch(const UmmaConvLaunch& L, cudaStream_t stream) {
       (g.Cout != 128 && g.Cout != 256) || g.num_tiles != tiles)
     return set_error(SDPC_ERR_UNSUPPORTED, "conv_umma: unsupported shape Cin=%d Cout=%d tile=%dx%d tiles=%d", g.Cin, g.Cout,
                      g.BH, g.BW, g.num_tiles);
-  const bool cl = L.use_cluster && swapped && g.passes == 1 && (g.num_tiles % 2) == 0;
+  const bool cl = L.use_cluster && swapped && (g.passes == 1 || conv_umma_x3_cluster()) && (g.num_tiles % 2) == 0;
   if (L.elem_bytes == 2) {
     if (g.Cout == 128) return cl ? launch_t<__nv_bfloat16, 256, true, 128, true>(L, stream) : launch_t<__nv_bfloat16, 256, true, 128, false>(L, stream);
     if (!swapped) return launch_t<__nv_bfloat16, 256, false, 256, false>(L, stream);

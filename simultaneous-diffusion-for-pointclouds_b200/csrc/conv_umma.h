@@ -13,6 +13,7 @@ struct UmmaConvLaunch {
   CUtensorMap tmap_b;   // weights        {Cin, Cout, taps}, box {BK, conv_umma_weight_rows(Cout), 1}
   CUtensorMap tmap_a_lo, tmap_b_lo;   // residual (lo) planes of the bf16x3 arm (copies of a / b otherwise)
   CUtensorMap tmap_half;   // cluster variant: half-sized box of the operand the two CTAs of a cluster share (see conv_umma.cu)
+  CUtensorMap tmap_half_lo;   // the same box on the residual (lo) plane of that operand (bf16x3 arm in clusters; copy of tmap_half otherwise)
   int use_cluster;         // 1: tmap_half is valid and the layer may run as 2-CTA clusters
   ConvGeom geom;
   EpiParams epi;
@@ -28,5 +29,6 @@ int conv_umma_stats_parts(int Cout);   // partial-statistics slots per pixel til
 int conv_umma_weight_rows(int Cout);   // rows of the weight TMA box
 bool conv_umma_swap256();
 bool conv_umma_cluster();
+bool conv_umma_x3_cluster();   // bf16x3 arm in clusters / CTA pairs too (default; SDPC_X3_CLUSTER=0: single CTAs)
 
 }  // namespace sdpc

@@ -175,7 +175,7 @@ __global__ void merge_max_kernel(unsigned int* max_bits, const float* other, int
 // ------------------------------------------------------------------------------------------
 constexpr int kMaxGroup = 32;
 constexpr int kSeg = 128;               // source pixels per work item of the production traversal (one warp, 4 per lane)
-constexpr int kTravThreads = 256;       // 8 warps per persistent block
+constexpr int kTravThreads = 256;       // 8 warps per persistent block, two blocks per SM
 constexpr int kTravWarps = kTravThreads / 32;
 
 __device__ const double g_log2_tab[SDPC_LOG2_TABLE_DOUBLES] = {SDPC_LOG2_TABLE};
@@ -205,6 +205,7 @@ struct StepArgs {
   int want_key;                 // the nearest candidate is needed (controlled average or cell-level debug output)
   int winner_mode;              // 0: verify the packed winner where it matters; 1: verify every filled cell;
                                 // 2: flag every filled cell (the exact traversal decides every winner)
+  int dev_probe;                // SDPC_DEV_HOOKS builds only: SDPC_DEV_PROBE from the environment
 };
 
 struct SourcePoint {            // a source pixel in world coordinates (pose variant: homogeneous)
@@ -254,12 +255,26 @@ __device__ __forceinline__ void to_target(const StepArgs& a, const SourcePoint& 
 __device__ __forceinline__ void accumulate(const StepArgs& a, size_t cell, double r2, double nd, unsigned src_id,
                                            long long inten_fx) {
   CellRec* rec = a.ws.rec + cell;
+#ifdef SDPC_DEV_HOOKS                   // timing probe (tools/build_variant.py -D SDPC_DEV_HOOKS, SDPC_DEV_PROBE=1 in the environment):
+  if (a.dev_probe == 1) return;         // the traversal without its reductions (a run-time switch keeps the arithmetic alive)
+#endif
   if (a.want_key) {
     const unsigned long long key = (unsigned long long)__double_as_longlong(r2);      // r2 >= 0: monotone
     atomicMin(&rec->zmin, key);
     atomicMin(&rec->zpack, ((key >> a.key_shift) << a.key_shift) | (unsigned long long)src_id);
   }
-  atomicAdd((unsigned long long*)&rec->sum_d, (unsigned long long)depth_to_fixed(nd));
+#if defined(SDPC_DEV_PROBE_CNT_IN_REC)    // timing probes (results are wrong): every reduction of a candidate in ONE 32-byte sector
+  atomicAdd((unsigned long long*)&rec->sum_d, (unsigned long long)depth_to_fixed_magic(nd));
+  atomicAdd((unsigned long long*)&rec->sum_i, (unsigned long long)inten_fx + (1ull << 44));
+  return;
+#elif defined(SDPC_DEV_PROBE_ONE_RED)     // one 64-bit reduction per candidate
+  atomicAdd((unsigned long long*)&rec->sum_d, (unsigned long long)depth_to_fixed_magic(nd));
+  return;
+#elif defined(SDPC_DEV_PROBE_CNT_ONLY)    // one 32-bit reduction per candidate
+  atomicAdd(a.ws.cnt + cell, 1u);
+  return;
+#endif
+  atomicAdd((unsigned long long*)&rec->sum_d, (unsigned long long)depth_to_fixed_magic(nd));
   atomicAdd((unsigned long long*)&rec->sum_i, (unsigned long long)inten_fx);
   atomicAdd(a.ws.cnt + cell, 1u);
 }
@@ -417,7 +432,7 @@ __device__ __forceinline__ void traverse_items(const StepArgs& a, unsigned* coun
       }
     }
     __syncwarp();                      // the list may be overwritten by the next item from here on
-    // ---- target by target
+    // ---- target by target: the target's matrix comes out of shared memory once and serves the lane's pixels
     for (int t = t_lo; t < t_hi; ++t) {
       double m[12];
       if (a.variant == SDPC_VARIANT_POSE) {
@@ -443,13 +458,13 @@ __device__ __forceinline__ void traverse_items(const StepArgs& a, unsigned* coun
         int row, col;
         if (!pixel_fast(qx, qy, qz, a.geo, &row, &col)) continue;
         const size_t cell = (size_t)((unsigned)t * grid_cells + (unsigned)(row * a.geo.W + col));
-        const double r2 = range2(qx, qy, qz);
-        const unsigned src_id = (unsigned)(src_a * HW + pix[j]);
         if (FIX) {
           if (!(__ldcg(a.ws.cnt + cell) & kFlagBit)) continue;
         }
+        const double r2 = range2(qx, qy, qz);
         const double nd = fast_log_range_of_r2(r2, a.sigma_mod, a.geo, s_tab);
         if (!passes_min_depth(a, r2, nd)) continue;
+        const unsigned src_id = (unsigned)(src_a * HW + pix[j]);
         if (!FIX) accumulate(a, cell, r2, nd, src_id, ifx[j]);
         else report_winner(a, cell, r2, src_id);
       }
@@ -484,7 +499,7 @@ __device__ __forceinline__ void write_consumers(const StepArgs& a, int t, int gr
     a.ws.shared_mask[(size_t)t * HW + p] = (filled && (a.exist[p] != 0) && (a.sky[(size_t)t * HW + p] != 0)) ? 1 : 0;
   }
   if (use_m) {                                                    // the point-mirrored pixel, negative range
-    const int p = (H - 1 - gr) * W + ((gc + W / 2) % W);
+    const int p = (H - 1 - gr) * W + (gc + W / 2 >= W ? gc + W / 2 - W : gc + W / 2);
     const size_t i0 = ((size_t)t * 2) * HW + p;
     a.img[i0] = (float)(depth * -1.0);
     a.img[i0 + HW] = inten;
@@ -498,7 +513,7 @@ __device__ __forceinline__ void consumers_of(const StepArgs& a, int t, int gr, i
   const int HW = a.geo.H * a.geo.W, W = a.geo.W, H = a.geo.H, R = a.geo.R;
   const float* x0 = a.x + ((size_t)t * 2) * HW;
   *use_d = (gr >= R - H) && !(x0[(gr - (R - H)) * W + gc] < 0.0f);
-  *use_m = (gr < H) && (x0[(H - 1 - gr) * W + ((gc + W / 2) % W)] < 0.0f);
+  *use_m = (gr < H) && (x0[(H - 1 - gr) * W + (gc + W / 2 >= W ? gc + W / 2 - W : gc + W / 2)] < 0.0f);
 }
 
 __device__ __forceinline__ void rearm(const StepArgs& a, size_t cell) {
@@ -512,7 +527,9 @@ __device__ __forceinline__ void rearm(const StepArgs& a, size_t cell) {
 __device__ __forceinline__ void finish_cell(const StepArgs& a, int t, int gr, int gc, size_t cell, unsigned cn,
                                             const CellRec& rec, FusedFast f, long long winner) {
   const int HW = a.geo.H * a.geo.W;
-  const double min_d = a.want_key ? log_range_of_r2(__longlong_as_double((long long)rec.zmin), a.sigma_mod, a.geo) : 0.0;
+  // the nearest log-range: needed by a far cell and by the debug output only (one library log2 + sqrt)
+  const double min_d = (a.want_key && (f.far || a.dbg_min_d))
+                           ? log_range_of_r2(__longlong_as_double((long long)rec.zmin), a.sigma_mod, a.geo) : 0.0;
   if (f.far) {
     const int g = t / a.A, wa = (int)winner / HW, wp = (int)winner - wa * HW;
     fuse_far(&f, min_d, a.x[((size_t)(g * a.A + wa) * 2 + 1) * HW + wp], a.sigma_mod, a.allowance, a.geo.recip);
@@ -526,61 +543,87 @@ __device__ __forceinline__ void finish_cell(const StepArgs& a, int t, int gr, in
   rearm(a, cell);
 }
 
-// One thread per grid cell.  Pass 1 finishes what needs no winner (empty cells, plain averages) on the spot; cells whose
-// nearest candidate matters (far cells, or every filled cell in the verifying modes) are queued in shared memory and
-// pass 2 works the queue off with every lane busy: verification of the packed winner (one exact projection), the
-// reference's float64 pow / log2 for the far depth.
+// One thread per OUTPUT pixel: the cell it reads (crop, or the point mirror for a negative range), average /
+// controlled average, existMask.  Where the nearest candidate's identity matters (a far cell takes its intensity) the
+// packed winner is verified first; a cell whose packed winner is not confirmed is flagged and left to the fix pass,
+// which then also writes its pixels.
 __global__ void __launch_bounds__(256) resolve_kernel(StepArgs a) {
-  __shared__ unsigned short s_queue[256];
-  __shared__ unsigned s_n;
-  const int W = a.geo.W, R = a.geo.R;
+  const int HW = a.geo.H * a.geo.W, W = a.geo.W, H = a.geo.H, R = a.geo.R;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
   const int t = a.tgt_first + blockIdx.y;
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;          // cell of target t
-  if (threadIdx.x == 0) s_n = 0;
-  __syncthreads();
-  if (k < R * W) {
-    const int gr = k / W, gc = k - gr * W;
-    const size_t cell = (size_t)t * R * W + k;
-    const unsigned cn = a.ws.cnt[cell];
-    if (cn == 0) {                                                // empty: the cell is still armed
-      bool use_d, use_m;
-      consumers_of(a, t, gr, gc, &use_d, &use_m);
-      // the reference's arithmetic on an empty cell ends in +0 (-0 after the mirror's sign flip) and intensity 0
-      write_consumers(a, t, gr, gc, use_d, use_m, 0.0, 0.0f, false);
-      if (a.dbg_cnt) a.dbg_cnt[cell] = 0;
-      if (a.dbg_winner) a.dbg_winner[cell] = -1;
-      if (a.dbg_min_d) a.dbg_min_d[cell] = 0.0;
-    } else {
-      const CellRec rec = a.ws.rec[cell];
-      const FusedFast f = fuse_cell_fast(cn, rec.sum_d, rec.sum_i, __longlong_as_double((long long)rec.zmin), a.sigma_mod,
-                                         a.allowance, a.geo);
-      if (a.want_key && (f.far || a.winner_mode >= 1)) s_queue[atomicAdd(&s_n, 1u)] = (unsigned short)threadIdx.x;
-      else finish_cell(a, t, gr, gc, cell, cn, rec, f, -1);
-    }
-  }
-  __syncthreads();
-  const unsigned n = s_n;
-  for (unsigned i = threadIdx.x; i < n; i += blockDim.x) {
-    const int kk = blockIdx.x * blockDim.x + s_queue[i];
-    const int gr = kk / W, gc = kk - gr * W;
-    const size_t cell = (size_t)t * R * W + kk;
-    const unsigned cn = a.ws.cnt[cell];
-    const CellRec rec = a.ws.rec[cell];
-    const FusedFast f = fuse_cell_fast(cn, rec.sum_d, rec.sum_i, __longlong_as_double((long long)rec.zmin), a.sigma_mod,
-                                       a.allowance, a.geo);
-    const unsigned id = (unsigned)(rec.zpack & ((1ull << a.key_shift) - 1ull));
-    const bool confirmed = a.winner_mode != 2 && exact_key_of(a, t, id) == rec.zmin;
-    if (!confirmed) {                                             // leave the cell to the fix pass
-      a.ws.rec[cell].zpack = ~0ull;
-      a.ws.cnt[cell] = cn | kFlagBit;
-      atomicAdd(&a.ws.hdr->flag_count, 1u);
-      continue;
-    }
-    finish_cell(a, t, gr, gc, cell, cn, rec, f, (long long)id);
-  }
-  // the scatter's work counters are free again
-  if (blockIdx.x == 0 && blockIdx.y == 0)
+  if (blockIdx.x == 0 && blockIdx.y == 0)                       // the scatter's work counters are free again
     for (int i = threadIdx.x; i < a.ws.n_groups; i += blockDim.x) a.ws.work_ctr[i] = 0u;
+  if (p >= HW) return;
+  const int r = p / W, c = p - r * W;
+  const size_t i0 = ((size_t)t * 2) * HW + p;
+  const bool neg = a.x[i0] < 0.0f;
+  // crop rows [R-H, R); negative ranges read the point-mirrored cell (KITTISampling.py:401-403)
+  const int gr = neg ? (H - 1 - r) : (r + R - H);
+  const int gc = neg ? (c - W / 2 < 0 ? c - W / 2 + W : c - W / 2) : c;
+  const size_t cell = ((size_t)t * R + gr) * W + gc;
+  const unsigned cn = a.ws.cnt[cell] & ~kFlagBit;
+  double depth = 0.0;
+  float inten = 0.0f;
+  if (cn > 0) {
+    const CellRec rec = a.ws.rec[cell];
+    FusedFast f = fuse_cell_fast(cn, rec.sum_d, rec.sum_i, __longlong_as_double((long long)rec.zmin), a.sigma_mod,
+                                 a.allowance, a.geo);
+    if (f.far || (a.want_key && a.winner_mode == 2)) {
+      const unsigned id = (unsigned)(rec.zpack & ((1ull << a.key_shift) - 1ull));
+      const bool confirmed = a.winner_mode != 2 && rec.zpack != ~0ull && exact_key_of(a, t, id) == rec.zmin;
+      if (!confirmed) {                                           // leave the cell (and this pixel) to the fix pass
+        if (!(atomicOr(a.ws.cnt + cell, kFlagBit) & kFlagBit)) {  // first pixel to flag it (a cell serves up to two)
+          a.ws.rec[cell].zpack = ~0ull;
+          atomicAdd(&a.ws.hdr->flag_count, 1u);
+        }
+        return;
+      }
+      if (f.far) {
+        const int g = t / a.A, wa = (int)id / HW, wp = (int)id - wa * HW;
+        fuse_far(&f, log_range_of_r2(__longlong_as_double((long long)rec.zmin), a.sigma_mod, a.geo),
+                 a.x[((size_t)(g * a.A + wa) * 2 + 1) * HW + wp], a.sigma_mod, a.allowance, a.geo.recip);
+      }
+    }
+    depth = f.depth;
+    inten = f.inten;
+  }
+  // the reference's arithmetic on an empty cell ends in +0 (-0 after the mirror's sign flip) and intensity 0
+  a.img[i0] = (float)(neg ? depth * -1.0 : depth);
+  a.img[i0 + HW] = inten;
+  a.ws.shared_mask[(size_t)t * HW + p] = (cn > 0 && (a.exist[p] != 0) && (a.sky[(size_t)t * HW + p] != 0)) ? 1 : 0;
+}
+
+// One thread per grid cell, after resolve: cell-level debug output (with every filled cell's winner verified) and
+// re-arming, so that the z-buffers are empty again when the call returns and no step needs a memset.  Flagged cells
+// are left to the fix pass.
+__global__ void __launch_bounds__(256) rearm_kernel(StepArgs a) {
+  const size_t grid_cells = (size_t)a.geo.R * a.geo.W;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)a.tgt_count * grid_cells) return;
+  const size_t cell = (size_t)a.tgt_first * grid_cells + i;
+  const unsigned c = a.ws.cnt[cell];
+  if (c == 0) {
+    if (a.dbg_cnt) a.dbg_cnt[cell] = 0;
+    if (a.dbg_winner) a.dbg_winner[cell] = -1;
+    if (a.dbg_min_d) a.dbg_min_d[cell] = 0.0;
+    return;
+  }
+  if (c & kFlagBit) return;
+  if (a.want_key && a.winner_mode >= 1) {       // verifying modes (cell-level debug output selects one): every filled cell
+    const CellRec rec = a.ws.rec[cell];
+    const int t = (int)(cell / grid_cells);
+    const unsigned id = (unsigned)(rec.zpack & ((1ull << a.key_shift) - 1ull));
+    if (a.winner_mode == 2 || exact_key_of(a, t, id) != rec.zmin) {   // not confirmed: the fix pass finds the exact winner
+      a.ws.rec[cell].zpack = ~0ull;
+      a.ws.cnt[cell] = c | kFlagBit;
+      atomicAdd(&a.ws.hdr->flag_count, 1u);
+      return;
+    }
+    if (a.dbg_cnt) a.dbg_cnt[cell] = (int32_t)c;
+    if (a.dbg_winner) a.dbg_winner[cell] = (int32_t)id;
+    if (a.dbg_min_d) a.dbg_min_d[cell] = log_range_of_r2(__longlong_as_double((long long)rec.zmin), a.sigma_mod, a.geo);
+  }
+  rearm(a, cell);
 }
 
 // After a fix traversal: the last block to finish completes the flagged cells of this call's target range.
@@ -702,7 +745,7 @@ static bool use_full_scatter(const sdpc_step_params* p, const sdpc_step_buffers*
 
 extern "C" int sdpc_step_kernel_launches(const sdpc_step_params* p, const sdpc_step_buffers* b) {
   if (!p || !b) return set_error(SDPC_ERR_ARG, "null params/buffers");
-  return p->share ? 5 : 1;          // update [+ scatter, resolve, fix (exits at once unless a cell was flagged), correct]
+  return p->share ? 6 : 1;          // update [+ scatter, resolve, re-arm, fix (exits at once unless a cell was flagged), correct]
 }
 
 extern "C" size_t sdpc_step_workspace_bytes(int n_views, int height, int width, int big_rows) {
@@ -789,14 +832,20 @@ extern "C" int sdpc_crossview_share(const sdpc_step_params* p, const sdpc_step_b
   if (p->key_shift_override > a.key_shift && p->key_shift_override < 52) a.key_shift = p->key_shift_override;
   a.want_key = (p->allowance >= 0.0 || dbg_cells) ? 1 : 0;
   a.winner_mode = p->winner_mode;
+  a.dev_probe = 0;
+#ifdef SDPC_DEV_HOOKS
+  if (const char* v = getenv("SDPC_DEV_PROBE")) a.dev_probe = atoi(v);
+#endif
   if (dbg_cells && a.winner_mode == 0) a.winner_mode = 1;        // the debug output names every cell's winner
   a.ws.n_groups = p->n_views / p->group_size;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  // persistent traversal: blocks per group so that the whole grid is about two blocks per SM
+  // persistent traversal: blocks per group so that the whole grid is about two blocks (16 warps) per SM
+  // (SDPC_XVIEW_BLOCKS_PER_SM: tuning knob; measured flat from 2 to 4)
+  static const int blocks_per_sm = [] { const char* v = getenv("SDPC_XVIEW_BLOCKS_PER_SM"); int n = v ? atoi(v) : 2; return n > 0 ? n : 2; }();
   const int per_group = std::max(1, std::min((HW / kSeg * p->group_size + kTravWarps - 1) / kTravWarps,
-                                             (2 * sms + a.ws.n_groups - 1) / a.ws.n_groups));
+                                             (blocks_per_sm * sms + a.ws.n_groups - 1) / a.ws.n_groups));
   const dim3 sgrid(per_group, a.ws.n_groups);
   if (full) {
     const dim3 grid((HW + 255) / 256, p->group_size, p->n_views / p->group_size);
@@ -805,8 +854,10 @@ extern "C" int sdpc_crossview_share(const sdpc_step_params* p, const sdpc_step_b
     scatter_fast_kernel<<<sgrid, kTravThreads, 0, stream>>>(a);
   }
   SDPC_CUDA(cudaGetLastError());
-  const dim3 rgrid((unsigned)((p->big_rows * p->width + 255) / 256), tcount);
+  const dim3 rgrid((unsigned)((HW + 255) / 256), tcount);
   resolve_kernel<<<rgrid, 256, 0, stream>>>(a);
+  SDPC_CUDA(cudaGetLastError());
+  rearm_kernel<<<(unsigned)(((size_t)tcount * p->big_rows * p->width + 255) / 256), 256, 0, stream>>>(a);
   SDPC_CUDA(cudaGetLastError());
   if (a.want_key) {
     if (HW % kSeg == 0) {

@@ -155,6 +155,7 @@ SDPC_HD double log_range(double qx, double qy, double qz, float sigma_mod, const
 // per-cell sum of log-ranges, which is accumulated in 2^-40 fixed point (9e-13) and ends as a float32.
 // tab: the {rc, T} pairs of log2_table.h (shared memory on the device).
 #define SDPC_LOG2_TABLE_DOUBLES 256
+constexpr double kRoundMagicLog = 6755399441055744.0;          // 1.5 * 2^52
 SDPC_HD double fast_log2(double v, const double* tab) {
   const double c[6] = {SDPC_LOG2_COEF};
   long long bits;
@@ -164,6 +165,10 @@ SDPC_HD double fast_log2(double v, const double* tab) {
   const long long mb = (bits & 0x000FFFFFFFFFFFFFll) | 0x3FF0000000000000ll;
   double m;
   memcpy(&m, &mb, 8);
+  const long long eb = 0x4338000000000000ll + (long long)e;       // (double)e without the conversion unit
+  double ed;
+  memcpy(&ed, &eb, 8);
+  ed -= kRoundMagicLog;
   const double t = fma(m, tab[2 * i], -1.0);
   double p = c[5];
   p = fma(p, t, c[4]);
@@ -171,7 +176,7 @@ SDPC_HD double fast_log2(double v, const double* tab) {
   p = fma(p, t, c[2]);
   p = fma(p, t, c[1]);
   p = fma(p, t, c[0]);
-  return (double)e + fma(t, p, tab[2 * i + 1]);
+  return ed + fma(t, p, tab[2 * i + 1]);
 }
 SDPC_HD double fast_log_range_of_r2(double r2, float sigma_mod, const GeoConsts& g, const double* tab) {
   double nd = fast_log2(sqrt(r2) + 1.0, tab);
@@ -207,34 +212,72 @@ SDPC_HD float fast_atan2f(float y, float x) {
   return copysignf(a, y);
 }
 
+// round-half-to-even of a float64 with |v| < 2^31 without the conversion unit: adding 1.5 * 2^52 leaves the rounded
+// integer in the low mantissa bits (two's complement in the low 32 bits), subtracting it again gives rint(v)
+constexpr double kRoundMagic = 6755399441055744.0;
+SDPC_HD int magic_low32(double biased) {
+  long long b;
+  memcpy(&b, &biased, 8);
+  return (int)(unsigned)(b & 0xFFFFFFFFll);
+}
+
 // Same integers as reproject(), cheaper: each float64 atan2 is replaced by fast_atan2f whenever the estimated pixel
 // coordinate is provably far from a rounding boundary.  Error budget of the estimate: fast_atan2f 7.6e-5 px, the
-// float32 rounding of its inputs 2e-5 px, sqrtf of the planar norm 2e-5 px: < 1.2e-4 px; guard band 4e-4 px (3x).
-// Candidates inside the band (0.08 % per axis), non-finite or huge coordinates take the float64 expressions of the
-// reference, so the integers are identical (tests/host_emul checks every candidate of every CPU test case; the GPU
-// tests compare with the full float64 kernel).  Validity is decided on the rounded doubles: col = W-1-rc is inside
-// [0, W) iff rc is inside [0, W-1]; NaN fails every comparison (the reference's INT_MIN is outside the grid too).
+// float32 rounding of its inputs 1e-5 px, the approximate square root of the planar norm 2e-5 px: < 1.1e-4 px; guard
+// band 4e-4 px (3.6x).  Candidates inside the band (0.08 % per axis), non-finite or huge coordinates take the float64
+// expressions of the reference, so the integers are identical (tests/host_emul checks every candidate of every CPU
+// test case; the GPU tests compare with the full float64 kernel).  Two stages so that a kernel can run the estimates
+// of several candidates without a branch between them:
+//   pixel_estimate : biased (+ kRoundMagic) column / row coordinates and whether both are safely inside a pixel
+//   pixel_exact    : the reference's float64 expressions, biased the same way
+//   pixel_finish   : validity and the flipped integers.  Validity is decided on the rounded doubles: col = W-1-rc is
+//                    inside [0, W) iff rc is inside [0, W-1]; NaN fails every comparison (the reference's INT_MIN is
+//                    outside the grid too).
 constexpr double kPixelGuard = 4e-4;
-SDPC_HD bool pixel_fast(double qx, double qy, double qz, const GeoConsts& g, int* row, int* col) {
+SDPC_HD bool pixel_estimate(double qx, double qy, double qz, const GeoConsts& g, double* cm, double* rm) {
   const float fx = (float)qx, fy = (float)qy, fz = (float)qz;
   const bool tame = fmaxf(fmaxf(fabsf(fx), fabsf(fy)), fabsf(fz)) < 1e15f;      // false for NaN / inf / huge
+  const float xy = fx * fx + fy * fy;
+#if defined(__CUDA_ARCH__)
+  const float rxy = xy * rsqrtf(xy);                                            // 0 * inf = NaN for xy = 0: exact path
+#else
+  const float rxy = sqrtf(xy);
+#endif
   const double cf = ((double)fast_atan2f(fy, fx) - g.h_min) * g.inv_dh;
-  double rc = rint(cf);
-  if (!(tame && fabs(cf - rc) < 0.5 - kPixelGuard)) rc = rint(sdiv(atan2(qy, qx) - g.h_min, g.dh, g.recip));
-  const double rf = ((double)fast_atan2f(fz, sqrtf(fx * fx + fy * fy)) - g.big_row_min) * g.inv_dv;
-  double rr = rint(rf);
-  if (!(tame && fabs(rf - rr) < 0.5 - kPixelGuard))
-    rr = rint(sdiv(atan2(qz, sqrt(qx * qx + qy * qy)) - g.big_row_min, g.dv, g.recip));
+  const double rf = ((double)fast_atan2f(fz, rxy) - g.big_row_min) * g.inv_dv;
+  *cm = cf + kRoundMagic;
+  *rm = rf + kRoundMagic;
+  return tame && fabs(cf - (*cm - kRoundMagic)) < 0.5 - kPixelGuard && fabs(rf - (*rm - kRoundMagic)) < 0.5 - kPixelGuard;
+}
+SDPC_HD void pixel_exact(double qx, double qy, double qz, const GeoConsts& g, double* cm, double* rm) {
+  // rint() of the reference first: the biased sum of an already integral double is exact
+  *cm = rint(sdiv(atan2(qy, qx) - g.h_min, g.dh, g.recip)) + kRoundMagic;
+  *rm = rint(sdiv(atan2(qz, sqrt(qx * qx + qy * qy)) - g.big_row_min, g.dv, g.recip)) + kRoundMagic;
+}
+SDPC_HD bool pixel_finish(double cm, double rm, const GeoConsts& g, int* row, int* col) {
+  const double rc = cm - kRoundMagic, rr = rm - kRoundMagic;
   const bool ok = rc >= 0.0 && rc <= (double)(g.W - 1) && rr >= 0.0 && rr <= (double)(g.R - 1);
-  *col = ok ? g.W - 1 - (int)rc : -1;
-  *row = ok ? g.R - 1 - (int)rr : -1;
+  *col = g.W - 1 - magic_low32(cm);
+  *row = g.R - 1 - magic_low32(rm);
   return ok;
+}
+SDPC_HD bool pixel_fast(double qx, double qy, double qz, const GeoConsts& g, int* row, int* col) {
+  double cm, rm;
+  if (!pixel_estimate(qx, qy, qz, g, &cm, &rm)) pixel_exact(qx, qy, qz, g, &cm, &rm);
+  return pixel_finish(cm, rm, g, row, col);
 }
 
 // Fixed-point accumulation makes the per-pixel sums order independent (deterministic atomics).
 constexpr double kDepthScale = 1099511627776.0;      // 2^40
 constexpr double kIntenScale = 4294967296.0;         // 2^32
 SDPC_HD long long depth_to_fixed(double nd) { return (long long)rint(nd * kDepthScale); }
+// the same value for 0 <= nd < 2048 (it is: nd <= log2(1e15 + 1) / 6 * 50) without the conversion unit
+SDPC_HD long long depth_to_fixed_magic(double nd) {
+  const double biased = nd * kDepthScale + kRoundMagic;
+  long long b;
+  memcpy(&b, &biased, 8);
+  return b - 0x4338000000000000ll;
+}
 SDPC_HD long long inten_to_fixed(float v) { return (long long)rint((double)v * kIntenScale); }
 
 struct Fused {

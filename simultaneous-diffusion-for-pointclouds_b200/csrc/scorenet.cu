@@ -446,19 +446,23 @@ struct Builder {
     L.tmap_a_lo = L.tmap_a;
     L.tmap_b_lo = L.tmap_b;
     L.tmap_half = L.tmap_a;
+    L.tmap_half_lo = L.tmap_a;
     L.use_cluster = 0;
-    if (conv_umma_cluster() && !h->x3() && tile_px == 256 && g.num_tiles % 2 == 0) {
+    if (conv_umma_cluster() && (!h->x3() || conv_umma_x3_cluster()) && tile_px == 256 && g.num_tiles % 2 == 0) {
       // the operand two paired tiles share, with a half-sized box: the activation tile (two channel halves of a
       // Cout = 256 layer) or the weights (two neighbouring pixel tiles of a Cout = 128 layer)
       int st;
       if (cw.Cout == 256) {
         uint32_t hbox[4] = {(uint32_t)bk, (uint32_t)(g.BH >= 2 ? g.BW : g.BW / 2), (uint32_t)(g.BH >= 2 ? g.BH / 2 : 1), 1u};
         st = make_tmap(&L.tmap_half, in.ptr, L.elem_bytes, 4, adims, hbox);
+        if (!st && h->x3()) st = make_tmap(&L.tmap_half_lo, in.ptr + in.lo_off * 2, 2, 4, adims, hbox);
       } else {
         uint32_t hbox[3] = {(uint32_t)bk, 64u, 1u};
         st = make_tmap(&L.tmap_half, cw.w_tc, L.elem_bytes, 3, bdims, hbox);
+        if (!st && h->x3()) st = make_tmap(&L.tmap_half_lo, cw.w_tc_lo, 2, 3, bdims, hbox);
       }
       if (st) { status = st; return; }
+      if (!h->x3()) L.tmap_half_lo = L.tmap_half;
       L.use_cluster = 1;
     }
     if (h->x3()) {

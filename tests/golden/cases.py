@@ -81,6 +81,38 @@ def full_multiview(B=3, A=3, H=64, W=1024, seed=4242):
                 allowance=10, coef=0.01, toWorld=to_world, fromWorld=from_world)
 
 
+CONFIG3_MODIFICATIONS = [[0, 0, 0], [5, -5, 0], [-5, -5, 0], [0, 5, 0], [-10, 10, 0], [10, 10, 0], [-10, 0, 0], [10, 0, 0]]
+FULL_TRANS_RUNS = {"hi7": (7.5, 7, False), "lo8": (0.3, 8, False), "lo7d": (0.3, 7, True)}   # tag: sigma, setting, densify
+
+
+def full_translation(densify=False, B=8, A=8, H=64, W=1024, seed=5151):
+    """a-5 at the full image size in the shape of BASELINE configs 3 / 4: V = A = 8 views at the configured
+    offsets (Inpainting.yml's seven + one more), existMask = the reference's own processed data file (kept bit-packed in
+    the package), view 0 the target; `densify`: its known pixels are rows 0::4 only (16 of 64 beams).  A tenth of the sky
+    flags are cleared (the KITTI datasets never do that, the API allows it), 3 % of the ranges are negative."""
+    import sdpc_b200  # noqa: F401
+    from sdpc_b200.synthetic_data import lidargen_exist_mask
+    r = _rng(seed, 6)
+    refer = smooth_range_image(B, H, W, seed)
+    x = refer + torch.from_numpy(r.normal(0, 0.05, size=refer.shape).astype(np.float32))
+    neg = torch.from_numpy(r.uniform(size=(B, H, W)) < 0.03)
+    x[:, 0] = torch.where(neg, -x[:, 0].abs() * 0.5, x[:, 0])
+    known = r.uniform(size=(B, 1, H, W)) < 0.6
+    supp = r.uniform(size=(B, 1, H, W)) < 0.9
+    if densify:
+        rows = np.zeros((1, 1, H, 1), dtype=bool)
+        rows[:, :, 0::4] = True
+        known = np.broadcast_to(rows, known.shape)
+    first = (np.arange(B) % A == 0).reshape(B, 1, 1, 1)
+    mask = torch.from_numpy(np.ascontiguousarray(np.where(first, known, supp)).astype(np.int32)).repeat(1, 2, 1, 1).contiguous()
+    sky = torch.from_numpy(r.uniform(size=(B, 1, H, W)) < 0.9)
+    ex = lidargen_exist_mask(H, W)
+    assert ex is not None, "data/exist_mask_lidargen.npz is missing (tests/golden/make_golden_exist.py writes it)"
+    exist = torch.from_numpy(np.ascontiguousarray(np.broadcast_to(ex, (A, H, W))))
+    return dict(B=B, A=A, H=H, W=W, R=big_rows(H), x=x, refer=refer, mask=mask, sky=sky, exist=exist, allowance=10,
+                coef=0.01, mods=torch.tensor(CONFIG3_MODIFICATIONS[:A], dtype=torch.int64))
+
+
 def short_sigmas():
     """4-level schedule spanning sigma>1 (sigmaMod=sigma) and sigma<=1 (sigmaMod=1); numpy float32
     like the runner's get_sigmas(config).cpu().numpy() (ncsn_runner_kitti_simultaneous.py:491-492)."""

@@ -23,6 +23,8 @@ Fixtures written to tests/golden/:
   sampler_trans.npz     a-5 short schedule trajectory
   sampler_single.npz    a-6 short schedule trajectory
   crossview_full.npz    a-4 one step at 64x1024, B=A=3: strided samples + checksums
+  crossview_full_trans.npz  a-5 one step at 64x1024, V=A=8 (BASELINE configs 3/4: configured offsets, the shipped existTotal
+                        mask, inpainting and rows-0::4 densification masks, settings 7 and 8): strided samples + checksums
 """
 import argparse
 import os
@@ -279,9 +281,39 @@ def gen_full():
          min_d_sum=np.float64(r["min_d"].sum()))
 
 
+def _full_summary(r):
+    s = cases.FULL_STRIDE
+    flat = lambda a: a.reshape(-1)
+    w = np.arange(r["colr"].size) % 1009
+    return dict(
+        new_images_s=flat(r["new_images"])[::s], x_final_s=flat(r["x_final"])[::s],
+        colr_s=flat(r["colr"])[::s], rowr_s=flat(r["rowr"])[::s], cnt_s=flat(r["cnt"])[::s],
+        colr_sum=np.int64(r["colr"].astype(np.int64).sum()), rowr_sum=np.int64(r["rowr"].astype(np.int64).sum()),
+        colr_wsum=np.int64((r["colr"].astype(np.int64).reshape(-1) * w).sum()),
+        rowr_wsum=np.int64((r["rowr"].astype(np.int64).reshape(-1) * w).sum()),
+        cnt_sum=np.int64(r["cnt"].sum()), n_filled=np.int64((r["cnt"] > 0).sum()),
+        new_images_abs_sum=np.float64(np.abs(r["new_images"].astype(np.float64)).sum()),
+        x_final_abs_sum=np.float64(np.abs(r["x_final"].astype(np.float64)).sum()))
+
+
+def gen_full_trans():
+    arrs = {}
+    for tag, (sigma, setting, densify) in cases.FULL_TRANS_RUNS.items():
+        case = cases.full_translation(densify=densify)
+        r = run_one_step("trans", case, sigma, setting)
+        out = _full_summary(r)
+        if "min_d" in r:
+            s = cases.FULL_STRIDE
+            out.update(min_d_s=r["min_d"].reshape(-1)[::s], min_i_s=r["min_i"].reshape(-1)[::s],
+                       min_d_sum=np.float64(r["min_d"].sum()))
+        arrs.update({f"{tag}:{k}": v for k, v in out.items()})
+        print(tag, "filled cells", int(out["n_filled"]), "candidates", int(out["cnt_sum"]))
+    save("crossview_full_trans.npz", **arrs)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count())
-    which = sys.argv[1:] or ["sigmas", "scorenet", "crossview", "samplers", "n4", "full"]
+    which = sys.argv[1:] or ["sigmas", "scorenet", "crossview", "samplers", "n4", "full", "full_trans"]
     for w in which:
         {"sigmas": gen_sigmas, "scorenet": gen_scorenet, "crossview": gen_crossview,
-         "samplers": gen_samplers, "n4": gen_n4, "full": gen_full}[w]()
+         "samplers": gen_samplers, "n4": gen_n4, "full": gen_full, "full_trans": gen_full_trans}[w]()

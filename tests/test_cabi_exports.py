@@ -52,7 +52,7 @@ def test_product_path_fails_loudly_without_cuda():
 
 
 def test_step_kernel_launches():
-    """host-only query behind bench.py's gpu_launches: update + (scatter, resolve, fix, correct) - the z-buffers are re-armed
+    """host-only query behind bench.py's gpu_launches: update + (scatter, resolve, re-arm, fix, correct) - the z-buffers are re-armed
     by the resolve pass, so a step has no memset besides the 4-byte max word - in every winner mode."""
     import ctypes as C
     lib = cabi.load()
@@ -60,7 +60,7 @@ def test_step_kernel_launches():
     p.height, p.width, p.share = 64, 1024, 1
     for mode in (0, 1, 2):
         p.winner_mode = mode
-        assert lib.sdpc_step_kernel_launches(C.byref(p), C.byref(b)) == 5
+        assert lib.sdpc_step_kernel_launches(C.byref(p), C.byref(b)) == 6
     p.share = 0
     assert lib.sdpc_step_kernel_launches(C.byref(p), C.byref(b)) == 1
     assert lib.sdpc_step_kernel_launches(None, None) < 0

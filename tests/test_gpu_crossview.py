@@ -286,3 +286,44 @@ def test_production_scatter_full_size():
         assert torch.equal(ni_a, ni_b) and torch.equal(x_a, x_b), mode
     x_p, ni_p, _ = _cuda_step("pose", case, 0.3, 5, debug=False)
     assert torch.equal(ni_a, ni_p) and torch.equal(x_a, x_p)
+
+
+@pytest.mark.parametrize("tag", sorted(cases.FULL_TRANS_RUNS))
+def test_full_size_translation_configs(tag):
+    """a-5 in the shape of BASELINE configs 3 / 4: V = A = 8 at 64x1024, the configured view offsets, the reference's own
+    existTotal mask, inpainting / rows-0::4 densification masks, sky filter, unconditional min-depth filter, settings 7
+    (allowance 10) and 8 (allowance 5).  (1) indices, validity, counts, winners and nearest depths bit-exact against the
+    oracle on the same device; (2) the production kernels (no debug output) give the same images bit for bit;
+    (3) against one step of the unmodified reference on the CPU (crossview_full_trans.npz): a handful of index flips at
+    most (CPU / CUDA powf and atan2 differ in the last ulp), checksums within that."""
+    sigma, setting, densify = cases.FULL_TRANS_RUNS[tag]
+    case = cases.full_translation(densify=densify)
+    x, ni, run = _cuda_step("trans", case, sigma, setting)
+    ni_ref, x_ref, th, d = _oracle("trans", case, sigma, setting, DEV)
+    dbg = run.debug
+    assert torch.equal(dbg["row"], d["row"]) and torch.equal(dbg["col"], d["col"])
+    assert torch.equal(dbg["valid"].bool(), d["valid"])
+    assert torch.equal(dbg["cnt"], d["cnt"].int())
+    tied = d["n_tied"] > 1                                  # exact depth ties: the reference leaves the winner undefined
+    assert torch.equal(dbg["winner"][~tied], d["winner"].int()[~tied]) and int(tied.sum()) <= 8
+    assert torch.equal(dbg["min_d"], d["min_d"])
+    assert torch.allclose(ni, ni_ref, rtol=1e-5, atol=1e-6) and torch.allclose(x, x_ref, rtol=1e-5, atol=1e-6)
+    x_p, ni_p, _ = _cuda_step("trans", case, sigma, setting, debug=False)
+    assert torch.equal(ni, ni_p) and torch.equal(x, x_p)
+    # the unmodified reference on the CPU
+    g = np.load(os.path.join(G, "crossview_full_trans.npz"))
+    k = lambda n: g[f"{tag}:{n}"]
+    x_c, ni_c, run_c = _cuda_step("trans", case, sigma, setting, recip=False)
+    s = cases.FULL_STRIDE
+    colr = (1023 - run_c.debug["col"]).cpu().numpy().astype(np.int64)
+    rowr = (run_c.geo.R - 1 - run_c.debug["row"]).cpu().numpy().astype(np.int64)
+    flips = int((colr.reshape(-1)[::s] != k("colr_s")).sum() + (rowr.reshape(-1)[::s] != k("rowr_s")).sum())
+    cnt = run_c.debug["cnt"].cpu().numpy()
+    print(f"[a-5 full {tag}] sampled index flips vs CPU reference: {flips} of {k('colr_s').size}; checksum deltas "
+          f"{int(colr.sum()) - int(k('colr_sum'))} {int(rowr.sum()) - int(k('rowr_sum'))}; count delta "
+          f"{int(cnt.sum()) - int(k('cnt_sum'))}; filled delta {int((cnt > 0).sum()) - int(k('n_filled'))}")
+    assert flips <= 2
+    assert abs(int(colr.sum()) - int(k("colr_sum"))) <= 128 and abs(int(rowr.sum()) - int(k("rowr_sum"))) <= 128
+    assert abs(int(cnt.sum()) - int(k("cnt_sum"))) <= 64 and abs(int((cnt > 0).sum()) - int(k("n_filled"))) <= 64
+    assert int((np.abs(ni_c.cpu().numpy().reshape(-1)[::s] - k("new_images_s")) > 1e-4).sum()) <= 4
+    assert int((np.abs(x_c.cpu().numpy().reshape(-1)[::s] - k("x_final_s")) > 1e-4).sum()) <= 4

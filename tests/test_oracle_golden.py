@@ -207,3 +207,33 @@ def test_crossview_full_size_checksums():
     assert int(d["cnt"].sum()) == int(g["cnt_sum"]) and int((d["cnt"] > 0).sum()) == int(g["n_filled"])
     assert np.array_equal(d["min_d"].numpy().reshape(-1)[::s], g["min_d_s"])
     assert np.allclose(ni.numpy().reshape(-1)[::s], g["new_images_s"], atol=1e-6)
+
+
+@pytest.mark.parametrize("tag", sorted(cases.FULL_TRANS_RUNS))
+def test_crossview_full_size_translation_checksums(tag):
+    """a-5 in the shape of BASELINE configs 3 / 4 (V = A = 8 at 64x1024, configured offsets, the shipped existTotal mask,
+    inpainting / rows-0::4 densification masks, settings 7 and 8): the oracle against one step of the unmodified reference
+    (models/__init__.py:112-602; fixture crossview_full_trans.npz) - every index, every count, the samples of the values."""
+    g = _load("crossview_full_trans.npz")
+    sigma, setting, densify = cases.FULL_TRANS_RUNS[tag]
+    case = cases.full_translation(densify=densify)
+    geo = cv.make_geometry(64, 1024)
+    sm = sigma if sigma > 1 else 1
+    ni, im, th, d = cv.shared_images(case["x"], geo, sm, case["A"], case["exist"], case["sky"],
+                                     origins=cv.translation_origins(case["mods"]), min_depth_filter=True,
+                                     controlled_average=True, allowance=(5.0 if setting >= 8 else 10.0), sky_filter=True,
+                                     return_debug=True)
+    x_final = cv.apply_correction(case["x"], ni, im, case["sky"], case["mask"], th, case["coef"])
+    s = cases.FULL_STRIDE
+    k = lambda n: g[f"{tag}:{n}"]
+    colr = (1023 - d["col"]).numpy().astype(np.int64)
+    rowr = (geo.R - 1 - d["row"]).numpy().astype(np.int64)
+    w = np.arange(colr.size) % 1009
+    assert int(colr.sum()) == int(k("colr_sum")) and int(rowr.sum()) == int(k("rowr_sum"))
+    assert int((colr.reshape(-1) * w).sum()) == int(k("colr_wsum")) and int((rowr.reshape(-1) * w).sum()) == int(k("rowr_wsum"))
+    assert int(d["cnt"].sum()) == int(k("cnt_sum")) and int((d["cnt"] > 0).sum()) == int(k("n_filled"))
+    assert np.array_equal(d["cnt"].numpy().reshape(-1)[::s], k("cnt_s"))
+    assert np.array_equal(d["min_d"].numpy().reshape(-1)[::s], k("min_d_s"))
+    assert np.allclose(ni.numpy().reshape(-1)[::s], k("new_images_s"), atol=1e-6)
+    assert np.allclose(x_final.numpy().reshape(-1)[::s], k("x_final_s"), atol=1e-6)
+    assert abs(float(np.abs(ni.numpy().astype(np.float64)).sum()) - float(k("new_images_abs_sum"))) < 1e-6 * float(k("new_images_abs_sum"))
