@@ -194,6 +194,16 @@ int sdpc_langevin_update(const sdpc_step_params* p, const sdpc_step_buffers* b,
 /* Optional hook between update and share for sharded runs: fold other ranks' max|x0| in. */
 int sdpc_step_merge_max(void* workspace, const float* other_max, int n, void* stream);
 int sdpc_step_read_max(void* workspace, float* out_max, void* stream);
+/* View sharding over ranks (the reference's group concatenation KITTISampling.py:189-206 happens on one
+ * device): ONE exchange per step.  A rank's slot of the gather buffer holds its `views_per_rank` updated views
+ * [views_per_rank,2,H,W] followed by its max |x0| word (sdpc_shard_slot_floats floats per slot, slots contiguous in rank
+ * order).  pack fills the rank's own slot after sdpc_langevin_update; the caller all-gathers the slots (NCCL
+ * all_gather_into_tensor in place); unpack copies the other ranks' views into x (rank-major view order) and folds their
+ * maxima into the workspace, after which sdpc_crossview_share runs on the rank's target range. */
+size_t sdpc_shard_slot_floats(int views_per_rank, int height, int width);
+int sdpc_shard_pack(void* workspace, const float* x_own, float* slot, int views_per_rank, int height, int width, void* stream);
+int sdpc_shard_unpack(void* workspace, float* x, const float* gathered, int world, int rank, int views_per_rank,
+                      int height, int width, void* stream);
 /* Cross-view block on the updated sample (KITTISampling.py:160-490): un-project, pose transform,
  * re-project, z-buffer (count, sums, nearest), fusion, crop/mirror, correction. */
 int sdpc_crossview_share(const sdpc_step_params* p, const sdpc_step_buffers* b,

@@ -49,6 +49,12 @@ def sources():
     return deps
 
 
+def kernel_digest():
+    """sha256 over the convolution kernel sources: profiles/conv_traffic.json records it, so bench.py can tell whether
+    the committed ncu capture is of the kernels this library was built from."""
+    return _digest([os.path.join(CSRC, f) for f in ("conv_umma.cu", "conv_umma.h", "sm100_prims.cuh")])
+
+
 def build(force=False, verbose=False):
     os.makedirs(OBJ, exist_ok=True)
     stamp = os.path.join(OBJ, "stamp")

@@ -74,6 +74,9 @@ SYMBOLS = [
     ("sdpc_langevin_update", _I, [C.POINTER(StepParams), C.POINTER(StepBuffers), _P, _SZ, _P]),
     ("sdpc_step_merge_max", _I, [_P, _P, _I, _P]),
     ("sdpc_step_read_max", _I, [_P, _P, _P]),
+    ("sdpc_shard_slot_floats", _SZ, [_I, _I, _I]),
+    ("sdpc_shard_pack", _I, [_P, _P, _P, _I, _I, _I, _P]),
+    ("sdpc_shard_unpack", _I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
     ("sdpc_crossview_share", _I, [C.POINTER(StepParams), C.POINTER(StepBuffers), _P, _SZ, _P]),
     ("sdpc_step_kernel_launches", _I, [C.POINTER(StepParams), C.POINTER(StepBuffers)]),
     ("sdpc_langevin_reproject_step", _I, [C.POINTER(StepParams), C.POINTER(StepBuffers), _P, _SZ, _P]),

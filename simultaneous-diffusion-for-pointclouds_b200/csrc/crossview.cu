@@ -171,6 +171,31 @@ __global__ void merge_max_kernel(unsigned int* max_bits, const float* other, int
 }
 
 // ------------------------------------------------------------------------------------------
+// view sharding: one exchange per step.  A rank's slot of the gather buffer = its updated x planes followed
+// by its max |x0| word; after the all-gather one kernel copies the other ranks' planes into x and folds their maxima in.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+shard_pack_kernel(const float4* __restrict__ x_own, float4* __restrict__ slot, const unsigned int* __restrict__ max_bits,
+                  size_t n_vec) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_vec) slot[i] = x_own[i];
+  if (i == 0) reinterpret_cast<unsigned int*>(slot + n_vec)[0] = *max_bits;
+}
+
+__global__ void __launch_bounds__(256)
+shard_unpack_kernel(float4* __restrict__ x, const float4* __restrict__ gbuf, unsigned int* __restrict__ max_bits,
+                    int world, int rank, size_t n_vec, size_t slot_vec) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = blockIdx.y;
+  if (r != rank && i < n_vec) x[(size_t)r * n_vec + i] = gbuf[(size_t)r * slot_vec + i];
+  if (r == 0 && i == 0) {              // torch.max over every view of the call (KITTISampling.py:162); a NaN pattern is the largest
+    unsigned b = *max_bits;
+    for (int k = 0; k < world; ++k) b = max(b, reinterpret_cast<const unsigned int*>(gbuf + (size_t)k * slot_vec + n_vec)[0]);
+    *max_bits = b;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // scatter / resolve / fix
 // ------------------------------------------------------------------------------------------
 constexpr int kMaxGroup = 32;
@@ -785,6 +810,34 @@ extern "C" int sdpc_langevin_update(const sdpc_step_params* p, const sdpc_step_b
 extern "C" int sdpc_step_merge_max(void* workspace, const float* other_max, int n, void* stream) {
   if (!workspace || !other_max || n <= 0) return set_error(SDPC_ERR_ARG, "merge_max: bad argument");
   merge_max_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((unsigned int*)workspace, other_max, n);
+  SDPC_CUDA(cudaGetLastError());
+  return SDPC_OK;
+}
+
+extern "C" size_t sdpc_shard_slot_floats(int views_per_rank, int height, int width) {
+  return (size_t)views_per_rank * 2 * height * width + 32;       // the planes + one 128-byte line for the max word
+}
+
+extern "C" int sdpc_shard_pack(void* workspace, const float* x_own, float* slot, int views_per_rank, int height, int width,
+                               void* stream) {
+  if (!workspace || !x_own || !slot || views_per_rank <= 0) return set_error(SDPC_ERR_ARG, "shard_pack: bad argument");
+  const size_t n = (size_t)views_per_rank * 2 * height * width;
+  if (n % 4) return set_error(SDPC_ERR_ARG, "shard_pack: H*W must be a multiple of 2");
+  shard_pack_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      (const float4*)x_own, (float4*)slot, &((StepHeader*)workspace)->max_bits, n / 4);
+  SDPC_CUDA(cudaGetLastError());
+  return SDPC_OK;
+}
+
+extern "C" int sdpc_shard_unpack(void* workspace, float* x, const float* gathered, int world, int rank, int views_per_rank,
+                                 int height, int width, void* stream) {
+  if (!workspace || !x || !gathered || world <= 0 || rank < 0 || rank >= world)
+    return set_error(SDPC_ERR_ARG, "shard_unpack: bad argument");
+  const size_t n = (size_t)views_per_rank * 2 * height * width;
+  const size_t slot = sdpc_shard_slot_floats(views_per_rank, height, width);
+  const dim3 grid((unsigned)((n / 4 + 255) / 256), world);
+  shard_unpack_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((float4*)x, (const float4*)gathered,
+                                                             &((StepHeader*)workspace)->max_bits, world, rank, n / 4, slot / 4);
   SDPC_CUDA(cudaGetLastError());
   return SDPC_OK;
 }

@@ -34,7 +34,7 @@ def _rel(a, b):
     return float((a - b).abs().max() / b.abs().max())
 
 
-@pytest.mark.parametrize("precision,tol", [("fp32", 1e-3), ("bf16x3", 1e-3)])
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-5), ("bf16x3", 1e-4)])      # measured 3.7e-6 / 2.3e-5 (north_star: 1e-3)
 def test_config1_single_view_baseline(precision, tol):
     """BASELINE.json configs[0]: a-6, B=1, 2x64x1024, 10-level geometric schedule (model.num_classes=10), denoise."""
     H, W, L = 64, 1024, 10
@@ -56,7 +56,9 @@ def test_config1_single_view_baseline(precision, tol):
     assert max(errs) <= tol
 
 
-@pytest.mark.parametrize("precision,tol,max_flip_frac", [("bf16x3", 1e-3, 0.01), ("bf16", 5e-2, 0.05)])
+# bounds at about 2x what a B200 measures (round 2): final sample 2.5e-5 (bf16x3) / 8.9e-3 (bf16) of the oracle's, shared-image
+# pixels that moved to a neighbouring cell 0.17 % / 1.75 %
+@pytest.mark.parametrize("precision,tol,max_flip_frac", [("bf16x3", 1e-4, 0.004), ("bf16", 2e-2, 0.035)])
 def test_line_sampler_with_real_network(precision, tol, max_flip_frac):
     """a-4 with the real score network on 4 views (A=4), levels spread over the schedule so that both sigmaMod
     branches and the minStepToShare switch are crossed."""

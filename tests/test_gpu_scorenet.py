@@ -2,12 +2,13 @@
 
 Oracle: oracle/scorenet_ref.py (torch fp32, pinned bit-for-bit on the reference) and the golden
 fixture tests/golden/scorenet_small.npz produced by the unmodified reference module.
-Tolerances (max abs error / max abs value of the reference tensor):
-  fp32  (CUDA-core FMA)            1e-4
-  bf16x3 (tcgen05, hi/lo split)    1e-3   the tensor-core arm that meets north_star's fp32 bound
-  tf32  (tcgen05 kind::tf32)       2e-2   (measured 6e-3..8e-3; what cuDNN's default TF32 convs give the reference on a GPU)
-  bf16  (tcgen05 kind::f16, bf16)  1.5e-1 (measured 5e-2..6e-2), stated separately as north_star asks
-The fp32 arm is the one that meets north_star's 1e-3; per-block intermediates are held to 5x tighter bounds.
+Tolerances (max abs error / max abs value of the reference tensor), set at about 1.5x what a B200 measures
+(round 2, 16x64 fixture / 64x1024 oracle) so that a regression of the arithmetic is caught:
+  fp32  (CUDA-core FMA)            5e-5   measured 2.3e-5 / 2.9e-5
+  bf16x3 (tcgen05, hi/lo split)    3e-4   measured 1.5e-4 / 1.7e-4 - the tensor-core arm inside north_star's 1e-3 fp32 bound
+  tf32  (tcgen05 kind::tf32)       1.2e-2 measured 6.3e-3 / 7.8e-3 (what cuDNN's default TF32 convs give the reference on a GPU)
+  bf16  (tcgen05 kind::f16, bf16)  8e-2   measured 6.3e-2 / 5.7e-2, stated separately as north_star asks
+Per-block intermediates (13 taps) have their own bounds, about 2x the largest measured tap error of the arm.
 """
 import argparse
 import os
@@ -26,8 +27,10 @@ pytestmark = pytest.mark.gpu
 G = os.path.join(os.path.dirname(__file__), "golden")
 DEV = "cuda:0"
 N = argparse.Namespace
-TOL = {"fp32": 1e-4, "bf16x3": 1e-3, "tf32": 2e-2, "bf16": 1.5e-1}      # output; per-block taps are 5x tighter (see below)
-TAP_TOL = {"fp32": 2e-5, "bf16x3": 2e-4, "tf32": 4e-3, "bf16": 3e-2}
+NORTH_STAR_FP32 = 1e-3                                                     # score within 1e-3 relative in fp32
+TOL = {"fp32": 5e-5, "bf16x3": 3e-4, "tf32": 1.2e-2, "bf16": 8e-2}         # output
+TAP_TOL = {"fp32": 1e-5, "bf16x3": 3e-4, "tf32": 3e-3, "bf16": 2e-2}       # per-block taps (largest measured: 4.9e-6, 1.5e-4, 1.6e-3, 1.1e-2)
+assert TOL["fp32"] <= NORTH_STAR_FP32 and TOL["bf16x3"] <= NORTH_STAR_FP32
 TAPS = ["begin_conv", "res1.0", "res1.1", "res2.0", "res2.1", "res3.0", "res3.1", "res4.0", "res4.1",
         "refine1", "refine2", "refine3", "refine4"]
 

@@ -8,7 +8,8 @@ arm under test, update, cross-view block) with the same injected noise, and four
   score      max-abs error of the CUDA score / max-abs of the oracle's (the arm's tolerance: 1e-3 bf16x3, 8e-2 bf16)
   update     the same for the sample after the Langevin update
   exact      the cross-view block on IDENTICAL input (the oracle's post-update sample): pixel indices, validity, counts,
-             winners, nearest depths must be bit-exact against the oracle (asserted), newImages within 1e-5
+             winners, nearest depths must be bit-exact against the oracle (asserted), newImages and the corrected
+             sample within 1e-6 of the image's largest value
   end to end the CUDA step on its OWN post-update sample against the oracle's step: cells whose count differs (candidates
              that crossed a pixel boundary because the score differs in the last digits - the flip count), and the error
              of the final sample and of newImages outside those cells
@@ -120,7 +121,9 @@ def sweep(precision, V=8, H=64, W=1024, L=232, steps_each=1, levels=None, dev="c
                                x_rel_identical_input=rel(x_id, x_next))
                     assert ok_cnt and ok_win and ok_min, row
                     assert int(run.too_high.item()) == int(bool(th_ref)), row
-                    assert torch.allclose(ni_id, ni_ref, rtol=1e-5, atol=1e-6), row
+                    # values: against the LARGEST value of the image (at the first levels samples and intensities reach
+                    # the hundreds and the oracle's own float32 sums carry 1e-5 absolute rounding on near-cancelling cells)
+                    assert row["new_images_rel_identical_input"] <= 1e-6 and row["x_rel_identical_input"] <= 1e-6, row
                     # ---- the whole CUDA step on its own numbers
                     x_e2e = x.clone()
                     ni_e2e = torch.zeros_like(x_e2e)
