@@ -278,7 +278,13 @@ SDPC_HD long long depth_to_fixed_magic(double nd) {
   memcpy(&b, &biased, 8);
   return b - 0x4338000000000000ll;
 }
-SDPC_HD long long inten_to_fixed(float v) { return (long long)rint((double)v * kIntenScale); }
+// Non-finite intensities enter the sum as 0 (the reference's float sum would make the cell NaN), finite ones are clamped to
+// +-2^20 so that 2^11 candidates of one cell cannot overflow the 64-bit sum (deviations).
+SDPC_HD long long inten_to_fixed(float v) {
+  if (!(fabsf(v) <= 3.4028234663852886e38f)) return 0;
+  const float c = fminf(fmaxf(v, -1048576.0f), 1048576.0f);
+  return (long long)rint((double)c * kIntenScale);
+}
 
 struct Fused {
   double depth;  // float64 log-range of the shared image at this grid cell
