@@ -59,7 +59,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default=os.environ.get("SDPC_PRECISION", "bf16"),
-                    choices=["bf16", "bf16x3", "fp16", "tf32", "fp32"])
+                    choices=["bf16", "bf16x3", "tf32", "fp32"])
     ap.add_argument("--variant", default="line", choices=sorted(VARIANTS))
     ap.add_argument("--views-per-gpu", type=int, default=VIEWS_PER_GPU)
     ap.add_argument("--group-size", type=int, default=8,

@@ -239,7 +239,16 @@ __device__ __forceinline__ void store_op8<__nv_bfloat16>(__nv_bfloat16* dst, con
 // One thread: 8 channels x PIX consecutive pixels of a row (all loads issued before use: 128 bytes in flight per
 // thread, i.e. 4 pixels of fp32 input or 8 pixels of bf16 input).  With HALO_ZERO the halo is not written here: the
 // buffer's border is cleared by zero_halo_kernel.
-template <typename TIn> __host__ __device__ constexpr int op_pix() { return sizeof(TIn) == 2 ? 8 : 4; }
+#ifndef SDPC_OP_PIX_F32            // tuning knobs of tools/build_variant.py -D ...: pixels per thread, resident blocks per SM
+#define SDPC_OP_PIX_F32 4
+#endif
+#ifndef SDPC_OP_PIX_H16
+#define SDPC_OP_PIX_H16 8
+#endif
+#ifndef SDPC_OP_MINB
+#define SDPC_OP_MINB 2
+#endif
+template <typename TIn> __host__ __device__ constexpr int op_pix() { return sizeof(TIn) == 2 ? SDPC_OP_PIX_H16 : SDPC_OP_PIX_F32; }
 template <typename T, int MINB, typename TIn = float>
 __global__ void __launch_bounds__(256, MINB)
 to_operand_kernel(const TIn* __restrict__ in, const float* __restrict__ coef, T* __restrict__ out, int N, int H,

@@ -313,8 +313,8 @@ struct Builder {
     const bool in_h = x.elem == 2;                           // bf16 raw input (see raw_h())
     push([=](cudaStream_t s, const float*, const int64_t*, float*) -> int {
       if (zero) SDPC_CUDA(launch_k(zero_halo_kernel<T>, dim3(blocks(border)), dim3(256), 0, s, o, nz, H, W, C, P));
-      if (in_h) SDPC_CUDA(launch_k(to_operand_kernel<T, 2, __nv_bfloat16>, dim3(blocks(total)), dim3(256), 0, s, (const __nv_bfloat16*)in, coef, o, n, H, W, C, P, mode, halo, tf32, lo_off));
-      else SDPC_CUDA(launch_k(to_operand_kernel<T, 2>, dim3(blocks(total)), dim3(256), 0, s, in, coef, o, n, H, W, C, P, mode, halo, tf32, lo_off));
+      if (in_h) SDPC_CUDA(launch_k(to_operand_kernel<T, SDPC_OP_MINB, __nv_bfloat16>, dim3(blocks(total)), dim3(256), 0, s, (const __nv_bfloat16*)in, coef, o, n, H, W, C, P, mode, halo, tf32, lo_off));
+      else SDPC_CUDA(launch_k(to_operand_kernel<T, SDPC_OP_MINB>, dim3(blocks(total)), dim3(256), 0, s, in, coef, o, n, H, W, C, P, mode, halo, tf32, lo_off));
       SDPC_CUDA(cudaGetLastError());
       return SDPC_OK;
     }, zero ? 2 : 1);
