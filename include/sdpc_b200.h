@@ -41,8 +41,11 @@ enum sdpc_precision {
   SDPC_PREC_FP32 = 0, /* CUDA-core fp32 FMA, strict-parity arm (matches CPU fp32 to ~1e-5) */
   SDPC_PREC_TF32 = 1, /* tcgen05 kind::tf32, fp32 activations rounded to tf32, fp32 accumulate */
   SDPC_PREC_BF16 = 2, /* tcgen05 kind::f16 (bf16 operands), fp32 accumulate in TMEM */
-  SDPC_PREC_BF16X3 = 3 /* fp32-parity arm on the tensor cores: operands split into bf16 hi + lo planes,
+  SDPC_PREC_BF16X3 = 3, /* fp32-parity arm on the tensor cores: operands split into bf16 hi + lo planes,
                           X_hi.W_hi + X_hi.W_lo + X_lo.W_hi accumulated in fp32 (3 tcgen05 passes, ~16-bit operands) */
+  SDPC_PREC_FP16 = 4   /* tcgen05 kind::f16 with IEEE half operands (11-bit significand: the precision class of the TF32
+                          convolutions the reference runs on a GPU, at the bf16 arm's rate), fp32 accumulate; finite values
+                          saturate at +-65504 */
 };
 
 int sdpc_abi_version(void);

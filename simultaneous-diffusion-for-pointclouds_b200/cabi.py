@@ -11,8 +11,8 @@ LIB_PATH = os.environ.get("SDPC_LIB") or os.path.join(_HERE, "libsdpc_b200.so") 
 
 ABI_VERSION = 2          # SDPC_ABI_VERSION of include/sdpc_b200.h
 SDPC_VARIANT_POSE, SDPC_VARIANT_TRANSLATION = 0, 1
-PREC_FP32, PREC_TF32, PREC_BF16, PREC_BF16X3 = 0, 1, 2, 3
-PRECISIONS = {"fp32": PREC_FP32, "tf32": PREC_TF32, "bf16": PREC_BF16, "bf16x3": PREC_BF16X3}
+PREC_FP32, PREC_TF32, PREC_BF16, PREC_BF16X3, PREC_FP16 = 0, 1, 2, 3, 4
+PRECISIONS = {"fp32": PREC_FP32, "tf32": PREC_TF32, "bf16": PREC_BF16, "bf16x3": PREC_BF16X3, "fp16": PREC_FP16}
 
 
 class StepParams(C.Structure):

@@ -87,7 +87,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   constexpr int kBK = kRowBytes / (int)sizeof(T);     // channels per k-block: 64 bf16 / 32 tf32
   constexpr int kUmmaK = 32 / (int)sizeof(T);         // 16 / 8 -> 32 bytes per MMA along K
   constexpr int kMmasPerStage = kBK / kUmmaK;         // 4
-  constexpr uint32_t kIdesc = umma_idesc(kTf32 ? 2u : 1u, CG * kTileM, N_TILE);
+  // operand format of the MMA: tf32 for 32-bit operands; for 16-bit operands bf16 (1) or, in the fp16 arm, half (0)
+  const uint32_t kIdesc = umma_idesc(kTf32 ? 2u : (e.op_tf32 ? 0u : 1u), CG * kTileM, N_TILE);
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -306,7 +307,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             if (e.acc_bf16) {
               __nv_bfloat16* ap = reinterpret_cast<__nv_bfloat16*>(e.out_acc) + raw0;
 #pragma unroll
-              for (int j = 0; j < 32; ++j) ap[j * kCout] = __float2bfloat16_rn(v[j]);
+              for (int j = 0; j < 32; ++j) *reinterpret_cast<uint16_t*>(&ap[j * kCout]) = pack1_h16(v[j], e.op_tf32 != 0);
             } else {
               float* ap = reinterpret_cast<float*>(e.out_acc) + raw0;
 #pragma unroll
@@ -321,7 +322,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             if (e.raw_bf16) {
               __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(e.out_raw) + raw0;
 #pragma unroll
-              for (int j = 0; j < 32; ++j) op[j * kCout] = __float2bfloat16_rn(v[j]);
+              for (int j = 0; j < 32; ++j) *reinterpret_cast<uint16_t*>(&op[j * kCout]) = pack1_h16(v[j], e.op_tf32 != 0);
             } else {
               float* op = e.out_raw + raw0;
 #pragma unroll
@@ -421,7 +422,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
               for (int it = 0; it < 8; ++it) {
                 const float a4[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
-                store_op4<__nv_bfloat16>(ap + it * 4 * kCout, a4, false, 0);
+                store_op4<__nv_bfloat16>(ap + it * 4 * kCout, a4, e.op_tf32 != 0, 0);
               }
             } else {
               float* ap = reinterpret_cast<float*>(e.out_acc) + raw0 + ch;
@@ -439,7 +440,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
               for (int it = 0; it < 8; ++it) {
                 const float a4[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
-                store_op4<__nv_bfloat16>(op + it * 4 * kCout, a4, false, 0);
+                store_op4<__nv_bfloat16>(op + it * 4 * kCout, a4, e.op_tf32 != 0, 0);
               }
             } else {
               float* op = e.out_raw + raw0 + ch;

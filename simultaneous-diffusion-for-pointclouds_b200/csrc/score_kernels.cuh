@@ -220,7 +220,12 @@ __device__ __forceinline__ void store_op8(T* dst, const float* v, bool tf32, siz
 }
 // bf16: one 16-byte store per plane instead of two 8-byte ones
 template <>
-__device__ __forceinline__ void store_op8<__nv_bfloat16>(__nv_bfloat16* dst, const float* v, bool, size_t lo_off) {
+__device__ __forceinline__ void store_op8<__nv_bfloat16>(__nv_bfloat16* dst, const float* v, bool alt, size_t lo_off) {
+  if (alt) {                                                  // fp16 arm
+    *reinterpret_cast<uint4*>(dst) = make_uint4(pack2_h16(v[0], v[1], true), pack2_h16(v[2], v[3], true),
+                                                pack2_h16(v[4], v[5], true), pack2_h16(v[6], v[7], true));
+    return;
+  }
   __nv_bfloat162 h[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) h[k] = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
@@ -289,10 +294,8 @@ to_operand_kernel(const TIn* __restrict__ in, const float* __restrict__ coef, T*
   for (int j = 0; j < PIX; ++j) {
     float v[8];
     if constexpr (sizeof(TIn) == 2) {                          // bf16 input (conv1 outputs of the plain bf16 arm)
-      const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&q[j].x));
-      const float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&q[j].y));
-      const float2 f2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&q[j].z));
-      const float2 f3 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&q[j].w));
+      const float2 f0 = unpack2_h16(q[j].x, tf32 != 0), f1 = unpack2_h16(q[j].y, tf32 != 0);
+      const float2 f2 = unpack2_h16(q[j].z, tf32 != 0), f3 = unpack2_h16(q[j].w, tf32 != 0);
       v[0] = f0.x; v[1] = f0.y; v[2] = f1.x; v[3] = f1.y; v[4] = f2.x; v[5] = f2.y; v[6] = f3.x; v[7] = f3.y;
     } else {
       v[0] = __uint_as_float(q[j].x); v[1] = __uint_as_float(q[j].y); v[2] = __uint_as_float(q[j].z); v[3] = __uint_as_float(q[j].w);
@@ -433,8 +436,16 @@ maxpool5_kernel(const float* __restrict__ in, float* __restrict__ x0_out, T* __r
 constexpr int kPoolHCB = 64;
 constexpr int kPoolHThreads = (kPoolTW + 4) * (kPoolHCB / 8);   // 288
 
-__device__ __forceinline__ uint4 hmax8(const uint4& a, const uint4& b) {
+__device__ __forceinline__ uint32_t hmax2_half(uint32_t a, uint32_t b) {
+  const __half2 m = __hmax2(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
+  return *reinterpret_cast<const uint32_t*>(&m);
+}
+__device__ __forceinline__ uint4 hmax8(const uint4& a, const uint4& b, bool alt) {
   uint4 r;
+  if (alt) {                                                  // fp16 arm: the words are half pairs
+    r.x = hmax2_half(a.x, b.x); r.y = hmax2_half(a.y, b.y); r.z = hmax2_half(a.z, b.z); r.w = hmax2_half(a.w, b.w);
+    return r;
+  }
   const __nv_bfloat162 x = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a.x), *reinterpret_cast<const __nv_bfloat162*>(&b.x));
   const __nv_bfloat162 y = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a.y), *reinterpret_cast<const __nv_bfloat162*>(&b.y));
   const __nv_bfloat162 z = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a.z), *reinterpret_cast<const __nv_bfloat162*>(&b.z));
@@ -443,15 +454,11 @@ __device__ __forceinline__ uint4 hmax8(const uint4& a, const uint4& b) {
   r.z = *reinterpret_cast<const uint32_t*>(&z); r.w = *reinterpret_cast<const uint32_t*>(&w);
   return r;
 }
-__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
-  const __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<const uint32_t*>(&t);
-}
 
 template <typename TIn>
 __global__ void __launch_bounds__(kPoolHThreads)
 maxpool5_h2_kernel(const TIn* __restrict__ in, float* __restrict__ x0_out, __nv_bfloat16* __restrict__ out, int N, int H,
-                   int W, int C, int P, int elu_in) {
+                   int W, int C, int P, int elu_in, int alt) {
   pdl_sync();
   __shared__ uint4 tv[kPoolTH][kPoolTW + 4][kPoolHCB / 8];       // 36 KB
   const int CBn = C / kPoolHCB, TWn = W / kPoolTW, THn = H / kPoolTH;
@@ -461,7 +468,9 @@ maxpool5_h2_kernel(const TIn* __restrict__ in, float* __restrict__ x0_out, __nv_
   const int th = b % THn;
   const int n = b / THn;
   const int h0 = th * kPoolTH, w0 = tw * kPoolTW, c0 = cb * kPoolHCB;
-  const uint4 ninf = make_uint4(0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u);      // bf16 -inf pairs
+  const uint32_t ni2 = alt ? 0xFC00FC00u : 0xFF80FF80u;                                   // -inf pairs (half / bf16)
+  const uint4 ninf = make_uint4(ni2, ni2, ni2, ni2);
+  const bool h16 = alt != 0;
   {
     const int c8 = threadIdx.x & 7, cc = threadIdx.x >> 3;        // cc in [0, 36): input column
     const int ww = w0 - 2 + cc;
@@ -487,7 +496,7 @@ maxpool5_h2_kernel(const TIn* __restrict__ in, float* __restrict__ x0_out, __nv_
             }
             if (elu_in) { a = ea; c = ec; }
           }
-          v[r] = make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(c.x, c.y), pack_bf16x2(c.z, c.w));
+          v[r] = make_uint4(pack2_h16(a.x, a.y, h16), pack2_h16(a.z, a.w, h16), pack2_h16(c.x, c.y, h16), pack2_h16(c.z, c.w, h16));
         }
       }
     }
@@ -495,7 +504,7 @@ maxpool5_h2_kernel(const TIn* __restrict__ in, float* __restrict__ x0_out, __nv_
     for (int r = 0; r < kPoolTH; ++r) {
       uint4 m = v[r];
 #pragma unroll
-      for (int k = 1; k < 5; ++k) m = hmax8(m, v[r + k]);
+      for (int k = 1; k < 5; ++k) m = hmax8(m, v[r + k], h16);
       tv[r][cc][c8] = m;
     }
   }
@@ -511,7 +520,7 @@ maxpool5_h2_kernel(const TIn* __restrict__ in, float* __restrict__ x0_out, __nv_
     for (int j = 0; j < 8; ++j) {
       uint4 m = cfl[j];
 #pragma unroll
-      for (int k = 1; k < 5; ++k) m = hmax8(m, cfl[j + k]);
+      for (int k = 1; k < 5; ++k) m = hmax8(m, cfl[j + k], h16);
       const int w = w0 + seg * 8 + j;
       const HaloPos d = halo_pos(h, w, H, W, P);
       for_each_halo_pos(d, [&](int hp, int wp) {
@@ -810,9 +819,13 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, T* __restrict_
   const float v = src[i];
   if (dst_tc) {
     if constexpr (sizeof(T) == 2) {
-      const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-      dst_tc[((size_t)tap * Cout + co) * Cin + ci] = hi;
-      if (dst_lo) dst_lo[((size_t)tap * Cout + co) * Cin + ci] = __float2bfloat16_rn(v - __bfloat162float(hi));
+      if (tf32) {                                             // fp16 arm: half bit patterns
+        *reinterpret_cast<uint16_t*>(&dst_tc[((size_t)tap * Cout + co) * Cin + ci]) = pack1_h16(v, true);
+      } else {
+        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+        dst_tc[((size_t)tap * Cout + co) * Cin + ci] = hi;
+        if (dst_lo) dst_lo[((size_t)tap * Cout + co) * Cin + ci] = __float2bfloat16_rn(v - __bfloat162float(hi));
+      }
     } else {
       dst_tc[((size_t)tap * Cout + co) * Cin + ci] = tf32 ? round_tf32(v) : v;
     }

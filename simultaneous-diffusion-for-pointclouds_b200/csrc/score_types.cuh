@@ -1,6 +1,7 @@
 // Shared types of the score-network kernels: convolution geometry, fused epilogue.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -32,7 +33,8 @@ struct EpiParams {
   void* out_op;           // operand (T) with halo `op_pad`, value = act(after bias+residual), or null
   int op_pad;
   int op_elu;             // 1: ELU before the operand store
-  int op_tf32;            // 1: round the fp32 operand to tf32 (rna)
+  int op_tf32;            // 1: the arm's alternate operand format - a 32-bit operand is rounded to tf32 (rna), a 16-bit operand
+                          //    (and the 16-bit out_raw / out_acc copies) holds IEEE half instead of bf16 (fp16 arm)
   size_t op_lo_off;       // bf16x3 arm: element offset of the residual (lo) plane of out_op, else 0
   int prefetch_residual;  // 1: the epilogue warps prefetch the tile's residual rows into L2 before the accumulator is ready
 #ifdef SDPC_DEV_HOOKS
@@ -63,6 +65,28 @@ __device__ __forceinline__ float round_tf32(float v) {
   return __uint_as_float(r);
 }
 
+// 16-bit containers (declared __nv_bfloat16 throughout) hold bf16 bit patterns or, in the fp16 arm, IEEE half bit patterns:
+// the `tf32` / `alt` flag that rounds a 32-bit operand to tf32 selects the half format for a 16-bit one ("the arm's
+// alternate operand format").  Half conversions saturate finite values at +-65504 (NaN stays NaN).
+__device__ __forceinline__ float sat_half(float v) { return fabsf(v) > 65504.0f ? copysignf(65504.0f, v) : v; }
+__device__ __forceinline__ uint32_t pack2_h16(float a, float b, bool alt) {
+  if (alt) {
+    const __half2 t = __floats2half2_rn(sat_half(a), sat_half(b));
+    return *reinterpret_cast<const uint32_t*>(&t);
+  }
+  const __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&t);
+}
+__device__ __forceinline__ float2 unpack2_h16(uint32_t w, bool alt) {
+  if (alt) return __half22float2(*reinterpret_cast<const __half2*>(&w));
+  return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w));
+}
+__device__ __forceinline__ uint16_t pack1_h16(float v, bool alt) {
+  if (alt) { const __half t = __float2half_rn(sat_half(v)); return *reinterpret_cast<const uint16_t*>(&t); }
+  const __nv_bfloat16 t = __float2bfloat16_rn(v);
+  return *reinterpret_cast<const uint16_t*>(&t);
+}
+
 // lo_off != 0 (bf16x3 arm): the operand is stored as two bf16 planes, hi = bf16(v) at dst and the rounding
 // residual lo = bf16(v - hi) at dst + lo_off, so that hi + lo carries ~16 mantissa bits.
 template <typename T>
@@ -74,7 +98,11 @@ __device__ __forceinline__ void store_op4<float>(float* dst, const float* v, boo
   *reinterpret_cast<float4*>(dst) = o;
 }
 template <>
-__device__ __forceinline__ void store_op4<__nv_bfloat16>(__nv_bfloat16* dst, const float* v, bool, size_t lo_off) {
+__device__ __forceinline__ void store_op4<__nv_bfloat16>(__nv_bfloat16* dst, const float* v, bool alt, size_t lo_off) {
+  if (alt) {                                                  // fp16 arm: half bit patterns, single plane
+    *reinterpret_cast<uint2*>(dst) = make_uint2(pack2_h16(v[0], v[1], true), pack2_h16(v[2], v[3], true));
+    return;
+  }
   __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]);
   __nv_bfloat162 b = __floats2bfloat162_rn(v[2], v[3]);
   uint2 o;
@@ -98,7 +126,8 @@ __device__ __forceinline__ void store_op1(T* dst, float v, bool tf32, size_t lo_
 template <>
 __device__ __forceinline__ void store_op1<float>(float* dst, float v, bool tf32, size_t) { *dst = tf32 ? round_tf32(v) : v; }
 template <>
-__device__ __forceinline__ void store_op1<__nv_bfloat16>(__nv_bfloat16* dst, float v, bool, size_t lo_off) {
+__device__ __forceinline__ void store_op1<__nv_bfloat16>(__nv_bfloat16* dst, float v, bool alt, size_t lo_off) {
+  if (alt) { *reinterpret_cast<uint16_t*>(dst) = pack1_h16(v, true); return; }
   const __nv_bfloat16 hi = __float2bfloat16_rn(v);
   *dst = hi;
   if (lo_off) dst[lo_off] = __float2bfloat16_rn(v - __bfloat162float(hi));

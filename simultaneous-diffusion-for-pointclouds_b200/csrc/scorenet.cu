@@ -97,8 +97,15 @@ struct sdpc_score {
     if (!ev_pool.empty()) { cudaEvent_t e = ev_pool.back(); ev_pool.pop_back(); return e; }
     cudaEvent_t e; cudaEventCreate(&e); return e;
   }
-  int elem_bytes() const { return (cfg.precision == SDPC_PREC_BF16 || cfg.precision == SDPC_PREC_BF16X3) ? 2 : 4; }
+  int elem_bytes() const {
+    return (cfg.precision == SDPC_PREC_BF16 || cfg.precision == SDPC_PREC_BF16X3 || cfg.precision == SDPC_PREC_FP16) ? 2 : 4;
+  }
   bool x3() const { return cfg.precision == SDPC_PREC_BF16X3; }
+  // single-pass 16-bit arms (bf16 and fp16 operands): packed max-pooling, 16-bit copies of the tensors only a norm pass reads
+  bool plain16() const { return cfg.precision == SDPC_PREC_BF16 || cfg.precision == SDPC_PREC_FP16; }
+  // the arm's alternate operand format (EpiParams::op_tf32): tf32 rounding of 32-bit operands, half instead of bf16 in
+  // 16-bit containers
+  int alt_fmt() const { return (cfg.precision == SDPC_PREC_TF32 || cfg.precision == SDPC_PREC_FP16) ? 1 : 0; }
   const float* P(const std::string& n) const { return params[index.at(n)].dev; }
 };
 
@@ -215,7 +222,7 @@ struct Builder {
   Buf raw(int H, int W, int C) { return alloc(N, H, W, C, 0, 4); }
   // A tensor that only an InstanceNorm++ -> ELU -> operand pass reads (conv1 of a residual block): the plain bf16 arm
   // stores it in bf16 (its statistics come from the fp32 accumulators in the epilogue), halving that write and re-read.
-  Buf raw_h(int H, int W, int C) { return (h->cfg.precision == SDPC_PREC_BF16 && !getenv("SDPC_RAW_FP32")) ? alloc(N, H, W, C, 0, 2) : raw(H, W, C); }
+  Buf raw_h(int H, int W, int C) { return (h->plain16() && !getenv("SDPC_RAW_FP32")) ? alloc(N, H, W, C, 0, 2) : raw(H, W, C); }
   Buf operand(int H, int W, int C, int pad) {
     if (!h->x3()) return alloc(N, H, W, C, pad, h->elem_bytes());
     Buf b = alloc(2 * N, H, W, C, pad, 2);                 // hi planes of all views, then lo planes
@@ -322,29 +329,29 @@ struct Builder {
   Buf to_operand(const Buf& x, const float* coef, int pad, int mode, int halo, bool force_fp32 = false) {
     Buf out = force_fp32 ? alloc(N, x.H, x.W, x.C, pad, 4) : operand(x.H, x.W, x.C, pad);
     if (dry()) return out;
-    const int tf32 = (!force_fp32 && h->cfg.precision == SDPC_PREC_TF32) ? 1 : 0;
+    const int tf32 = force_fp32 ? 0 : h->alt_fmt();
     if (out.elem == 2) to_operand_t<__nv_bfloat16>(x, coef, out, mode, halo, tf32);
     else to_operand_t<float>(x, coef, out, mode, halo, tf32);
     return out;
   }
 
   // the plain bf16 arm pools on packed bf16 pairs and lets the CRP convolution leave its out_acc in bf16
-  bool pool_h2() const { return h->cfg.precision == SDPC_PREC_BF16; }
+  bool pool_h2() const { return h->plain16(); }
   Buf maxpool(const Buf& x, bool elu_in, Buf* x0_out) {
     Buf out = operand(x.H, x.W, x.C, 1);
     if (dry()) return out;
     const float* in = (const float*)x.ptr;
     float* x0 = x0_out ? (float*)x0_out->ptr : nullptr;
     const int n = N, H = x.H, W = x.W, C = x.C;
-    const int tf32 = h->cfg.precision == SDPC_PREC_TF32;
+    const int tf32 = h->alt_fmt();
     void* o = out.ptr;
     const int elem = out.elem, ei = elu_in ? 1 : 0, in_elem = x.elem;
     const size_t lo_off = out.lo_off;
     if (pool_h2()) {
       const unsigned nblk = (unsigned)((size_t)n * (H / kPoolTH) * (W / kPoolTW) * (C / kPoolHCB));
       push([=](cudaStream_t s, const float*, const int64_t*, float*) -> int {
-        if (in_elem == 2) SDPC_CUDA(launch_k(maxpool5_h2_kernel<__nv_bfloat16>, dim3(nblk), dim3(kPoolHThreads), 0, s, (const __nv_bfloat16*)in, x0, (__nv_bfloat16*)o, n, H, W, C, 1, ei));
-        else SDPC_CUDA(launch_k(maxpool5_h2_kernel<float>, dim3(nblk), dim3(kPoolHThreads), 0, s, in, x0, (__nv_bfloat16*)o, n, H, W, C, 1, ei));
+        if (in_elem == 2) SDPC_CUDA(launch_k(maxpool5_h2_kernel<__nv_bfloat16>, dim3(nblk), dim3(kPoolHThreads), 0, s, (const __nv_bfloat16*)in, x0, (__nv_bfloat16*)o, n, H, W, C, 1, ei, tf32));
+        else SDPC_CUDA(launch_k(maxpool5_h2_kernel<float>, dim3(nblk), dim3(kPoolHThreads), 0, s, in, x0, (__nv_bfloat16*)o, n, H, W, C, 1, ei, tf32));
         SDPC_CUDA(cudaGetLastError());
         return SDPC_OK;
       });
@@ -398,7 +405,7 @@ struct Builder {
     e.out_op = out_op ? out_op->ptr : nullptr;
     e.op_pad = out_op ? out_op->pad : 0;
     e.op_elu = op_elu ? 1 : 0;
-    e.op_tf32 = h->cfg.precision == SDPC_PREC_TF32;
+    e.op_tf32 = h->alt_fmt();
     e.op_lo_off = out_op ? out_op->lo_off : 0;
     e.prefetch_residual = getenv("SDPC_NO_PREFETCH") ? 0 : 1;
 #ifdef SDPC_DEV_HOOKS
@@ -560,7 +567,7 @@ struct Builder {
     float* orr = out_raw ? (float*)out_raw->ptr : nullptr;
     const int elem = out_op ? out_op->elem : 4;
     const size_t lo_off = out_op ? out_op->lo_off : 0;
-    const int n = N, H = x.H, W = x.W, C = x.C, tf32 = h->cfg.precision == SDPC_PREC_TF32;
+    const int n = N, H = x.H, W = x.W, C = x.C, tf32 = h->alt_fmt();
     const size_t total = (size_t)n * (H / 2) * (W / 2) * (C / 4);
     if (fuse) {
       float2* sp = (float2*)(base + plan->parts_off + stats_out->off);
@@ -813,7 +820,7 @@ extern "C" int sdpc_score_create(const sdpc_score_config* cfg, sdpc_score_t** ou
   if (!cfg || !out) return set_error(SDPC_ERR_ARG, "score_create: null argument");
   if (cfg->channels != 2) return set_error(SDPC_ERR_UNSUPPORTED, "channels must be 2");
   if (cfg->ngf != 128) return set_error(SDPC_ERR_UNSUPPORTED, "ngf must be 128 (the only LiDAR configuration)");
-  if (cfg->precision < 0 || cfg->precision > 3) return set_error(SDPC_ERR_ARG, "unknown precision %d", cfg->precision);
+  if (cfg->precision < 0 || cfg->precision > SDPC_PREC_FP16) return set_error(SDPC_ERR_ARG, "unknown precision %d", cfg->precision);
   if (cfg->height < 16 || cfg->width < 64 || cfg->width % 64 || cfg->height % 16 || (cfg->width & (cfg->width - 1)))
     return set_error(SDPC_ERR_UNSUPPORTED, "need H %% 16 == 0, W a power of two >= 64 (got %dx%d)", cfg->height, cfg->width);
   if (cfg->num_classes <= 0 || cfg->max_views <= 0) return set_error(SDPC_ERR_ARG, "num_classes/max_views must be positive");
@@ -897,8 +904,8 @@ extern "C" int sdpc_score_finalize(sdpc_score_t* h, void* stream_) {
     } else {
       if (!cw.w_tc) SDPC_CUDA(cudaMalloc(&cw.w_tc, n * sizeof(__nv_bfloat16)));
       if (h->x3() && !cw.w_tc_lo) SDPC_CUDA(cudaMalloc(&cw.w_tc_lo, n * sizeof(__nv_bfloat16)));
-      pack_weight_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>(p.dev, (__nv_bfloat16*)cw.w_tc, nullptr, cw.Cout, cw.Cin, cw.taps, 0,
-                                                                    (__nv_bfloat16*)cw.w_tc_lo);
+      pack_weight_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>(p.dev, (__nv_bfloat16*)cw.w_tc, nullptr, cw.Cout, cw.Cin, cw.taps,
+                                                                    h->alt_fmt(), (__nv_bfloat16*)cw.w_tc_lo);
     }
     SDPC_CUDA(cudaGetLastError());
   }

@@ -57,8 +57,8 @@ def test_config1_single_view_baseline(precision, tol):
 
 
 # bounds at about 2x what a B200 measures (round 2): final sample 2.5e-5 (bf16x3) / 8.9e-3 (bf16) of the oracle's, shared-image
-# pixels that moved to a neighbouring cell 0.17 % / 1.75 %
-@pytest.mark.parametrize("precision,tol,max_flip_frac", [("bf16x3", 1e-4, 0.004), ("bf16", 2e-2, 0.035)])
+# pixels that moved to a neighbouring cell 0.17 % / 1.75 %; fp16 arm: 1.05e-3 and 1.2 %
+@pytest.mark.parametrize("precision,tol,max_flip_frac", [("bf16x3", 1e-4, 0.004), ("fp16", 2.5e-3, 0.025), ("bf16", 2e-2, 0.035)])
 def test_line_sampler_with_real_network(precision, tol, max_flip_frac):
     """a-4 with the real score network on 4 views (A=4), levels spread over the schedule so that both sigmaMod
     branches and the minStepToShare switch are crossed."""

@@ -7,6 +7,7 @@ Tolerances (max abs error / max abs value of the reference tensor), set at about
   fp32  (CUDA-core FMA)            5e-5   measured 2.3e-5 / 2.9e-5
   bf16x3 (tcgen05, hi/lo split)    3e-4   measured 1.5e-4 / 1.7e-4 - the tensor-core arm inside north_star's 1e-3 fp32 bound
   tf32  (tcgen05 kind::tf32)       1.2e-2 measured 6.3e-3 / 7.8e-3 (what cuDNN's default TF32 convs give the reference on a GPU)
+  fp16  (tcgen05 kind::f16, half)  1.5e-2 measured 6.9e-3 / 9.9e-3: the same class as tf32, at the bf16 arm's rate
   bf16  (tcgen05 kind::f16, bf16)  8e-2   measured 6.3e-2 / 5.7e-2, stated separately as north_star asks
 Per-block intermediates (13 taps) have their own bounds, about 2x the largest measured tap error of the arm.
 """
@@ -28,8 +29,8 @@ G = os.path.join(os.path.dirname(__file__), "golden")
 DEV = "cuda:0"
 N = argparse.Namespace
 NORTH_STAR_FP32 = 1e-3                                                     # score within 1e-3 relative in fp32
-TOL = {"fp32": 5e-5, "bf16x3": 3e-4, "tf32": 1.2e-2, "bf16": 8e-2}         # output
-TAP_TOL = {"fp32": 1e-5, "bf16x3": 3e-4, "tf32": 3e-3, "bf16": 2e-2}       # per-block taps (largest measured: 4.9e-6, 1.5e-4, 1.6e-3, 1.1e-2)
+TOL = {"fp32": 5e-5, "bf16x3": 3e-4, "tf32": 1.2e-2, "fp16": 1.5e-2, "bf16": 8e-2}         # output
+TAP_TOL = {"fp32": 1e-5, "bf16x3": 3e-4, "tf32": 3e-3, "fp16": 3e-3, "bf16": 2e-2}       # per-block taps (largest measured: 4.9e-6, 1.5e-4, 1.6e-3, 1.6e-3, 1.1e-2)
 assert TOL["fp32"] <= NORTH_STAR_FP32 and TOL["bf16x3"] <= NORTH_STAR_FP32
 TAPS = ["begin_conv", "res1.0", "res1.1", "res2.0", "res2.1", "res3.0", "res3.1", "res4.0", "res4.1",
         "refine1", "refine2", "refine3", "refine4"]
@@ -56,7 +57,7 @@ def _rel(a, b):
     return float((a - b).abs().max() / b.abs().max())
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16x3", "tf32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3", "tf32", "fp16", "bf16"])
 def test_small_forward_vs_reference_golden(precision):
     g = np.load(os.path.join(G, "scorenet_small.npz"))
     x, y = torch.from_numpy(g["x"]).to(DEV), torch.from_numpy(g["y"]).to(DEV)
@@ -74,7 +75,7 @@ def test_small_forward_vs_reference_golden(precision):
     assert err <= TOL[precision], err
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16x3", "tf32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3", "tf32", "fp16", "bf16"])
 def test_batch_and_reuse_consistency(precision):
     """views are independent (InstanceNorm is per sample): a batched forward equals per-view forwards,
     and buffer reuse across the plan does not leak between runs."""
@@ -90,7 +91,7 @@ def test_batch_and_reuse_consistency(precision):
         assert _rel(single, out[i:i + 1]) <= 1e-6
 
 
-@pytest.mark.parametrize("precision,H,W", [("fp32", 32, 128), ("bf16x3", 64, 1024), ("tf32", 64, 1024), ("bf16", 64, 1024)])
+@pytest.mark.parametrize("precision,H,W", [("fp32", 32, 128), ("bf16x3", 64, 1024), ("tf32", 64, 1024), ("fp16", 64, 1024), ("bf16", 64, 1024)])
 def test_larger_forward_vs_oracle(precision, H, W):
     """full-size input (the 128-wide TMA box and multi-tile scheduling) against the fp32 oracle on the device."""
     torch.backends.cudnn.allow_tf32 = False

@@ -131,3 +131,19 @@ def test_runner_output_files_have_the_reference_names_and_layouts(tmp_path):
     from PIL import Image
     im = Image.open(os.path.join(str(tmp_path), "1_0_Masked_image_grid_897.png"))
     assert im.size == (2 * (Ws + 2) + 2, 3 * (Hs + 2) + 2)                       # make_grid: 6 tiles, 2 per row, 2 px padding
+
+
+def test_get_sigmas_is_bit_equal_to_the_reference_fixture():
+    """row a-7: the package's get_sigmas (the runners' and the network buffer's schedule) against sigmas.npz, recorded from
+    the unmodified reference's get_sigmas (models/__init__.py:5-18) for the 232- and the 10-level geometric schedules"""
+    from sdpc_b200.sigmas import get_sigmas
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "sigmas.npz"))
+    for L in (232, 10):
+        cfg = NS(model=NS(sigma_dist="geometric", sigma_begin=50, sigma_end=0.01, num_classes=L), device="cpu")
+        s = get_sigmas(cfg)
+        assert s.dtype == torch.float32 and np.array_equal(s.numpy(), g[f"geometric_{L}"])
+    cfg = NS(model=NS(sigma_dist="uniform", sigma_begin=1.0, sigma_end=0.01, num_classes=5), device="cpu")
+    assert np.array_equal(get_sigmas(cfg).numpy(), np.linspace(1.0, 0.01, 5).astype(np.float32))
+    import pytest
+    with pytest.raises(NotImplementedError):
+        get_sigmas(NS(model=NS(sigma_dist="other", sigma_begin=1.0, sigma_end=0.01, num_classes=5), device="cpu"))
