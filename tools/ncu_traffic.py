@@ -3,7 +3,7 @@ bench.py's roofline.traffic reads: dram__bytes_read.sum + dram__bytes_write.sum 
 with the digest of the kernel sources the capture was taken of (bench.py drops the figure when the library was built from
 other sources).
 
-    python tools/ncu_traffic.py bf16=gpurun_out/r2_prof_conv_cg2.ncu-rep [bf16x3=...] --source "profiles/r02_ncu_conv.txt"
+    python tools/ncu_traffic.py bf16=gpurun_out/r2_prof_conv_cg2.ncu-rep [bf16x3=...] --source "profiles/r02_ncu_conv.txt" [--out file]
 """
 import csv
 import json
@@ -50,7 +50,8 @@ def main():
                                 tensor_pipe_pct_mean=sum(l["tensor_pipe_pct"] for l in ls) / max(1, len(ls)))
         print(arm, len(ls), "launches, mean dram bytes", rec["arms"][arm]["dram_bytes_per_launch_mean"],
               "tensor pipe %", rec["arms"][arm]["tensor_pipe_pct_mean"])
-    with open(os.path.join(ROOT, "profiles", "conv_traffic.json"), "w") as f:
+    out = sys.argv[sys.argv.index("--out") + 1] if "--out" in sys.argv else os.path.join(ROOT, "profiles", "conv_traffic.json")
+    with open(out, "w") as f:
         json.dump(rec, f, indent=1)
 
 
