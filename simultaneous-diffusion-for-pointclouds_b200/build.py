@@ -52,7 +52,11 @@ def sources():
 def kernel_digest():
     """sha256 over the convolution kernel sources: profiles/conv_traffic.json records it, so bench.py can tell whether
     the committed ncu capture is of the kernels this library was built from."""
-    return _digest([os.path.join(CSRC, f) for f in ("conv_umma.cu", "conv_umma.h", "sm100_prims.cuh")])
+    h = hashlib.sha256()                     # file names + contents, not paths: the capture is taken on another box
+    for f in ("conv_umma.cu", "conv_umma.h", "sm100_prims.cuh", "score_types.cuh"):
+        with open(os.path.join(CSRC, f), "rb") as fh:
+            h.update(f.encode() + b"\0" + fh.read())
+    return h.hexdigest()
 
 
 def build(force=False, verbose=False):
