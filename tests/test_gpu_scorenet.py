@@ -130,7 +130,7 @@ def test_state_dict_roundtrip_and_ema():
 def test_conv_kernel_variants_agree(shape, tmp_path):
     """The shipped convolution path (swapped operands, 2-CTA clusters: CTA pairs on one cta_group::2 MMA for Cout = 256,
     TMA multicast of the weights for Cout = 128) against its own fallbacks, each in a fresh process: multicast clusters
-    without cta_group::2 and single CTAs (what the bf16x3 arm and odd tile counts use) must be bit-identical - same
+    without cta_group::2 and single CTAs (what odd tile counts use) must be bit-identical - same
     tiles, same K order - and the unswapped 128-pixel x 256-channel tiling (statistics summed in another order) stays within the arm's tolerance.  32x128 exercises the two-row half box of the multicast, 64x1024 the half-row one."""
     import subprocess
     import sys
