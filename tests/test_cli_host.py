@@ -170,3 +170,23 @@ def test_runner_flow_with_stand_in_samplers(tmp_path, monkeypatch, name, arms):
         assert a.shape == (2 * n, 3, 16, 64) and float(a.min()) == 0.75 and float(a.max()) == 0.75
     for f in glob.glob(os.path.join(out, "*_Shared_completion_initial897.pth.npy")):
         assert float(np.load(f).max()) == 0.25
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """CPU: `bench.py --impl reference` (the arm the driver times beside the GPU arm) runs the oracle port on one view-step of
+    the B = A = 8 workload and prints ONE JSON line with the contract's keys; a non-zero rank prints nothing."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, check=True).stdout.strip().splitlines()
+    assert len(out) == 1
+    line = json.loads(out[0])
+    assert line["impl"] == "reference" and line["metric"] == "view-steps/sec" and line["steps"] == 1 and line["warmup"] == 0
+    assert line["value"] > 0 and line["higher_is_better"] is True and line["cpu_baseline"]["kind"] == "port"
+    assert line["config"]["group_size"] == 8 and line["e2e"]["h2d_bytes_per_step"] == 0
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2")
+    quiet = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1"],
+                           capture_output=True, text=True, timeout=600, check=True, env=env).stdout.strip()
+    assert quiet == ""
