@@ -74,13 +74,26 @@ class ViewShard:
         stream = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
         cabi.check(run.lib, run.lib.sdpc_shard_pack(ptr(run.workspace), ptr(x[self.lo:self.hi]), ptr(mine), self.per, H, W, stream),
                    "sdpc_shard_pack")
-        dist.all_gather_into_tensor(self._gbuf, mine, group=self.pg)
+        if dist.get_backend(self.pg) == "nccl":
+            dist.all_gather_into_tensor(self._gbuf, mine, group=self.pg)
+        else:
+            # gloo moves CUDA tensors only through broadcast / all-reduce: gather = SUM of slots that are zero everywhere
+            # but at the owner (x + 0 is exact; test-only path, tests/test_gpu_dist.py::test_sharded_two_ranks_on_one_gpu)
+            for r in range(self.world):
+                if r != self.rank:
+                    self._gbuf[r * slot:(r + 1) * slot].zero_()
+            dist.all_reduce(self._gbuf, op=dist.ReduceOp.SUM, group=self.pg)
         cabi.check(run.lib, run.lib.sdpc_shard_unpack(ptr(run.workspace), ptr(x), ptr(self._gbuf), self.world, self.rank,
                                                       self.per, H, W, stream), "sdpc_shard_unpack")
 
     def _all_gather(self, out, mine):
-        if out.is_cuda:
+        if out.is_cuda and dist.get_backend(self.pg) == "nccl":
             dist.all_gather_into_tensor(out, mine, group=self.pg)        # in place: `mine` is out's own block
+        elif out.is_cuda:                                                # gloo with CUDA tensors (one-GPU test): see _exchange_fused
+            mine = mine.clone()
+            out.zero_()
+            out[self.rank * self.per:(self.rank + 1) * self.per] = mine
+            dist.all_reduce(out, op=dist.ReduceOp.SUM, group=self.pg)
         else:                                                            # gloo (CPU tests)
             parts = [torch.empty_like(mine) for _ in range(self.world)]
             dist.all_gather(parts, mine.contiguous(), group=self.pg)
