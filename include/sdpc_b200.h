@@ -135,11 +135,12 @@ typedef struct sdpc_step_params {
   int32_t tgt_count;     /* number of target views, else n_views */
   int32_t scalar_div_recip; /* 1: tensor/python-scalar divisions as x*(1/s) like torch's CUDA kernels (matches the
                                reference on a GPU bit-for-bit); 0: IEEE division like torch's CPU kernels */
-  int32_t key_shift_override; /* test hook: bits of the log-range dropped from the packed (depth | source id) key, which
+  int32_t key_shift_override; /* test hook: bits of the squared range dropped from the packed (range | source id) key, which
                                  makes packed winners wrong so that verification and the fix pass are exercised; 0 = auto */
-  int32_t winner_mode;   /* how the nearest candidate of a z-buffer cell is identified.  The scatter keeps min(log-range)
-                            and min(packed log-range | source id) with two fire-and-forget 64-bit reductions; 0 (production):
-                            the packed winner is verified (its exact log-range recomputed) only where its identity matters -
+  int32_t winner_mode;   /* how the nearest candidate of a z-buffer cell is identified.  The scatter keeps min(r^2) (the exact
+                            squared range: the log-range is a monotone function of it) and min(packed r^2 | source id) with two
+                            fire-and-forget 64-bit reductions; 0 (production): the packed winner is verified (its exact squared
+                            range recomputed) only where its identity matters -
                             cells the controlled average declares "far", or every filled cell when cell-level debug output
                             is requested; 1: every filled cell is verified; 2: every filled cell goes through the exact
                             second traversal (smallest source id at exactly the nearest depth).  A cell whose packed winner
