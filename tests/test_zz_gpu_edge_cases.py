@@ -48,3 +48,48 @@ def test_identity_poses_shift_the_group_mean_down_one_row(shape):
     want = case["x"] + case["coef"] * (-(case["x"] - ni))
     want[:, :, 0] = case["x"][:, :, 0]
     assert torch.allclose(x, want, rtol=0, atol=1e-6)
+
+
+@pytest.mark.parametrize("kind,shape", [("pose", (4, 16, 64)), ("pose", (3, 64, 1024)), ("trans", (4, 16, 64))])
+def test_step_stays_inside_its_buffers(kind, shape):
+    """compute-sanitizer is closed on this pool, so bounds are checked with canaries: the sample, newImages, the gradient of
+    the likelihood and the step workspace live inside larger allocations filled with a pattern; after steps in every
+    winner mode (flagged cells and the fix pass included) every byte outside the declared extents is untouched."""
+    import ctypes as C
+    from sdpc_b200 import cabi
+    from tests.test_gpu_crossview import _runner
+    B, H, W = shape
+    case = cases.small_multiview(kind) if (H, W) == (16, 64) else cases.full_multiview(B=B, A=B)
+    dev = "cuda:0"
+    guard = 4096                                                   # floats / bytes on either side
+    n = case["x"].numel()
+
+    def guarded_f32():
+        buf = torch.full((n + 2 * guard,), 12345.678, device=dev)
+        return buf, buf[guard:guard + n].view(case["x"].shape)
+
+    xb, x = guarded_f32()
+    nb, ni = guarded_f32()
+    gb, gl = guarded_f32()
+    run = _runner(kind, case, debug=False)
+    ws_bytes = run.workspace.numel()
+    wsb = torch.full((ws_bytes + 2 * guard,), 0xA5, dtype=torch.uint8, device=dev)
+    run.workspace = wsb[guard:guard + ws_bytes]
+    assert run.workspace.data_ptr() % 256 == 0
+    cabi.check(run.lib, run.lib.sdpc_step_workspace_init(C.c_void_p(run.workspace.data_ptr()), ws_bytes, case["B"], case["H"],
+                                                         case["W"], run.geo.R, run._stream()), "init")
+    grad = torch.randn(case["x"].shape, device=dev)
+    noise = torch.randn(case["x"].shape, device=dev)
+    for mode, shift in ((0, 0), (1, 0), (2, 0), (0, 50), (1, 50)):
+        x.copy_(case["x"].to(dev))
+        run.winner_mode, run.key_shift_override = mode, shift
+        if kind == "pose":
+            p = run.params(1e-6, 1e-3, 1.0, case["coef"], 1, True, True, 10.0, False)
+        else:
+            p = run.params(1e-6, 1e-3, 1.0, case["coef"], 1, True, True, 10.0, True)
+        run.step(p, run.buffers(x, grad, noise, grad_likelihood=gl, new_images=ni))
+    torch.cuda.synchronize()
+    for name, buf in (("x", xb), ("new_images", nb), ("grad_likelihood", gb)):
+        assert bool((buf[:guard] == 12345.678).all()) and bool((buf[guard + n:] == 12345.678).all()), name
+    assert bool((wsb[:guard] == 0xA5).all()) and bool((wsb[guard + ws_bytes:] == 0xA5).all())
+    assert bool(torch.isfinite(ni).all()) and float(ni.abs().max()) > 0
