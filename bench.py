@@ -475,7 +475,7 @@ def run_b200(args):
         step_kernels = run.kernel_launches(p, run.buffers(x, x, x, new_images=new_images)) + (1 if world > 1 else 0)
         res["gpu_launches"] = ((net.launch_count(x) - 1) + step_kernels) * steps
         # ---- end-to-end: HOST sample buffers through sdpc_langevin_reproject_step_host -----------------------------
-        host = [g["x"].clone().pin_memory(), torch.empty_like(g["x"]).pin_memory()]
+        host = [g["x"].clone().pin_memory()]              # x in / out: a step's result is the next step's input
         ni_host = torch.empty_like(g["x"]).pin_memory()
         xd, gd = torch.empty_like(x), torch.empty_like(x)
         stream = torch.cuda.current_stream(dev)
@@ -496,7 +496,6 @@ def run_b200(args):
                 host[0].copy_(xd, non_blocking=True)
                 ni_host.copy_(new_images, non_blocking=True)
             stream.synchronize()                     # the caller reads the result before the next step
-            host[1].copy_(host[0])                   # (host-side hand-over: the result is the next step's input)
 
         for _ in range(2):
             e2e_step()
