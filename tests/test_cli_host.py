@@ -190,3 +190,45 @@ def test_bench_reference_arm_prints_the_contract_line():
     quiet = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1"],
                            capture_output=True, text=True, timeout=600, check=True, env=env).stdout.strip()
     assert quiet == ""
+
+
+def test_bench_workloads_and_traffic_record():
+    """CPU: the benchmark's input generator (BASELINE configs 2-5) and the ncu traffic record bench.py's roofline reads."""
+    import json
+    import sys
+    import numpy as np
+    import torch
+    from sdpc_b200 import build as b
+    from sdpc_b200.synthetic_data import INPAINTING_MODIFICATIONS, bench_group, lidargen_exist_mask
+    ex = lidargen_exist_mask(64, 1024)
+    assert ex is not None and ex.shape == (64, 1024) and abs(ex.mean() - 0.680) < 5e-4 and int(ex.any(axis=1).sum()) == 57
+    assert lidargen_exist_mask(16, 64) is None
+    for variant in ("line", "inpainting", "densification"):
+        g = bench_group(16, 8, 64, 1024, 1234, variant)
+        g2 = bench_group(16, 8, 64, 1024, 1234, variant)
+        assert all(torch.equal(g[k], g2[k]) for k in g if isinstance(g[k], torch.Tensor))          # reproducible bytes
+        assert g["x"].shape == (16, 2, 64, 1024) and g["mask"].dtype == torch.int32 and g["exist"].shape == (8, 64, 1024)
+        assert torch.equal(g["exist"][0], torch.from_numpy(ex)) and bool(g["sky"].all())
+        if variant == "line":
+            assert g["toWorld"].shape == (16, 1, 4, 4) and g["toWorld"].dtype == torch.float64
+            eye = torch.bmm(g["toWorld"].reshape(16, 4, 4), g["fromWorld"].reshape(16, 4, 4))
+            assert torch.allclose(eye, torch.eye(4, dtype=torch.float64).expand(16, 4, 4), atol=1e-9)
+        else:
+            assert g["mods"].tolist() == INPAINTING_MODIFICATIONS[:8]
+            first, others = g["mask"][0::8, 0].float().mean().item(), g["mask"][1, 0].float().mean().item()
+            assert abs(others - 0.9) < 0.01
+            if variant == "densification":                       # the target keeps rows 0::4 only: 16 of 64 beams
+                assert abs(first - 0.25) < 1e-6 and bool((g["mask"][0, 0, 0::4] == 1).all()) and int(g["mask"][0, 0, 1::4].sum()) == 0
+            else:
+                assert abs(first - 0.6) < 0.01
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    rec = json.load(open(os.path.join(root, "profiles", "conv_traffic.json")))
+    assert set(rec["arms"]) >= {"bf16", "bf16x3", "fp16"} and all(a["n"] >= 4 for a in rec["arms"].values())
+    sys.path.insert(0, root)
+    import bench
+    traffic, src = bench.measured_conv_traffic("bf16")
+    if rec["kernel_source_digest"] == b.kernel_digest():        # the committed capture is of the kernels in this tree
+        assert traffic == rec["arms"]["bf16"]["dram_bytes_per_launch_mean"] and 5e7 < traffic < 1e9
+    else:                                                        # sources moved on: the figure is dropped, never guessed
+        assert traffic is None and "older build" in src
+    assert bench.measured_conv_traffic("fp32")[0] is None
